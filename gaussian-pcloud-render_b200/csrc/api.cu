@@ -1,0 +1,251 @@
+// api.cu -- the C ABI of libgsplat_b200.so (include/gsplat_b200.h) and the host orchestration of one frame.
+//
+// Replaces CudaRasterizer::Rasterizer::{forward,backward,markVisible}
+// (dgr/cuda_rasterizer/rasterizer_impl.cu:141-153,198-434).  Differences in structure, not in results:
+//   * every launch goes to the caller's stream (the reference uses the legacy default stream);
+//   * num_rendered comes from per-block atomics in preprocess, so the one host read-back (kept in gs_forward for
+//     drop-in buffer sizing, rasterizer_impl.cu:281) overlaps with the depth sort that is already queued;
+//     gs_forward_nosync has no host synchronisation at all;
+//   * scan + 64-bit pair sort + range detection are replaced by the depth sort + two tile passes of binning.cu.
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+
+#include "gs_common.cuh"
+
+namespace {
+std::atomic<long long> g_launches{0};
+std::mutex g_err_mu;
+std::string g_err;
+
+struct HostCtx {  // per-thread pinned status slot + event for the num_rendered read-back
+    GsHeader* pinned = nullptr;
+    cudaEvent_t ev = nullptr;
+    int device = -1;
+    bool ensure() {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return false;
+        if (pinned && dev == device) return true;
+        if (!pinned && cudaHostAlloc((void**)&pinned, sizeof(GsHeader), cudaHostAllocDefault) != cudaSuccess) return false;
+        if (ev) cudaEventDestroy(ev);
+        if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) return false;
+        device = dev;
+        return true;
+    }
+};
+thread_local HostCtx t_ctx;
+
+int ceil_log2(unsigned v) {
+    int b = 0;
+    while ((1u << b) < v) b++;
+    return b;
+}
+
+int make_frame(const GsScene* s, void* stream, GsFrame& f, bool forward = true) {
+    if (!s || s->P < 0 || s->width <= 0 || s->height <= 0) return GS_ERR_INVALID;
+    if (s->P > 0) {
+        if (!s->means3D || (forward && !s->opacities) || !s->viewmatrix || !s->projmatrix || !s->campos || !s->background)
+            return GS_ERR_INVALID;
+        if ((s->shs == nullptr) == (s->colors_precomp == nullptr)) return GS_ERR_INVALID;
+        const bool has_sr = s->scales != nullptr && s->rotations != nullptr;
+        if (has_sr == (s->cov3D_precomp != nullptr)) return GS_ERR_INVALID;
+        if (s->shs && s->sh_stride < (s->sh_degree + 1) * (s->sh_degree + 1)) return GS_ERR_INVALID;
+        if (s->sh_degree < 0 || s->sh_degree > 3) return GS_ERR_INVALID;
+    }
+    f.s = *s;
+    f.gx = (s->width + GS_TILE - 1) / GS_TILE;
+    f.gy = (s->height + GS_TILE - 1) / GS_TILE;
+    f.Tn = f.gx * f.gy;
+    f.row0 = 0;
+    f.row1 = f.gy;
+    if (s->tile_row_end > s->tile_row_begin) {
+        f.row0 = s->tile_row_begin < 0 ? 0 : s->tile_row_begin;
+        f.row1 = s->tile_row_end > f.gy ? f.gy : s->tile_row_end;
+        if (f.row1 < f.row0) f.row1 = f.row0;
+    }
+    if (f.gx > 65535 || f.gy > 65535 || f.Tn > 65536) return GS_ERR_UNSUPPORTED;
+    f.tile_bits = ceil_log2((unsigned)f.Tn);
+    f.hi_bits = f.tile_bits > GS_RADIX_BITS ? f.tile_bits - GS_RADIX_BITS : 1;
+    f.idx_bits = 32 - f.hi_bits;
+    if ((unsigned long long)s->P > (1ull << f.idx_bits)) return GS_ERR_UNSUPPORTED;
+    f.focal_y = s->height / (2.0f * s->tan_fovy);  // rasterizer_impl.cu:222-223
+    f.focal_x = s->width / (2.0f * s->tan_fovx);
+    f.stream = (cudaStream_t)stream;
+    return GS_OK;
+}
+
+#define GS_CU(x)                                   \
+    do {                                           \
+        cudaError_t e_ = (x);                      \
+        if (e_ != cudaSuccess) {                   \
+            gs_set_error(#x, e_);                  \
+            return GS_ERR_CUDA;                    \
+        }                                          \
+    } while (0)
+
+// debug mode = the reference's CHECK_CUDA (auxiliary.h:166-173): synchronise + check after every stage
+#define GS_STAGE(x)                                                   \
+    do {                                                              \
+        GS_CU(x);                                                     \
+        if (f.s.debug) GS_CU(cudaStreamSynchronize(f.stream));        \
+    } while (0)
+
+}  // namespace
+
+void gs_note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+void gs_set_error(const char* what, cudaError_t e) {
+    std::lock_guard<std::mutex> lk(g_err_mu);
+    g_err = std::string(what) + ": " + cudaGetErrorString(e);
+}
+
+extern "C" {
+
+int64_t gs_launch_count(void) { return g_launches.load(); }
+const char* gs_last_error(void) {
+    std::lock_guard<std::mutex> lk(g_err_mu);
+    static thread_local std::string copy;
+    copy = g_err;
+    return copy.c_str();
+}
+int32_t gs_abi_version(void) { return GS_ABI_VERSION; }
+
+size_t gs_geometry_bytes(int32_t P) { return GsGeom(nullptr, (size_t)(P < 0 ? 0 : P)).bytes; }
+size_t gs_image_bytes(int32_t width, int32_t height) {
+    const size_t gx = (width + GS_TILE - 1) / GS_TILE, gy = (height + GS_TILE - 1) / GS_TILE;
+    return GsImage(nullptr, (size_t)width * height, gx * gy).bytes;
+}
+size_t gs_binning_bytes(int64_t cap, int32_t P, int32_t, int32_t) {
+    return GsBinning(nullptr, (size_t)(cap < 0 ? 0 : cap), (size_t)(P < 0 ? 0 : P)).bytes;
+}
+
+int64_t gs_forward(const GsScene* scene, GsBuffer geometry, GsBuffer binning, GsBuffer image, float* out_color,
+                   int32_t* radii, void* stream) {
+    GsFrame f;
+    const int rc = make_frame(scene, stream, f);
+    if (rc != GS_OK) return rc;
+    if (!geometry.fn || !binning.fn || !image.fn || !out_color) return GS_ERR_INVALID;
+    if (f.s.P == 0) return 0;  // rasterize_points.cu:81 -- nothing is launched, outputs stay zero-filled
+    if (!t_ctx.ensure()) { gs_set_error("pinned status slot", cudaGetLastError()); return GS_ERR_CUDA; }
+
+    char* gptr = geometry.fn(geometry.user, GsGeom(nullptr, f.s.P).bytes);
+    char* iptr = image.fn(image.user, GsImage(nullptr, (size_t)f.s.width * f.s.height, f.Tn).bytes);
+    if (!gptr || !iptr) return GS_ERR_ALLOC;
+    GsGeom g(gptr, f.s.P);
+    GsImage im(iptr, (size_t)f.s.width * f.s.height, f.Tn);
+
+    GS_CU(cudaMemsetAsync(gptr, 0, g.zero_bytes, f.stream));
+    GS_STAGE(gs_launch_preprocess(f, g, radii));
+    // read num_rendered back while the depth sort (which does not depend on it) is already queued behind it
+    GS_CU(cudaMemcpyAsync(t_ctx.pinned, g.hdr, 16, cudaMemcpyDeviceToHost, f.stream));
+    GS_CU(cudaEventRecord(t_ctx.ev, f.stream));
+    int side = 0;
+    GS_STAGE(gs_launch_depth_sort(f, g, &side));
+    GS_CU(cudaEventSynchronize(t_ctx.ev));
+    const unsigned long long R = t_ctx.pinned->num_rendered;
+    if (t_ctx.pinned->code == GS_ERR_PREFILTERED) return GS_ERR_PREFILTERED;
+    if (R > 0x7fffffffull) return GS_ERR_UNSUPPORTED;
+
+    char* bptr = binning.fn(binning.user, GsBinning(nullptr, (size_t)R, f.s.P).bytes);
+    if (!bptr) return GS_ERR_ALLOC;
+    GsBinning b(bptr, (size_t)R, f.s.P);
+    GS_CU(cudaMemsetAsync(bptr, 0, b.zero_bytes, f.stream));
+    GS_STAGE(gs_launch_tile_binning(f, g, side, b, (size_t)R, im));
+    GS_STAGE(gs_launch_blend_forward(f, g, b, im, out_color));
+    return (int64_t)R;
+}
+
+int32_t gs_forward_nosync(const GsScene* scene, char* geometry, char* binning, int64_t cap, char* image,
+                          float* out_color, int32_t* radii, void* stream) {
+    GsFrame f;
+    const int rc = make_frame(scene, stream, f);
+    if (rc != GS_OK) return rc;
+    if (!geometry || !binning || !image || !out_color || cap < 0) return GS_ERR_INVALID;
+    if (f.s.P == 0) return GS_OK;
+    GsGeom g(geometry, f.s.P);
+    GsImage im(image, (size_t)f.s.width * f.s.height, f.Tn);
+    GsBinning b(binning, (size_t)cap, f.s.P);
+    GS_CU(cudaMemsetAsync(geometry, 0, g.zero_bytes, f.stream));
+    GS_CU(cudaMemsetAsync(binning, 0, b.zero_bytes, f.stream));
+    GS_STAGE(gs_launch_preprocess(f, g, radii));
+    int side = 0;
+    GS_STAGE(gs_launch_depth_sort(f, g, &side));
+    GS_STAGE(gs_launch_tile_binning(f, g, side, b, (size_t)cap, im));
+    GS_STAGE(gs_launch_blend_forward(f, g, b, im, out_color));
+    return GS_OK;
+}
+
+int32_t gs_read_status(const char* geometry, GsStatus* out, void* stream) {
+    if (!geometry || !out) return GS_ERR_INVALID;
+    static_assert(sizeof(GsStatus) == 16, "GsStatus mirrors the first 16 bytes of GsHeader");
+    GS_CU(cudaMemcpyAsync(out, geometry, sizeof(GsStatus), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return GS_OK;
+}
+
+int32_t gs_backward(const GsScene* scene, int64_t num_rendered, const int32_t* radii, const char* geometry,
+                    const char* binning, const char* image, const float* dL_dpix, float* dL_dmean2D,
+                    float* dL_dconic, float* dL_dopacity, float* dL_dcolor, float* dL_dmean3D, float* dL_dcov3D,
+                    float* dL_dsh, float* dL_dscale, float* dL_drot, void* stream) {
+    GsFrame f;
+    const int rc = make_frame(scene, stream, f, false);
+    if (rc != GS_OK) return rc;
+    if (f.s.P == 0) return GS_OK;
+    if (!geometry || !image || !radii || !dL_dpix || !dL_dmean2D || !dL_dconic || !dL_dopacity || !dL_dcolor ||
+        !dL_dmean3D || !dL_dcov3D || num_rendered < 0)
+        return GS_ERR_INVALID;
+    if (f.s.shs && !dL_dsh) return GS_ERR_INVALID;
+    if (f.s.scales && (!dL_dscale || !dL_drot)) return GS_ERR_INVALID;
+    GsGeom g(const_cast<char*>(geometry), f.s.P);
+    GsImage im(const_cast<char*>(image), (size_t)f.s.width * f.s.height, f.Tn);
+    if (num_rendered > 0) {
+        if (!binning) return GS_ERR_INVALID;
+        GsBinning b(const_cast<char*>(binning), (size_t)num_rendered, f.s.P);
+        GS_STAGE(gs_launch_blend_backward(f, g, b, im, dL_dpix, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor));
+    }
+    GS_STAGE(gs_launch_preprocess_backward(f, g, radii, dL_dmean2D, dL_dconic, dL_dcolor, dL_dmean3D, dL_dcov3D, dL_dsh,
+                                          dL_dscale, dL_drot));
+    return GS_OK;
+}
+
+int32_t gs_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, const float* projmatrix,
+                        uint8_t* present, void* stream) {
+    (void)projmatrix;  // the reference's test only uses the view matrix (auxiliary.h:154)
+    if (P < 0 || (P > 0 && (!means3D || !viewmatrix || !present))) return GS_ERR_INVALID;
+    if (P == 0) return GS_OK;
+    GS_CU(gs_launch_mark_visible(P, means3D, viewmatrix, present, (cudaStream_t)stream));
+    return GS_OK;
+}
+
+int64_t gs_fetch(const GsScene* scene, const char* geometry, const char* binning, const char* image,
+                 int64_t num_rendered, const char* name, void* host_dst, int64_t max_bytes, void* stream) {
+    GsFrame f;
+    const int rc = make_frame(scene, stream, f, false);
+    if (rc != GS_OK) return rc;
+    if (!name || !host_dst || !geometry || !image || (num_rendered > 0 && !binning)) return GS_ERR_INVALID;
+    const size_t P = f.s.P, N = (size_t)f.s.width * f.s.height, R = (size_t)num_rendered;
+    GsGeom g(const_cast<char*>(geometry), P);
+    GsImage im(const_cast<char*>(image), N, f.Tn);
+    GsBinning b(const_cast<char*>(binning), R, P);
+    const void* src = nullptr;
+    size_t n = 0;
+    if (!strcmp(name, "records")) { src = g.rec; n = sizeof(GsRec) * P; }
+    else if (!strcmp(name, "sorted_idx")) { src = g.idx[0]; n = 4 * P; }
+    else if (!strcmp(name, "sorted_key")) { src = g.key[0]; n = 4 * P; }
+    else if (!strcmp(name, "cov3D")) { src = g.cov3D; n = 24 * P; }
+    else if (!strcmp(name, "clamped")) { src = g.clamp; n = P; }
+    else if (!strcmp(name, "tiles_touched")) { src = g.ntile; n = 4 * P; }
+    else if (!strcmp(name, "point_list")) { src = b.list; n = 4 * R; }
+    else if (!strcmp(name, "ranges")) { src = im.ranges; n = 8 * (size_t)f.Tn; }
+    else if (!strcmp(name, "n_contrib")) { src = im.n_contrib; n = 4 * N; }
+    else if (!strcmp(name, "final_T")) { src = im.final_T; n = 4 * N; }
+    else return GS_ERR_INVALID;
+    if ((src == nullptr && n) || (int64_t)n > max_bytes) return GS_ERR_INVALID;
+    if (n) {
+        GS_CU(cudaMemcpyAsync(host_dst, src, n, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+        GS_CU(cudaStreamSynchronize((cudaStream_t)stream));
+    }
+    return (int64_t)n;
+}
+
+}  // extern "C"

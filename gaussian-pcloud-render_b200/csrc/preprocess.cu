@@ -1,0 +1,198 @@
+// preprocess.cu -- per-Gaussian forward stage (K1) and markVisible (K10).
+//
+// Replaces dgr/cuda_rasterizer/forward.cu:158-259 (preprocessCUDA) + rasterizer_impl.cu:277 (the InclusiveSum that
+// only served to size the instance buffers) + rasterizer_impl.cu:54-66 (checkFrustum).
+//
+// One thread per Gaussian.  Output is ONE packed 48-B record per visible Gaussian (xy, conic, opacity, alpha
+// cut-off threshold, depth, rgb) that the blend kernels gather with three 16-B loads, plus the depth-sort key,
+// the tile rectangle and the tile count.  The total instance count (num_rendered) and the visible count are
+// reduced per block and added to the frame header with one atomic each, so no device-wide scan is needed.
+// HBM-bound: algorithmic bytes per point = 44 + 12*(D+1)^2 in, 8 out, + 67 per visible point.
+#include "gs_common.cuh"
+#include "gs_math.cuh"
+
+namespace {
+
+struct PreArgs {
+    int P, D, M, W, H, gx, gy, row0, row1;
+    float tanx, tany, fx, fy, mod;
+    int prefiltered;
+    const float* means; const float* scales; const float* rots; const float* opac; const float* shs;
+    const float* cov3D_pre; const float* colors_pre; const float* view; const float* proj; const float* campos;
+    int32_t* radii;
+    GsRec* rec; uint32_t* key; uint32_t* idx; ushort4* rect; uint32_t* ntile; float* cov3D; uint8_t* clamp;
+    GsHeader* hdr;
+};
+
+// SH -> RGB for one Gaussian; coefficient stride is M (may exceed (D+1)^2), SURVEY App. A item 9.
+__device__ __forceinline__ float3 sh_to_rgb(int deg, const float* __restrict__ sh, float3 mean, float3 cam,
+                                            unsigned& clamp_bits) {
+    float3 dir = make_float3(mean.x - cam.x, mean.y - cam.y, mean.z - cam.z);
+    const float len = sqrtf(dir.x * dir.x + dir.y * dir.y + dir.z * dir.z);
+    const float x = dir.x / len, y = dir.y / len, z = dir.z / len;
+    float res[3];
+#pragma unroll
+    for (int ch = 0; ch < 3; ch++) {
+#define SHC(i) sh[(i) * 3 + ch]
+        float r = GS_SH_C0 * SHC(0);
+        if (deg > 0) {
+            r = r - GS_SH_C1 * y * SHC(1) + GS_SH_C1 * z * SHC(2) - GS_SH_C1 * x * SHC(3);
+            if (deg > 1) {
+                const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+                r = r + GS_SH_C2[0] * xy * SHC(4) + GS_SH_C2[1] * yz * SHC(5) +
+                    GS_SH_C2[2] * (2.0f * zz - xx - yy) * SHC(6) + GS_SH_C2[3] * xz * SHC(7) +
+                    GS_SH_C2[4] * (xx - yy) * SHC(8);
+                if (deg > 2) {
+                    r = r + GS_SH_C3[0] * y * (3.0f * xx - yy) * SHC(9) + GS_SH_C3[1] * xy * z * SHC(10) +
+                        GS_SH_C3[2] * y * (4.0f * zz - xx - yy) * SHC(11) +
+                        GS_SH_C3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy) * SHC(12) +
+                        GS_SH_C3[4] * x * (4.0f * zz - xx - yy) * SHC(13) + GS_SH_C3[5] * z * (xx - yy) * SHC(14) +
+                        GS_SH_C3[6] * x * (xx - 3.0f * yy) * SHC(15);
+                }
+            }
+        }
+#undef SHC
+        r += 0.5f;
+        if (r < 0.f) clamp_bits |= 1u << ch;
+        res[ch] = (r < 0.0f) ? 0.0f : r;
+    }
+    return make_float3(res[0], res[1], res[2]);
+}
+
+__global__ void __launch_bounds__(256) preprocess_kernel(const PreArgs a) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned my_tiles = 0, my_vis = 0;
+    bool bad = false;
+    if (i < a.P) {
+        int radius_out = 0;
+        uint32_t key = 0xFFFFFFFFu;  // culled Gaussians sort to the end of the depth order
+        ushort4 rect = make_ushort4(0, 0, 0, 0);
+        do {
+            const float3 mean = make_float3(a.means[3 * i], a.means[3 * i + 1], a.means[3 * i + 2]);
+            const float3 p_view = xform43(a.view, mean);
+            if (p_view.z <= 0.2f) {  // near plane only (auxiliary.h:154)
+                bad = a.prefiltered != 0;
+                break;
+            }
+            const float4 p_hom = xform44(a.proj, mean);
+            const float p_w = 1.0f / (p_hom.w + 0.0000001f);
+            const float projx = p_hom.x * p_w, projy = p_hom.y * p_w;
+
+            float c6[6];
+            if (a.cov3D_pre != nullptr) {
+#pragma unroll
+                for (int k = 0; k < 6; k++) c6[k] = a.cov3D_pre[6 * (size_t)i + k];
+            } else {
+                const float3 sc = make_float3(a.scales[3 * i], a.scales[3 * i + 1], a.scales[3 * i + 2]);
+                const float4 q = reinterpret_cast<const float4*>(a.rots)[i];
+                cov3d_from_scale_rot(sc, a.mod, q, c6);
+#pragma unroll
+                for (int k = 0; k < 6; k++) a.cov3D[6 * (size_t)i + k] = c6[k];
+            }
+            Cov2D k2;
+            cov2d_eval(mean, a.fx, a.fy, a.tanx, a.tany, c6, a.view, k2);
+            const float3 cov = make_float3(k2.a, k2.b, k2.c);
+            const float det = (cov.x * cov.z - cov.y * cov.y);
+            if (det == 0.0f) break;
+            const float det_inv = 1.f / det;
+            const float3 conic = make_float3(cov.z * det_inv, -cov.y * det_inv, cov.x * det_inv);
+            const float mid = 0.5f * (cov.x + cov.z);
+            const float lambda1 = mid + sqrtf(fmaxf(0.1f, mid * mid - det));
+            const float lambda2 = mid - sqrtf(fmaxf(0.1f, mid * mid - det));
+            const float my_radius = ceilf(3.f * sqrtf(fmaxf(lambda1, lambda2)));
+            const float px = ndc_to_pix(projx, a.W), py = ndc_to_pix(projy, a.H);
+            int x0, y0, x1, y1;
+            tile_rect(px, py, (int)my_radius, a.gx, a.gy, x0, y0, x1, y1);
+            if ((x1 - x0) * (y1 - y0) == 0) break;
+
+            float3 rgb = make_float3(0.f, 0.f, 0.f);
+            unsigned clamp_bits = 0;
+            if (a.colors_pre == nullptr) {
+                rgb = sh_to_rgb(a.D, a.shs + (size_t)i * a.M * 3, mean, make_float3(a.campos[0], a.campos[1], a.campos[2]),
+                                clamp_bits);
+                a.clamp[i] = (uint8_t)clamp_bits;
+            } else {
+                rgb = make_float3(a.colors_pre[3 * i], a.colors_pre[3 * i + 1], a.colors_pre[3 * i + 2]);
+            }
+            const float op = a.opac[i];
+            // Conservative cut-off on `power`: below it, op*exp(power) < (1/255)(1 - 1e-3), so the blend kernels
+            // may skip the exponential with no change to the result (alpha < 1/255 is skipped anyway).
+            const float thr = -logf(255.0f * op) - 1.0e-3f;
+            GsRec r;
+            r.a = make_float4(px, py, conic.x, conic.y);
+            r.b = make_float4(conic.z, op, (op > 0.f) ? thr : 0.0f, p_view.z);
+            r.c = make_float4(rgb.x, rgb.y, rgb.z, 0.f);
+            a.rec[i] = r;
+            radius_out = (int)my_radius;
+            // shard clip: this rank only bins tile rows [row0,row1); radii/records stay those of the full frame
+            y0 = max(y0, a.row0);
+            y1 = min(y1, a.row1);
+            if (y1 > y0) {
+                rect = make_ushort4((unsigned short)x0, (unsigned short)y0, (unsigned short)x1, (unsigned short)y1);
+                my_tiles = (unsigned)((y1 - y0) * (x1 - x0));
+            }
+            key = __float_as_uint(p_view.z);
+            my_vis = 1;
+        } while (false);
+        if (a.radii) a.radii[i] = radius_out;
+        a.key[i] = key;
+        a.idx[i] = (uint32_t)i;
+        a.rect[i] = rect;
+        a.ntile[i] = my_tiles;
+    }
+    // block reduction of the instance / visible counts -> two atomics per block
+    __shared__ unsigned s_t[8], s_v[8];
+    unsigned t = my_tiles, v = my_vis;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        t += __shfl_xor_sync(GS_FULL, t, o);
+        v += __shfl_xor_sync(GS_FULL, v, o);
+    }
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { s_t[w] = t; s_v[w] = v; }
+    if (__syncthreads_or(bad)) {
+        if (threadIdx.x == 0) a.hdr->code = GS_ERR_PREFILTERED;
+    }
+    if (threadIdx.x == 0) {
+        unsigned long long tt = 0;
+        unsigned vv = 0;
+        for (int k = 0; k < 8; k++) { tt += s_t[k]; vv += s_v[k]; }
+        if (tt) atomicAdd(&a.hdr->num_rendered, tt);
+        if (vv) atomicAdd(&a.hdr->num_visible, vv);
+    }
+}
+
+__global__ void mark_visible_kernel(int P, const float* __restrict__ means, const float* __restrict__ view,
+                                    uint8_t* __restrict__ present) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    const float3 p = xform43(view, make_float3(means[3 * i], means[3 * i + 1], means[3 * i + 2]));
+    present[i] = p.z > 0.2f;
+}
+
+}  // namespace
+
+cudaError_t gs_launch_preprocess(const GsFrame& f, const GsGeom& g, int32_t* radii) {
+    const GsScene& s = f.s;
+    PreArgs a;
+    a.P = s.P; a.D = s.sh_degree; a.M = s.sh_stride; a.W = s.width; a.H = s.height; a.gx = f.gx; a.gy = f.gy;
+    a.row0 = f.row0; a.row1 = f.row1;
+    a.tanx = s.tan_fovx; a.tany = s.tan_fovy; a.fx = f.focal_x; a.fy = f.focal_y; a.mod = s.scale_modifier;
+    a.prefiltered = s.prefiltered;
+    a.means = s.means3D; a.scales = s.scales; a.rots = s.rotations; a.opac = s.opacities; a.shs = s.shs;
+    a.cov3D_pre = s.cov3D_precomp; a.colors_pre = s.colors_precomp; a.view = s.viewmatrix; a.proj = s.projmatrix;
+    a.campos = s.campos;
+    a.radii = radii;
+    a.rec = g.rec; a.key = g.key[0]; a.idx = g.idx[0]; a.rect = g.rect; a.ntile = g.ntile; a.cov3D = g.cov3D;
+    a.clamp = g.clamp; a.hdr = g.hdr;
+    preprocess_kernel<<<(unsigned)gs_div_up(s.P, 256), 256, 0, f.stream>>>(a);
+    gs_note_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t gs_launch_mark_visible(int P, const float* means3D, const float* view, uint8_t* present,
+                                   cudaStream_t stream) {
+    mark_visible_kernel<<<(unsigned)gs_div_up(P, 256), 256, 0, stream>>>(P, means3D, view, present);
+    gs_note_launch();
+    return cudaGetLastError();
+}

@@ -1,0 +1,230 @@
+"""`_C` -- binding of libgsplat_b200.so (include/gsplat_b200.h) with the call signatures of the reference's pybind
+module (dgr/ext.cpp:15-19, dgr/rasterize_points.h:18-66):
+
+    rasterize_gaussians(bg, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp, viewmatrix,
+                        projmatrix, tan_fovx, tan_fovy, image_height, image_width, sh, degree, campos, prefiltered,
+                        debug) -> (num_rendered, out_color, radii, geomBuffer, binningBuffer, imgBuffer)
+    rasterize_gaussians_backward(bg, means3D, radii, colors, scales, rotations, scale_modifier, cov3D_precomp,
+                        viewmatrix, projmatrix, tan_fovx, tan_fovy, dL_dout_color, sh, degree, campos, geomBuffer, R,
+                        binningBuffer, imageBuffer, debug)
+                     -> (dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations)
+    mark_visible(means3D, viewmatrix, projmatrix) -> bool tensor
+
+PyTorch is only used for device memory and the current stream; the library itself sees raw pointers.  There is NO
+CPU or eager fallback: if the shared library is missing or the tensors are not CUDA tensors this module raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Tuple
+
+import torch
+
+_PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_SO = os.path.join(_PKG, "libgsplat_b200.so")
+
+GS_ERRORS = {-1: "invalid argument", -2: "CUDA error", -3: "buffer allocation failed",
+             -4: "instance capacity exceeded", -5: "unsupported size (more than 65536 tiles or too many Gaussians)",
+             -6: "point culled although `prefiltered` is set"}
+
+
+class GsScene(C.Structure):
+    _fields_ = [("P", C.c_int32), ("sh_degree", C.c_int32), ("sh_stride", C.c_int32), ("width", C.c_int32),
+                ("height", C.c_int32), ("tan_fovx", C.c_float), ("tan_fovy", C.c_float), ("scale_modifier", C.c_float),
+                ("prefiltered", C.c_int32), ("debug", C.c_int32), ("tile_row_begin", C.c_int32),
+                ("tile_row_end", C.c_int32),
+                ("background", C.c_void_p), ("means3D", C.c_void_p), ("shs", C.c_void_p),
+                ("colors_precomp", C.c_void_p), ("opacities", C.c_void_p), ("scales", C.c_void_p),
+                ("rotations", C.c_void_p), ("cov3D_precomp", C.c_void_p), ("viewmatrix", C.c_void_p),
+                ("projmatrix", C.c_void_p), ("campos", C.c_void_p)]
+
+
+RESIZE_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t)
+
+
+class GsBuffer(C.Structure):
+    _fields_ = [("fn", RESIZE_FN), ("user", C.c_void_p)]
+
+
+class GsStatus(C.Structure):
+    _fields_ = [("num_rendered", C.c_int64), ("num_visible", C.c_int32), ("code", C.c_int32)]
+
+
+_lib: Optional[C.CDLL] = None
+
+
+def lib() -> C.CDLL:
+    """Loads libgsplat_b200.so; fails loudly when it has not been built (`__graft_entry__.build()`)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            raise ImportError(f"{_SO} is missing: build it with `make -C {os.path.join(_PKG, 'csrc')}` "
+                              "(there is no CPU fallback)")
+        L = C.CDLL(_SO)
+        L.gs_forward.restype = C.c_int64
+        L.gs_forward.argtypes = [C.POINTER(GsScene), GsBuffer, GsBuffer, GsBuffer, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.gs_forward_nosync.restype = C.c_int32
+        L.gs_forward_nosync.argtypes = [C.POINTER(GsScene), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p]
+        L.gs_read_status.restype = C.c_int32
+        L.gs_read_status.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.gs_backward.restype = C.c_int32
+        L.gs_backward.argtypes = [C.POINTER(GsScene), C.c_int64] + [C.c_void_p] * 15
+        L.gs_mark_visible.restype = C.c_int32
+        L.gs_mark_visible.argtypes = [C.c_int32] + [C.c_void_p] * 5
+        L.gs_fetch.restype = C.c_int64
+        L.gs_fetch.argtypes = [C.POINTER(GsScene), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_char_p,
+                               C.c_void_p, C.c_int64, C.c_void_p]
+        L.gs_geometry_bytes.restype = C.c_size_t
+        L.gs_geometry_bytes.argtypes = [C.c_int32]
+        L.gs_image_bytes.restype = C.c_size_t
+        L.gs_image_bytes.argtypes = [C.c_int32, C.c_int32]
+        L.gs_binning_bytes.restype = C.c_size_t
+        L.gs_binning_bytes.argtypes = [C.c_int64, C.c_int32, C.c_int32, C.c_int32]
+        L.gs_launch_count.restype = C.c_int64
+        L.gs_last_error.restype = C.c_char_p
+        L.gs_abi_version.restype = C.c_int32
+        _lib = L
+    return _lib
+
+
+def _check(rc: int, what: str) -> int:
+    if rc < 0:
+        detail = lib().gs_last_error().decode() if rc == -2 else ""
+        raise RuntimeError(f"{what}: {GS_ERRORS.get(int(rc), rc)} {detail}".strip())
+    return rc
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    """Device pointer of a contiguous fp32 CUDA tensor; an empty tensor (the reference's "not provided") -> NULL."""
+    if t is None or t.numel() == 0:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("diff_gaussian_rasterization (B200): all tensors must be CUDA tensors; no CPU path exists")
+    return t.data_ptr()
+
+
+def _prep(t: Optional[torch.Tensor], dtype=torch.float32) -> Optional[torch.Tensor]:
+    if t is None or t.numel() == 0:
+        return None
+    if t.dtype != dtype:
+        t = t.to(dtype)
+    return t.contiguous()
+
+
+class _Growable:
+    """A uint8 CUDA tensor that the library resizes through a C callback (resizeFunctional, rasterize_points.cu:27-33)."""
+
+    def __init__(self, device):
+        self.t = torch.empty(0, dtype=torch.uint8, device=device)
+
+        def _resize(_user, nbytes):
+            self.t.resize_(int(nbytes))
+            return self.t.data_ptr()
+
+        self._cb = RESIZE_FN(_resize)
+        self.buf = GsBuffer(self._cb, None)
+
+
+def make_scene(*, P, sh_degree, sh_stride, width, height, tan_fovx, tan_fovy, scale_modifier, prefiltered, debug,
+               background, means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, viewmatrix,
+               projmatrix, campos, tile_rows: Optional[Tuple[int, int]] = None) -> GsScene:
+    r0, r1 = tile_rows if tile_rows is not None else (0, 0)
+    return GsScene(P, sh_degree, sh_stride, width, height, tan_fovx, tan_fovy, scale_modifier, int(bool(prefiltered)),
+                   int(bool(debug)), int(r0), int(r1), _ptr(background), _ptr(means3D), _ptr(shs),
+                   _ptr(colors_precomp), _ptr(opacities), _ptr(scales), _ptr(rotations), _ptr(cov3D_precomp),
+                   _ptr(viewmatrix), _ptr(projmatrix), _ptr(campos))
+
+
+def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp,
+                        viewmatrix, projmatrix, tan_fovx, tan_fovy, image_height, image_width, sh, degree, campos,
+                        prefiltered, debug, tile_rows: Optional[Tuple[int, int]] = None, out_color=None):
+    if means3D.dim() != 2 or means3D.size(1) != 3:
+        raise RuntimeError("means3D must have dimensions (num_points, 3)")
+    if not means3D.is_cuda:
+        raise RuntimeError("diff_gaussian_rasterization (B200): means3D must be a CUDA tensor; no CPU path exists")
+    L = lib()
+    dev = means3D.device
+    P, H, W = int(means3D.size(0)), int(image_height), int(image_width)
+    with torch.cuda.device(dev):
+        keep = [_prep(t) for t in (background, means3D, sh, colors, opacity, scales, rotations, cov3D_precomp,
+                                   viewmatrix, projmatrix, campos)]
+        bg_, m3_, sh_, col_, op_, sc_, rot_, cov_, view_, proj_, cam_ = keep
+        M = int(sh.size(1)) if (sh is not None and sh.numel() != 0) else 0
+        if out_color is None:
+            out_color = torch.zeros((3, H, W), dtype=torch.float32, device=dev)
+        radii = torch.zeros((P,), dtype=torch.int32, device=dev)
+        geom, binning, img = _Growable(dev), _Growable(dev), _Growable(dev)
+        rendered = 0
+        if P != 0:
+            scene = make_scene(P=P, sh_degree=int(degree), sh_stride=M, width=W, height=H, tan_fovx=float(tan_fovx),
+                               tan_fovy=float(tan_fovy), scale_modifier=float(scale_modifier), prefiltered=prefiltered,
+                               debug=debug, background=bg_, means3D=m3_, shs=sh_, colors_precomp=col_, opacities=op_,
+                               scales=sc_, rotations=rot_, cov3D_precomp=cov_, viewmatrix=view_, projmatrix=proj_,
+                               campos=cam_, tile_rows=tile_rows)
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            rendered = _check(L.gs_forward(C.byref(scene), geom.buf, binning.buf, img.buf, out_color.data_ptr(),
+                                           radii.data_ptr(), stream), "rasterize_gaussians")
+    return int(rendered), out_color, radii, geom.t, binning.t, img.t
+
+
+def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rotations, scale_modifier, cov3D_precomp,
+                                 viewmatrix, projmatrix, tan_fovx, tan_fovy, dL_dout_color, sh, degree, campos,
+                                 geomBuffer, R, binningBuffer, imageBuffer, debug,
+                                 tile_rows: Optional[Tuple[int, int]] = None):
+    L = lib()
+    dev = means3D.device
+    P = int(means3D.size(0))
+    H, W = int(dL_dout_color.size(1)), int(dL_dout_color.size(2))
+    M = int(sh.size(1)) if (sh is not None and sh.numel() != 0) else 0
+    with torch.cuda.device(dev):
+        z = lambda *s: torch.zeros(s, dtype=torch.float32, device=dev)
+        dL_dmeans3D, dL_dmeans2D, dL_dcolors = z(P, 3), z(P, 3), z(P, 3)
+        dL_dconic, dL_dopacity, dL_dcov3D = z(P, 2, 2), z(P, 1), z(P, 6)
+        dL_dsh, dL_dscales, dL_drotations = z(P, M, 3), z(P, 3), z(P, 4)
+        if P != 0:
+            # note: unlike rasterize_points.cu:169,171 scales/rotations are made contiguous here too
+            keep = [_prep(t) for t in (background, means3D, sh, colors, scales, rotations, cov3D_precomp, viewmatrix,
+                                       projmatrix, campos, dL_dout_color)]
+            bg_, m3_, sh_, col_, sc_, rot_, cov_, view_, proj_, cam_, dpix_ = keep
+            radii_ = _prep(radii, torch.int32)
+            scene = make_scene(P=P, sh_degree=int(degree), sh_stride=M, width=W, height=H, tan_fovx=float(tan_fovx),
+                               tan_fovy=float(tan_fovy), scale_modifier=float(scale_modifier), prefiltered=False,
+                               debug=debug, background=bg_, means3D=m3_, shs=sh_, colors_precomp=col_,
+                               opacities=None, scales=sc_, rotations=rot_, cov3D_precomp=cov_, viewmatrix=view_,
+                               projmatrix=proj_, campos=cam_, tile_rows=tile_rows)
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _check(L.gs_backward(C.byref(scene), int(R), _ptr(radii_), _ptr(geomBuffer), _ptr(binningBuffer),
+                                 _ptr(imageBuffer), _ptr(dpix_), _ptr(dL_dmeans2D), _ptr(dL_dconic), _ptr(dL_dopacity),
+                                 _ptr(dL_dcolors), _ptr(dL_dmeans3D), _ptr(dL_dcov3D), _ptr(dL_dsh), _ptr(dL_dscales),
+                                 _ptr(dL_drotations), stream), "rasterize_gaussians_backward")
+    return dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations
+
+
+def mark_visible(means3D, viewmatrix, projmatrix):
+    if not means3D.is_cuda:
+        raise RuntimeError("diff_gaussian_rasterization (B200): means3D must be a CUDA tensor; no CPU path exists")
+    P = int(means3D.size(0))
+    present = torch.zeros((P,), dtype=torch.bool, device=means3D.device)
+    if P != 0:
+        with torch.cuda.device(means3D.device):
+            m, v, p = _prep(means3D), _prep(viewmatrix), _prep(projmatrix)
+            _check(lib().gs_mark_visible(P, _ptr(m), _ptr(v), _ptr(p), present.data_ptr(),
+                                         torch.cuda.current_stream(means3D.device).cuda_stream), "mark_visible")
+    return present
+
+
+_FETCH_DT = {"records": torch.float32, "sorted_idx": torch.int32, "sorted_key": torch.int32, "cov3D": torch.float32,
+             "clamped": torch.uint8, "tiles_touched": torch.int32, "point_list": torch.int32, "ranges": torch.int32,
+             "n_contrib": torch.int32, "final_T": torch.float32}
+
+
+def fetch(name: str, scene: GsScene, geomBuffer, binningBuffer, imageBuffer, num_rendered: int) -> torch.Tensor:
+    """Debug/test access to the library's internal arrays (host copy)."""
+    cap = max(64, 48 * scene.P, 8 * scene.width * scene.height, 4 * num_rendered)
+    host = torch.empty(cap, dtype=torch.uint8)
+    n = _check(lib().gs_fetch(C.byref(scene), _ptr(geomBuffer), _ptr(binningBuffer), _ptr(imageBuffer),
+                              int(num_rendered), name.encode(), host.data_ptr(), cap,
+                              torch.cuda.current_stream().cuda_stream), f"fetch({name})")
+    return host[:n].view(_FETCH_DT[name]).clone()

@@ -1,0 +1,133 @@
+/*
+ * gsplat_b200.h -- C ABI of the B200-native Gaussian-splat rasterizer (libgsplat_b200.so).
+ *
+ * Drop-in boundary for the hot path of huzi96/gaussian-pcloud-render.  Each entry point replaces one
+ * reference interface (paths relative to the reference repo, dgr/ = diff-gaussian-rasterization/):
+ *
+ *   gs_forward        <- CudaRasterizer::Rasterizer::forward    dgr/cuda_rasterizer/rasterizer.h:34-57
+ *                        (as driven by RasterizeGaussiansCUDA    dgr/rasterize_points.cu:35-115)
+ *   gs_backward       <- CudaRasterizer::Rasterizer::backward   dgr/cuda_rasterizer/rasterizer.h:59-84
+ *                        (RasterizeGaussiansBackwardCUDA          dgr/rasterize_points.cu:117-196)
+ *   gs_mark_visible   <- CudaRasterizer::Rasterizer::markVisible dgr/cuda_rasterizer/rasterizer.h:28-33
+ *                        (markVisible                             dgr/rasterize_points.cu:198-217)
+ *   gs_resize_fn      <- std::function<char*(size_t)> buffer callbacks, rasterizer.h:35-37 /
+ *                        resizeFunctional rasterize_points.cu:27-33
+ *
+ * Plain pointers and sizes only: no torch / C++ types cross this boundary.  All data pointers are DEVICE
+ * pointers on the current CUDA device unless stated otherwise; `stream` is a cudaStream_t passed as void*.
+ * Matrices are 16 floats, column-major (i.e. the transposed row-major tensors the reference's callers pass).
+ * A NULL optional pointer selects the same branch an empty tensor selects in the reference binding.
+ * Errors are returned as negative codes instead of C++ exceptions.
+ */
+#ifndef GSPLAT_B200_H_
+#define GSPLAT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GS_ABI_VERSION 1
+
+enum {
+    GS_OK = 0,
+    GS_ERR_INVALID = -1,      /* bad argument (null required pointer, negative size, ...) */
+    GS_ERR_CUDA = -2,         /* a CUDA call failed; gs_last_error() has the text */
+    GS_ERR_ALLOC = -3,        /* a gs_resize_fn returned NULL */
+    GS_ERR_CAPACITY = -4,     /* preallocated binning buffer too small for num_rendered (no-sync mode) */
+    GS_ERR_UNSUPPORTED = -5,  /* more than 65536 tiles, or P too large for the packed instance format */
+    GS_ERR_PREFILTERED = -6   /* `prefiltered` set but a point failed the near-plane test (reference: __trap) */
+};
+
+/* Scene + view: the arguments shared by forward and backward (rasterizer.h:38-55 / :60-74). */
+typedef struct GsScene {
+    int32_t P;              /* number of Gaussians */
+    int32_t sh_degree;      /* D: active SH degree 0..3 */
+    int32_t sh_stride;      /* M: SH coefficients stored per Gaussian (shs is [P][M][3]); 0 if shs == NULL */
+    int32_t width, height;  /* raster size in pixels */
+    float tan_fovx, tan_fovy;
+    float scale_modifier;
+    int32_t prefiltered;
+    int32_t debug;          /* !=0: synchronise and check for CUDA errors after every stage (auxiliary.h:166-173) */
+    /* Tile-row shard (multi-GPU): only tile rows [tile_row_begin, tile_row_end) are binned and
+     * blended; pixels of other rows are left untouched.  0,0 = the whole frame. */
+    int32_t tile_row_begin, tile_row_end;
+    const float* background;     /* [3] */
+    const float* means3D;        /* [P][3] */
+    const float* shs;            /* [P][M][3] or NULL */
+    const float* colors_precomp; /* [P][3] or NULL (exactly one of shs / colors_precomp) */
+    const float* opacities;      /* [P] */
+    const float* scales;         /* [P][3] or NULL */
+    const float* rotations;      /* [P][4] or NULL (un-normalised quaternions are used as they are) */
+    const float* cov3D_precomp;  /* [P][6] or NULL (exactly one of scales+rotations / cov3D_precomp) */
+    const float* viewmatrix;     /* [16] */
+    const float* projmatrix;     /* [16] */
+    const float* campos;         /* [3] */
+} GsScene;
+
+/* Growable scratch buffer: fn(user, bytes) must return a DEVICE pointer to at least `bytes` bytes that stays
+ * valid until the matching gs_backward call (the reference saves the three buffers on the autograd ctx). */
+typedef char* (*gs_resize_fn)(void* user, size_t bytes);
+typedef struct GsBuffer {
+    gs_resize_fn fn;
+    void* user;
+} GsBuffer;
+
+/* Forward render of one frame.  out_color [3][H][W] and radii [P] (may be NULL) are written by the library;
+ * like the reference binding, the caller zero-fills them first (pixels outside a tile-row shard stay untouched).
+ * One host synchronisation (read-back of num_rendered) happens inside, exactly as in rasterizer_impl.cu:281.
+ * Returns num_rendered (>= 0) or a negative GS_ERR_* code. */
+int64_t gs_forward(const GsScene* scene, GsBuffer geometry, GsBuffer binning, GsBuffer image, float* out_color,
+                   int32_t* radii, void* stream);
+
+/* Sizes for callers that preallocate (no-sync mode and integration tests). */
+size_t gs_geometry_bytes(int32_t P);
+size_t gs_image_bytes(int32_t width, int32_t height);
+size_t gs_binning_bytes(int64_t num_rendered_capacity, int32_t P, int32_t width, int32_t height);
+
+/* Forward without any host synchronisation: all three buffers are preallocated (sizes from the functions
+ * above, binning sized for `num_rendered_capacity`).  The frame's status (num_rendered, error flags) stays on
+ * the device; fetch it with gs_read_status whenever the caller next synchronises.  If num_rendered exceeded the
+ * capacity the frame is NOT rendered (status.code == GS_ERR_CAPACITY) and must be re-issued with a bigger buffer. */
+int32_t gs_forward_nosync(const GsScene* scene, char* geometry, char* binning, int64_t num_rendered_capacity,
+                          char* image, float* out_color, int32_t* radii, void* stream);
+
+typedef struct GsStatus {
+    int64_t num_rendered;
+    int32_t num_visible;
+    int32_t code; /* GS_OK, GS_ERR_CAPACITY or GS_ERR_PREFILTERED */
+} GsStatus;
+/* Asynchronously copies the status block of a geometry buffer into HOST memory `out` (pinned for true async). */
+int32_t gs_read_status(const char* geometry, GsStatus* out, void* stream);
+
+/* Backward.  geometry/binning/image are the buffers filled by the forward call of the same frame, `radii` its
+ * radii output.  All gradient arrays are caller-zeroed device arrays (rasterize_points.cu:151-159):
+ * dL_dmean2D [P][3], dL_dconic [P][2][2], dL_dopacity [P], dL_dcolor [P][3], dL_dmean3D [P][3],
+ * dL_dcov3D [P][6], dL_dsh [P][M][3], dL_dscale [P][3], dL_drot [P][4]; dL_dpix is [3][H][W]. */
+int32_t gs_backward(const GsScene* scene, int64_t num_rendered, const int32_t* radii, const char* geometry,
+                    const char* binning, const char* image, const float* dL_dpix, float* dL_dmean2D,
+                    float* dL_dconic, float* dL_dopacity, float* dL_dcolor, float* dL_dmean3D, float* dL_dcov3D,
+                    float* dL_dsh, float* dL_dscale, float* dL_drot, void* stream);
+
+/* present[i] = 1 if point i passes the reference's frustum test (near plane only, auxiliary.h:154). */
+int32_t gs_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, const float* projmatrix,
+                        uint8_t* present, void* stream);
+
+/* Introspection for tests / profiling: copies a named internal array of the last forward into HOST memory.
+ * names: "records" (P x 12 f32: x y cx cy | cz opacity thr depth | r g b 0), "point_list" (R x u32),
+ * "ranges" (Tn x 2 u32), "n_contrib" (H*W u32), "final_T" (H*W f32), "sorted_idx" (P u32), "cov3D" (P x 6 f32),
+ * "clamped" (P u8, bit c = channel c clamped), "tiles_touched" (P u32).  Returns bytes copied or a negative code. */
+int64_t gs_fetch(const GsScene* scene, const char* geometry, const char* binning, const char* image,
+                 int64_t num_rendered, const char* name, void* host_dst, int64_t max_bytes, void* stream);
+
+/* Number of kernels launched by this library since load (bench.py's "gpu_launches"). */
+int64_t gs_launch_count(void);
+const char* gs_last_error(void);
+int32_t gs_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSPLAT_B200_H_ */
