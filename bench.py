@@ -1,0 +1,449 @@
+#!/usr/bin/env python
+"""bench.py -- frames/s of the Gaussian-splat rasterizer hot path on BASELINE.json's headline configuration
+(THuman-shaped 800K-point cloud, 1920x1080, fov 45, forward; "C2" of BASELINE.md), N GPUs of one node.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference|cpu-port] [--workload C2|C1|C4]
+
+A step = one full forward frame (preprocess -> depth sort -> tile binning -> blend) of one view of a 120-view
+orbit (consecutive steps use consecutive views, so no frame re-uses the previous frame's L2 contents for its
+instance lists; the per-frame input set, 160 MB of Gaussian attributes, exceeds the 126 MB L2).
+  value : frames/s with the cloud resident in HBM (gs_forward_nosync, CUDA events, max over ranks)
+  e2e   : frames/s through the drop-in GaussianRasterizer API with HOST buffers: every step copies the
+          Gaussian attributes + camera from pinned host memory to the device and the rendered image back.
+  roofline     : the blend-forward kernel; algorithmic bytes 40*sum(need_t) + 20*N + 8*Tn,
+                 kernel time from CUDA events recorded inside the library on the launching stream.
+  cpu_baseline : the C/OpenMP oracle port (oracle/gs_oracle.c) on this host's cores, bounded sample.
+N > 1: tile-row sharding of every frame: each rank bins + blends a work-balanced contiguous range
+of tile rows and the ranks exchange their slabs with one grouped all-gather per frame ("scaling": "strong").
+--impl reference runs the UNMODIFIED reference CUDA rasterizer (oracle/_ref/libgs_ref.so, built from
+/root/reference by oracle/Makefile; the reference has no CPU implementation of this path) on the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "gaussian-pcloud-render_b200"))
+
+import scenes  # noqa: E402
+
+WORKLOADS = {
+    "C2": dict(desc="THuman-800K synthetic (799957 pts, sf 448), 1920x1080, fov 45, forward, 120-view orbit",
+               P=799957, W=1920, H=1080, views=120),
+    "C1": dict(desc="THuman-256 synthetic (221712 pts voxelised 1/256, sf 256), 1024x1024 (512^2 x ss2), 12-view orbit",
+               P=221712, W=1024, H=1024, views=12),
+    "C4": dict(desc="5M random Gaussians, SH degree 3, 2048x2048, 8-view orbit", P=5_000_000, W=2048, H=2048, views=8),
+}
+
+
+def make_workload(name):
+    w = WORKLOADS[name]
+    if name == "C2":
+        cloud = scenes.human_cloud(w["P"], scale_factor=448.0, seed=0)
+    elif name == "C1":
+        cloud = scenes.human_cloud(w["P"], scale_factor=256.0, seed=0, voxelize=256)
+    else:
+        cloud = scenes.random_cloud(w["P"], seed=1, sh_degree=3)
+    views = [scenes.make_view(c2w, w["W"], w["H"]) for c2w in scenes.orbit_c2w(w["views"])]
+    return cloud, views, w
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        super().__init__(daemon=True)
+        self.gpu_index = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu_index)], stdout=subprocess.PIPE, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:  # noqa: BLE001
+            pass
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        self.join(timeout=2)
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 9:
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_setup(n):
+    if n <= 1:
+        return 0, 1
+    import torch.distributed as dist
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
+    dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
+    return rank, world
+
+
+def max_over_ranks(x, world, dev):
+    if world <= 1:
+        return x
+    import torch.distributed as dist
+    t = torch.tensor([x], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def barrier(world):
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def algorithmic_blend_bytes(n_contrib_hw: torch.Tensor, W, H):
+    """40*sum_t(need_t) + 20*N + 8*Tn with need_t = max n_contrib over tile t."""
+    gy, gx = (H + 15) // 16, (W + 15) // 16
+    pad = torch.zeros((gy * 16, gx * 16), dtype=n_contrib_hw.dtype, device=n_contrib_hw.device)
+    pad[:H, :W] = n_contrib_hw
+    need = pad.view(gy, 16, gx, 16).amax(dim=(1, 3))
+    return 40 * int(need.sum()) + 20 * W * H + 8 * gx * gy, need
+
+
+def balanced_rows(row_cost: np.ndarray, world: int):
+    """Contiguous tile-row ranges with ~equal summed cost (prefix-sum balancing)."""
+    c = np.cumsum(row_cost.astype(np.float64))
+    total = c[-1] if c[-1] > 0 else 1.0
+    cuts = [0]
+    for k in range(1, world):
+        cuts.append(int(np.searchsorted(c, total * k / world, side="left")) + 1)
+    cuts.append(len(row_cost))
+    cuts = np.maximum.accumulate(np.minimum(cuts, len(row_cost)))
+    return [(int(cuts[k]), int(cuts[k + 1])) for k in range(world)]
+
+
+# ------------------------------------------------------------------------------------------------------------
+def run_b200(args, rank, world):
+    from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer, _C
+    from renderer import FrameRenderer
+    dev = torch.device("cuda", torch.cuda.current_device())
+    cloud, views, w = make_workload(args.workload)
+    W, H = w["W"], w["H"]
+    gy = (H + 15) // 16
+    L = _C.lib()
+    fr = FrameRenderer(cloud, W, H, [1.0, 1.0, 1.0], dev)
+    vdev = [fr.upload_view(v) for v in views]
+    nv = len(vdev)
+
+    # calibration (untimed): instance capacity, per-view blend bytes, and per-view balanced row partitions
+    fr.calibrate(vdev[:: max(1, nv // 12)])
+    blend_bytes, parts, rendered = [], [], []
+    for v in vdev:
+        fr.render(v)
+        nr = fr.status()[0]
+        rendered.append(nr)
+        scene = fr._scene(v, None)
+        ncon = _C.fetch("n_contrib", scene, fr.geom, fr.binning, fr.img, fr.capacity).view(H, W).to(dev)
+        b, need = algorithmic_blend_bytes(ncon, W, H)
+        blend_bytes.append(b)
+        if world > 1:
+            rng = _C.fetch("ranges", scene, fr.geom, fr.binning, fr.img, fr.capacity).view(-1, 2).to(torch.int64)
+            inst = (rng[:, 1] - rng[:, 0]).view(gy, -1)
+            cost = need.to(torch.float64).cpu().numpy().sum(1) + 0.25 * inst.to(torch.float64).numpy().sum(1) + 8.0
+            parts.append(balanced_rows(cost, world))
+    if world > 1:
+        import torch.distributed as dist
+
+    def frame(i, slot):
+        v = vdev[i % nv]
+        if world == 1:
+            fr.enqueue(v, slot=slot)
+        else:
+            rows = parts[i % nv]
+            r0, r1 = rows[rank]
+            if r1 > r0:
+                fr.enqueue(v, tile_rows=(r0, r1), slot=slot)
+            for c in range(3):  # grouped broadcast all-gather straight into the final (3,H,W) image
+                outs = [fr.color[c, min(H, a * 16):min(H, b * 16), :] for (a, b) in rows]
+                dist.all_gather(outs, outs[rank])
+
+    for i in range(args.warmup):
+        frame(i, i)
+    barrier(world)
+    L.gs_profile_enable(1 if world == 1 else 0)
+    clocks = ClockSampler(torch.cuda.current_device())
+    if rank == 0:
+        clocks.start()
+        time.sleep(0.15)
+    launches0 = L.gs_launch_count()
+    stage_ms = np.zeros(4)
+    barrier(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    if world == 1 and args.stage_timing:
+        ms4 = (torch.zeros(4, dtype=torch.float32)).numpy()
+        for i in range(args.steps):
+            frame(args.warmup + i, i)
+            L.gs_profile_read(ms4.ctypes.data)
+            stage_ms += ms4
+    else:
+        for i in range(args.steps):
+            frame(args.warmup + i, i)
+    e1.record()
+    barrier(world)
+    ms = e0.elapsed_time(e1)
+    launches = L.gs_launch_count() - launches0
+    clk = clocks.stop() if rank == 0 else None
+    L.gs_profile_enable(0)
+    for i in range(min(args.steps, fr.SLOTS)):
+        code = fr.status(i)[2]
+        if code != 0 and not (world > 1 and fr.status(i)[0] == 0):
+            raise RuntimeError(f"frame {i} failed with status {code}")
+    ms = max_over_ranks(ms, world, dev)
+    value = args.steps / (ms / 1e3)
+
+    # blend-kernel time: a separate, per-frame-synchronised pass (reading the events needs a sync per frame and
+    # would serialise the main loop), same frames
+    roof = None
+    if world == 1:
+        L.gs_profile_enable(1)
+        ms4 = np.zeros(4, dtype=np.float32)
+        tot = np.zeros(4)
+        bsum = 0
+        nprof = min(args.steps, 2 * nv)
+        for i in range(nprof):
+            fr.enqueue(vdev[(args.warmup + i) % nv])
+            L.gs_profile_read(ms4.ctypes.data)
+            tot += ms4
+            bsum += blend_bytes[(args.warmup + i) % nv]
+        L.gs_profile_enable(0)
+        stage_avg = tot / nprof
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:  # noqa: BLE001
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        ach = (bsum / nprof) / (stage_avg[3] * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": "blend_forward_kernel", "achieved": ach, "peak": peak, "unit": "GB/s",
+                "frac": ach / peak, "traffic": None, "peak_source": "measured" if peaks else "fallback",
+                "kernel_ms": float(stage_avg[3]), "algorithmic_bytes": bsum / nprof,
+                "stage_ms": {"preprocess": float(stage_avg[0]), "depth_sort": float(stage_avg[1]),
+                             "tile_binning": float(stage_avg[2]), "blend_forward": float(stage_avg[3])},
+                "note": "blend is FP32-issue/MUFU bound, not HBM bound (SURVEY.md 8d); HBM figure reported as the metric asks"}
+
+    # ---- e2e: drop-in API, host buffers ----
+    host = {k: cloud[k].contiguous().pin_memory() for k in ("means3D", "opacities", "scales", "rotations", "shs")}
+    hviews = [(torch.from_numpy(v.viewmatrix).pin_memory(), torch.from_numpy(v.projmatrix).pin_memory(),
+               torch.from_numpy(v.campos).pin_memory()) for v in views]
+    bg = torch.ones(3, device=dev)
+    img_host = torch.empty((3, H, W), dtype=torch.float32).pin_memory()
+    h2d = sum(t.numel() * 4 for t in host.values()) + (16 + 16 + 3) * 4
+    d2h = 3 * H * W * 4
+
+    def e2e_frame(i):
+        k = i % nv
+        d = {n: t.to(dev, non_blocking=True) for n, t in host.items()}
+        vm, pm, cp = (t.to(dev, non_blocking=True) for t in hviews[k])
+        rs = GaussianRasterizationSettings(H, W, views[k].tanfovx, views[k].tanfovy, bg, 1.0, vm, pm,
+                                           cloud["sh_degree"], cp, False, False)
+        tr = None if world == 1 else parts[k][rank]
+        if tr is None or tr[1] > tr[0]:
+            color, _ = GaussianRasterizer(rs, tile_rows=tr)(d["means3D"], None, d["opacities"], shs=d["shs"],
+                                                            scales=d["scales"], rotations=d["rotations"])
+        else:
+            color = torch.zeros((3, H, W), device=dev)
+        if world > 1:
+            rows = parts[k]
+            for c in range(3):
+                outs = [color[c, min(H, a * 16):min(H, b * 16), :] for (a, b) in rows]
+                dist.all_gather(outs, outs[rank])
+        if rank == 0:
+            img_host.copy_(color, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+    e2e_steps = max(3, min(args.steps, 40))
+    with torch.no_grad():
+        for i in range(3):
+            e2e_frame(i)
+        barrier(world)
+        e0.record()
+        for i in range(e2e_steps):
+            e2e_frame(3 + i)
+        e1.record()
+        barrier(world)
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1), world, dev)
+    e2e = {"value": e2e_steps / (e2e_ms / 1e3), "unit": "frames/s", "h2d_bytes_per_step": h2d,
+           "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+           "api": "diff_gaussian_rasterization.GaussianRasterizer (drop-in), pinned host inputs -> device -> host image"}
+
+    out = None
+    if rank == 0:
+        cpu = cpu_baseline(cloud, views, w) if (world == 1 and not args.no_cpu_baseline) else None
+        out = {"metric": "frames/sec at 1080p, 800K Gaussians" if args.workload == "C2" else f"frames/sec ({args.workload})",
+               "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+               "dtype": "f32", "data": "synthetic",
+               "config": {"workload": f"{args.workload}: {w['desc']}", "parallelism": "single GPU" if world == 1 else
+                          f"tile-row sharded x{world}, work-balanced rows, grouped all-gather of the image per frame",
+                          "l2_policy": "inputs larger than L2 (160 MB of attributes per frame; consecutive steps render different views)",
+                          "mean_num_rendered": float(np.mean(rendered))},
+               "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu}
+    return out
+
+
+def cpu_baseline(cloud, views, w, max_seconds=20.0):
+    """The oracle port timed on the host cores over a bounded sample of the same workload."""
+    from oracle.oracle import Oracle
+    o = Oracle(32)
+    kw = dict(means3D=cloud["means3D"], opacities=cloud["opacities"], W=w["W"], H=w["H"], bg=np.ones(3, np.float32),
+              sh_degree=cloud["sh_degree"], shs=cloud["shs"], scales=cloud["scales"], rotations=cloud["rotations"])
+
+    def one(v):
+        o.forward(viewmatrix=v.viewmatrix, projmatrix=v.projmatrix, campos=v.campos, tanfovx=v.tanfovx,
+                  tanfovy=v.tanfovy, **kw)
+
+    one(views[0])
+    t0, n = time.time(), 0
+    while n < len(views) and (time.time() - t0) < max_seconds and n < 16:
+        one(views[(n * 7) % len(views)])
+        n += 1
+    dt = time.time() - t0
+    return {"value": n / dt, "unit": "frames/s", "cores": o.threads, "kind": "port",
+            "sample": f"{n} full frames of the same workload (every 7th orbit view), {dt:.1f} s, OpenMP over {o.threads} threads"}
+
+
+def run_reference(args, rank, world):
+    """The UNMODIFIED reference CUDA rasterizer on the same workload (rank 0 only)."""
+    if rank != 0:
+        return None
+    from oracle.oracle import ReferenceCUDA
+    cloud, views, w = make_workload(args.workload)
+    W, H = w["W"], w["H"]
+    if not ReferenceCUDA.available() or not torch.cuda.is_available():
+        return run_cpu_port(args, cloud, views, w, impl="reference",
+                            note="oracle/_ref/libgs_ref.so or GPU missing: the oracle port stands in")
+    dev = torch.device("cuda", torch.cuda.current_device())
+    ref = ReferenceCUDA()
+    d = {k: cloud[k].to(dev) for k in ("means3D", "opacities", "scales", "rotations", "shs")}
+    bg = torch.ones(3, device=dev)
+    vd = [(torch.from_numpy(v.viewmatrix).to(dev), torch.from_numpy(v.projmatrix).to(dev),
+           torch.from_numpy(v.campos).to(dev)) for v in views]
+    nv = len(views)
+
+    def frame(i, dd=d, vv=None):
+        k = i % nv
+        vm, pm, cp = vd[k] if vv is None else vv
+        return ref.forward(means3D=dd["means3D"], opacities=dd["opacities"], W=W, H=H, viewmatrix=vm, projmatrix=pm,
+                           campos=cp, bg=bg, tanfovx=views[k].tanfovx, tanfovy=views[k].tanfovy,
+                           sh_degree=cloud["sh_degree"], shs=dd["shs"], scales=dd["scales"], rotations=dd["rotations"])[0]
+
+    for i in range(args.warmup):
+        frame(i)
+    torch.cuda.synchronize()
+    clocks = ClockSampler(torch.cuda.current_device())
+    clocks.start()
+    time.sleep(0.15)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        frame(args.warmup + i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    clk = clocks.stop()
+    host = {k: cloud[k].contiguous().pin_memory() for k in d}
+    hviews = [tuple(torch.from_numpy(a).pin_memory() for a in (v.viewmatrix, v.projmatrix, v.campos)) for v in views]
+    img_host = torch.empty((3, H, W), dtype=torch.float32).pin_memory()
+
+    def e2e_frame(i):
+        dd = {n: t.to(dev, non_blocking=True) for n, t in host.items()}
+        vv = tuple(t.to(dev, non_blocking=True) for t in hviews[i % nv])
+        color = frame(i, dd, vv)
+        img_host.copy_(color, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    e2e_steps = max(3, min(args.steps, 40))
+    for i in range(3):
+        e2e_frame(i)
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(e2e_steps):
+        e2e_frame(3 + i)
+    e1.record()
+    torch.cuda.synchronize()
+    e2e_ms = e0.elapsed_time(e1)
+    value = args.steps / (ms / 1e3)
+    return {"impl": "reference", "metric": "frames/sec at 1080p, 800K Gaussians" if args.workload == "C2" else f"frames/sec ({args.workload})",
+            "value": value, "unit": "frames/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "device": "cuda:0 (the reference's implementation of this path is CUDA-only)",
+            "config": {"workload": f"{args.workload}: {w['desc']}",
+                       "reference": "unmodified diff-gaussian-rasterization (forward.cu/backward.cu/rasterizer_impl.cu + CUB) compiled for sm_100a, driven through oracle/ref_shim.cu"},
+            "e2e": {"value": e2e_steps / (e2e_ms / 1e3), "unit": "frames/s",
+                    "h2d_bytes_per_step": sum(t.numel() * 4 for t in host.values()) + 35 * 4, "d2h_bytes_per_step": 3 * H * W * 4},
+            "cpu_baseline": {"value": value, "unit": "frames/s", "cores": 1, "kind": "reference",
+                             "sample": f"{args.steps} frames; the reference has no CPU path, so its own CUDA kernels ran on the B200 (host threads: 1)"},
+            "clocks": clk, "gpu_launches": 0}
+
+
+def run_cpu_port(args, cloud=None, views=None, w=None, impl="cpu-port", note=None):
+    if cloud is None:
+        cloud, views, w = make_workload(args.workload)
+    cpu = cpu_baseline(cloud, views, w, max_seconds=60.0)
+    return {"impl": impl, "metric": "frames/sec at 1080p, 800K Gaussians" if args.workload == "C2" else f"frames/sec ({args.workload})",
+            "value": cpu["value"], "unit": "frames/s", "n_gpus": 0, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 / cpu["value"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": {"workload": f"{args.workload}: {w['desc']}", "note": note},
+            "e2e": {"value": cpu["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "cpu_baseline": cpu, "gpu_launches": 0}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=240)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "cpu-port"])
+    ap.add_argument("--workload", default="C2", choices=list(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--stage-timing", action="store_true", help=argparse.SUPPRESS)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank, world = dist_setup(args.gpus)
+    if args.impl == "b200":
+        out = run_b200(args, rank, world)
+    elif args.impl == "reference":
+        out = run_reference(args, rank, world)
+    else:
+        out = run_cpu_port(args) if rank == 0 else None
+    if rank == 0 and out is not None:
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

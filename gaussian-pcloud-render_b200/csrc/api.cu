@@ -37,6 +37,23 @@ struct HostCtx {  // per-thread pinned status slot + event for the num_rendered 
 };
 thread_local HostCtx t_ctx;
 
+// Optional per-stage CUDA-event timing (bench.py's roofline leg): events are recorded on the caller's stream at the
+// stage boundaries of the most recent forward; gs_profile_read synchronises on the last one.
+struct Profiler {
+    bool on = false;
+    bool armed = false;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool ensure() {
+        for (auto& e : ev)
+            if (!e && cudaEventCreate(&e) != cudaSuccess) return false;
+        return true;
+    }
+    void mark(int k, cudaStream_t st) {
+        if (on && ensure()) { cudaEventRecord(ev[k], st); armed = (k == 4) ? true : armed; }
+    }
+};
+thread_local Profiler t_prof;
+
 int ceil_log2(unsigned v) {
     int b = 0;
     while ((1u << b) < v) b++;
@@ -136,12 +153,15 @@ int64_t gs_forward(const GsScene* scene, GsBuffer geometry, GsBuffer binning, Gs
     GsImage im(iptr, (size_t)f.s.width * f.s.height, f.Tn);
 
     GS_CU(cudaMemsetAsync(gptr, 0, g.zero_bytes, f.stream));
+    t_prof.mark(0, f.stream);
     GS_STAGE(gs_launch_preprocess(f, g, radii));
+    t_prof.mark(1, f.stream);
     // read num_rendered back while the depth sort (which does not depend on it) is already queued behind it
     GS_CU(cudaMemcpyAsync(t_ctx.pinned, g.hdr, 16, cudaMemcpyDeviceToHost, f.stream));
     GS_CU(cudaEventRecord(t_ctx.ev, f.stream));
     int side = 0;
     GS_STAGE(gs_launch_depth_sort(f, g, &side));
+    t_prof.mark(2, f.stream);
     GS_CU(cudaEventSynchronize(t_ctx.ev));
     const unsigned long long R = t_ctx.pinned->num_rendered;
     if (t_ctx.pinned->code == GS_ERR_PREFILTERED) return GS_ERR_PREFILTERED;
@@ -152,7 +172,9 @@ int64_t gs_forward(const GsScene* scene, GsBuffer geometry, GsBuffer binning, Gs
     GsBinning b(bptr, (size_t)R, f.s.P);
     GS_CU(cudaMemsetAsync(bptr, 0, b.zero_bytes, f.stream));
     GS_STAGE(gs_launch_tile_binning(f, g, side, b, (size_t)R, im));
+    t_prof.mark(3, f.stream);
     GS_STAGE(gs_launch_blend_forward(f, g, b, im, out_color));
+    t_prof.mark(4, f.stream);
     return (int64_t)R;
 }
 
@@ -168,11 +190,25 @@ int32_t gs_forward_nosync(const GsScene* scene, char* geometry, char* binning, i
     GsBinning b(binning, (size_t)cap, f.s.P);
     GS_CU(cudaMemsetAsync(geometry, 0, g.zero_bytes, f.stream));
     GS_CU(cudaMemsetAsync(binning, 0, b.zero_bytes, f.stream));
+    t_prof.mark(0, f.stream);
     GS_STAGE(gs_launch_preprocess(f, g, radii));
+    t_prof.mark(1, f.stream);
     int side = 0;
     GS_STAGE(gs_launch_depth_sort(f, g, &side));
+    t_prof.mark(2, f.stream);
     GS_STAGE(gs_launch_tile_binning(f, g, side, b, (size_t)cap, im));
+    t_prof.mark(3, f.stream);
     GS_STAGE(gs_launch_blend_forward(f, g, b, im, out_color));
+    t_prof.mark(4, f.stream);
+    return GS_OK;
+}
+
+void gs_profile_enable(int32_t on) { t_prof.on = on != 0; t_prof.armed = false; }
+
+int32_t gs_profile_read(float* ms4) {
+    if (!ms4 || !t_prof.on || !t_prof.armed) return GS_ERR_INVALID;
+    GS_CU(cudaEventSynchronize(t_prof.ev[4]));
+    for (int k = 0; k < 4; k++) GS_CU(cudaEventElapsedTime(&ms4[k], t_prof.ev[k], t_prof.ev[k + 1]));
     return GS_OK;
 }
 

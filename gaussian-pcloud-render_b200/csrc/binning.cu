@@ -346,19 +346,6 @@ __global__ void __launch_bounds__(T2_WARPS * 32) tile_pass2_kernel(const uint32_
     }
 }
 
-// ranges[tile] = [start, end) straight from the scanned pass-2 table (replaces identifyTileRanges + memset).
-__global__ void tile_ranges_kernel(const uint32_t* __restrict__ hist2, uint32_t units2,
-                                   const uint32_t* __restrict__ bucket_unit0, uint2* __restrict__ ranges, int Tn,
-                                   const GsHeader* __restrict__ hdr, unsigned long long Rcap) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= Tn) return;
-    if (hdr->num_rendered > Rcap) { ranges[t] = make_uint2(0, 0); return; }
-    const uint32_t lo = t & (GS_RADIX - 1), hi = (uint32_t)t >> GS_RADIX_BITS;
-    const uint32_t s = hist2[(size_t)hi * units2 + bucket_unit0[lo]];
-    const uint32_t e = hist2[(size_t)hi * units2 + bucket_unit0[lo + 1]];
-    ranges[t] = make_uint2(s, e);
-}
-
 cudaError_t launch_scan(uint32_t* data, size_t n, unsigned long long* state, unsigned int* ticket, uint32_t epoch,
                         cudaStream_t stream) {
     scan_kernel<<<(unsigned)gs_div_up(n, GS_SCAN_TILE), GS_SCAN_THREADS, 0, stream>>>(data, (uint32_t)n, state, ticket,
@@ -418,8 +405,5 @@ cudaError_t gs_launch_tile_binning(const GsFrame& f, const GsGeom& g, int sorted
                                                                     b.bucket_unit0, g.hdr, f.idx_bits, Rcap);
     gs_note_launch();
     GS_TRY(cudaGetLastError());
-    tile_ranges_kernel<<<(unsigned)gs_div_up(f.Tn, 256), 256, 0, f.stream>>>(b.hist2, units2, b.bucket_unit0, im.ranges,
-                                                                            f.Tn, g.hdr, Rcap);
-    gs_note_launch();
-    return cudaGetLastError();
+    return gs_launch_tile_order(f, g, b, Rcap, im);  // ranges + longest-first blend queue (blend_forward.cu)
 }

@@ -16,7 +16,7 @@
 //     list  [R] u32       final per-tile, depth-ordered Gaussian index list ("point_list")
 //     hist1/hist2 + look-back state of the two tile passes, bucket table
 //   image buffer
-//     final_T [N] f32, n_contrib [N] u32, ranges [Tn] uint2
+//     final_T [N] f32, n_contrib [N] u32, ranges [Tn] uint2, order [Tn] u32 (longest-list-first tile queue)
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -30,8 +30,8 @@
 
 struct __align__(16) GsRec {
     float4 a;  // x, y, conic.x, conic.y
-    float4 b;  // conic.z, opacity, alpha-cutoff threshold on `power`, depth
-    float4 c;  // r, g, b, 0
+    float4 b;  // conic.z, opacity, alpha-cutoff threshold on `power`, -conic.y/conic.z
+    float4 c;  // r, g, b, -conic.y/conic.x
 };
 
 struct GsHeader {  // lives at offset 0 of the geometry buffer
@@ -134,12 +134,14 @@ struct GsImage {
     float* final_T;
     uint32_t* n_contrib;
     uint2* ranges;
+    uint32_t* order;  // tiles of the shard, longest instance list first (blend work queue)
     size_t bytes;
     __host__ __device__ GsImage(char* base, size_t N, size_t Tn) {
         GsCarver c(base);
         final_T = c.take<float>(N);
         n_contrib = c.take<uint32_t>(N);
         ranges = c.take<uint2>(Tn);
+        order = c.take<uint32_t>(Tn);
         bytes = c.off + GS_ALIGN;
     }
 };
@@ -162,6 +164,7 @@ cudaError_t gs_launch_preprocess(const GsFrame& f, const GsGeom& g, int32_t* rad
 cudaError_t gs_launch_depth_sort(const GsFrame& f, const GsGeom& g, int* sorted_side);
 cudaError_t gs_launch_tile_binning(const GsFrame& f, const GsGeom& g, int sorted_side, const GsBinning& b,
                                    size_t Rcap, const GsImage& im);
+cudaError_t gs_launch_tile_order(const GsFrame& f, const GsGeom& g, const GsBinning& b, size_t Rcap, const GsImage& im);
 cudaError_t gs_launch_blend_forward(const GsFrame& f, const GsGeom& g, const GsBinning& b, const GsImage& im,
                                     float* out_color);
 cudaError_t gs_launch_blend_backward(const GsFrame& f, const GsGeom& g, const GsBinning& b, const GsImage& im,

@@ -118,10 +118,16 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreArgs a) {
             // Conservative cut-off on `power`: below it, op*exp(power) < (1/255)(1 - 1e-3), so the blend kernels
             // may skip the exponential with no change to the result (alpha < 1/255 is skipped anyway).
             const float thr = -logf(255.0f * op) - 1.0e-3f;
+            // op <= 0: alpha <= 0, always skipped (thr 0 skips every power < 0); NaN opacity: never skip.
+            const float thr_rec = (op > 0.f) ? thr : ((op <= 0.f) ? 0.0f : -INFINITY);
+            // -B/A and -B/C for the blend kernels' box-maximum cull; NaN (= never cull) unless the conic is PD
+            const bool pd = det > 0.f && conic.x > 0.f && conic.z > 0.f;
+            const float nBA = pd ? -conic.y / conic.x : __int_as_float(0x7fc00000);
+            const float nBC = pd ? -conic.y / conic.z : __int_as_float(0x7fc00000);
             GsRec r;
             r.a = make_float4(px, py, conic.x, conic.y);
-            r.b = make_float4(conic.z, op, (op > 0.f) ? thr : 0.0f, p_view.z);
-            r.c = make_float4(rgb.x, rgb.y, rgb.z, 0.f);
+            r.b = make_float4(conic.z, op, thr_rec, nBC);
+            r.c = make_float4(rgb.x, rgb.y, rgb.z, nBA);
             a.rec[i] = r;
             radius_out = (int)my_radius;
             // shard clip: this rank only bins tile rows [row0,row1); radii/records stay those of the full frame

@@ -83,6 +83,10 @@ def lib() -> C.CDLL:
         L.gs_binning_bytes.restype = C.c_size_t
         L.gs_binning_bytes.argtypes = [C.c_int64, C.c_int32, C.c_int32, C.c_int32]
         L.gs_launch_count.restype = C.c_int64
+        L.gs_profile_enable.restype = None
+        L.gs_profile_enable.argtypes = [C.c_int32]
+        L.gs_profile_read.restype = C.c_int32
+        L.gs_profile_read.argtypes = [C.c_void_p]
         L.gs_last_error.restype = C.c_char_p
         L.gs_abi_version.restype = C.c_int32
         _lib = L

@@ -1,0 +1,107 @@
+"""FrameRenderer -- the synchronisation-free forward path over preallocated workspaces (gs_forward_nosync).
+
+The drop-in `GaussianRasterizer` keeps the reference's behaviour of sizing the instance buffers from a host
+read-back of num_rendered (rasterizer_impl.cu:281).  A renderer that draws many frames of one cloud -- what
+PCML_Render.render does per view (simple_raw_render.py:411-522) -- does not need that: this class keeps the three
+workspaces resident, sizes the instance buffers for a capacity with headroom, and only looks at the frame status
+(num_rendered / overflow) when the caller synchronises anyway.  On overflow the frame is re-issued once with a
+larger capacity.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from diff_gaussian_rasterization import _C
+
+
+class FrameRenderer:
+    SLOTS = 1024  # pinned status slots: one per in-flight frame
+
+    def __init__(self, cloud: dict, width: int, height: int, bg, device, capacity: int = 0, headroom: float = 1.3,
+                 tile_rows: Optional[Tuple[int, int]] = None):
+        self.L = _C.lib()
+        self.dev = torch.device(device)
+        self.W, self.H = int(width), int(height)
+        f32 = lambda t: t.to(self.dev, torch.float32).contiguous()
+        self.means3D, self.opacities = f32(cloud["means3D"]), f32(cloud["opacities"])
+        self.scales, self.rotations, self.shs = f32(cloud["scales"]), f32(cloud["rotations"]), f32(cloud["shs"])
+        self.sh_degree = int(cloud["sh_degree"])
+        self.P = int(self.means3D.shape[0])
+        self.bg = torch.as_tensor(bg, dtype=torch.float32).to(self.dev)
+        self.headroom = headroom
+        self.tile_rows = tile_rows
+        with torch.cuda.device(self.dev):
+            self.geom = torch.empty(self.L.gs_geometry_bytes(self.P), dtype=torch.uint8, device=self.dev)
+            self.img = torch.empty(self.L.gs_image_bytes(self.W, self.H), dtype=torch.uint8, device=self.dev)
+            self.radii = torch.zeros(self.P, dtype=torch.int32, device=self.dev)
+            self.color = torch.zeros((3, self.H, self.W), dtype=torch.float32, device=self.dev)
+            self.status_host = torch.zeros((self.SLOTS, 2), dtype=torch.int64).pin_memory()
+        self.capacity = 0
+        self.binning = None
+        self._reserve(max(int(capacity), 1 << 16))
+
+    def _reserve(self, cap: int) -> None:
+        self.capacity = int(cap)
+        with torch.cuda.device(self.dev):
+            self.binning = torch.empty(self.L.gs_binning_bytes(self.capacity, self.P, self.W, self.H),
+                                       dtype=torch.uint8, device=self.dev)
+
+    def _scene(self, view_dev, tile_rows):
+        viewmatrix, projmatrix, campos, tanx, tany = view_dev
+        return _C.make_scene(P=self.P, sh_degree=self.sh_degree, sh_stride=int(self.shs.shape[1]), width=self.W,
+                             height=self.H, tan_fovx=float(tanx), tan_fovy=float(tany), scale_modifier=1.0,
+                             prefiltered=False, debug=False, background=self.bg, means3D=self.means3D, shs=self.shs,
+                             colors_precomp=None, opacities=self.opacities, scales=self.scales,
+                             rotations=self.rotations, cov3D_precomp=None, viewmatrix=viewmatrix,
+                             projmatrix=projmatrix, campos=campos, tile_rows=tile_rows)
+
+    def upload_view(self, view):
+        """host View (scenes.make_view) -> device tensors; done once per camera, outside the frame loop."""
+        t = lambda a: torch.from_numpy(a).to(self.dev).contiguous()
+        return (t(view.viewmatrix), t(view.projmatrix), t(view.campos), view.tanfovx, view.tanfovy)
+
+    def enqueue(self, view_dev, out_color: Optional[torch.Tensor] = None, tile_rows=None, slot: int = 0) -> torch.Tensor:
+        """Queues one frame on the current stream; no host synchronisation.  Returns the (3,H,W) colour tensor."""
+        out = self.color if out_color is None else out_color
+        scene = self._scene(view_dev, tile_rows if tile_rows is not None else self.tile_rows)
+        with torch.cuda.device(self.dev):
+            st = torch.cuda.current_stream(self.dev).cuda_stream
+            _C._check(self.L.gs_forward_nosync(C.byref(scene), self.geom.data_ptr(), self.binning.data_ptr(),
+                                               self.capacity, self.img.data_ptr(), out.data_ptr(),
+                                               self.radii.data_ptr(), st), "gs_forward_nosync")
+            _C._check(self.L.gs_read_status(self.geom.data_ptr(), self.status_host[slot % self.SLOTS].data_ptr(), st),
+                      "gs_read_status")
+        return out
+
+    def status(self, slot: int = 0) -> Tuple[int, int, int]:
+        """(num_rendered, num_visible, code) of the frame enqueued with `slot`; call after synchronising the stream."""
+        nr = int(self.status_host[slot % self.SLOTS, 0])
+        w = int(self.status_host[slot % self.SLOTS, 1])
+        return nr, w & 0xffffffff, C.c_int32((w >> 32) & 0xffffffff).value
+
+    def render(self, view_dev, out_color: Optional[torch.Tensor] = None, tile_rows=None) -> torch.Tensor:
+        """Frame + synchronise + overflow handling (grows the instance buffers and re-renders if needed)."""
+        out = self.enqueue(view_dev, out_color, tile_rows)
+        torch.cuda.current_stream(self.dev).synchronize()
+        nr, _, code = self.status()
+        if code == -4:
+            self._reserve(int(nr * self.headroom) + 1024)
+            out = self.enqueue(view_dev, out_color, tile_rows)
+            torch.cuda.current_stream(self.dev).synchronize()
+            nr, _, code = self.status()
+        if code != 0:
+            raise RuntimeError(f"render failed: {_C.GS_ERRORS.get(code, code)}")
+        return out
+
+    def calibrate(self, views_dev) -> int:
+        """Renders each view once and sizes the instance buffers for the largest num_rendered seen (x headroom)."""
+        worst = 0
+        for v in views_dev:
+            self.render(v)
+            worst = max(worst, self.status()[0])
+        if worst * self.headroom > self.capacity:
+            self._reserve(int(worst * self.headroom) + 1024)
+        return worst

@@ -116,11 +116,16 @@ int32_t gs_mark_visible(int32_t P, const float* means3D, const float* viewmatrix
                         uint8_t* present, void* stream);
 
 /* Introspection for tests / profiling: copies a named internal array of the last forward into HOST memory.
- * names: "records" (P x 12 f32: x y cx cy | cz opacity thr depth | r g b 0), "point_list" (R x u32),
+ * names: "records" (P x 12 f32: x y cx cy | cz opacity thr -cy/cz | r g b -cy/cx), "point_list" (R x u32),
  * "ranges" (Tn x 2 u32), "n_contrib" (H*W u32), "final_T" (H*W f32), "sorted_idx" (P u32), "cov3D" (P x 6 f32),
  * "clamped" (P u8, bit c = channel c clamped), "tiles_touched" (P u32).  Returns bytes copied or a negative code. */
 int64_t gs_fetch(const GsScene* scene, const char* geometry, const char* binning, const char* image,
                  int64_t num_rendered, const char* name, void* host_dst, int64_t max_bytes, void* stream);
+
+/* Per-stage device timing of the most recent forward on this host thread (CUDA events on the caller's stream):
+ * ms4 = {preprocess, depth sort, tile binning, blend forward}.  Off by default; enabling costs 5 event records. */
+void gs_profile_enable(int32_t on);
+int32_t gs_profile_read(float* ms4);
 
 /* Number of kernels launched by this library since load (bench.py's "gpu_launches"). */
 int64_t gs_launch_count(void);
