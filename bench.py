@@ -14,7 +14,7 @@ instance lists; the per-frame input set, 160 MB of Gaussian attributes, exceeds 
                  kernel time from CUDA events recorded inside the library on the launching stream.
   cpu_baseline : the C/OpenMP oracle port (oracle/gs_oracle.c) on this host's cores, bounded sample.
 N > 1: tile-row sharding of every frame: each rank bins + blends a work-balanced contiguous range
-of tile rows and the ranks exchange their slabs with one grouped all-gather per frame ("scaling": "strong").
+of tile rows and the ranks assemble the image with one collective per frame ("scaling": "strong").
 --impl reference runs the UNMODIFIED reference CUDA rasterizer (oracle/_ref/libgs_ref.so, built from
 /root/reference by oracle/Makefile; the reference has no CPU implementation of this path) on the same workload.
 """
@@ -34,6 +34,8 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "gaussian-pcloud-render_b200"))
 
 import scenes  # noqa: E402
+import sharding  # noqa: E402
+from sharding import balanced_rows  # noqa: E402,F401
 
 WORKLOADS = {
     "C2": dict(desc="THuman-800K synthetic (799957 pts, sf 448), 1920x1080, fov 45, forward, 120-view orbit",
@@ -130,18 +132,6 @@ def algorithmic_blend_bytes(n_contrib_hw: torch.Tensor, W, H):
     return 40 * int(need.sum()) + 20 * W * H + 8 * gx * gy, need
 
 
-def balanced_rows(row_cost: np.ndarray, world: int):
-    """Contiguous tile-row ranges with ~equal summed cost (prefix-sum balancing)."""
-    c = np.cumsum(row_cost.astype(np.float64))
-    total = c[-1] if c[-1] > 0 else 1.0
-    cuts = [0]
-    for k in range(1, world):
-        cuts.append(int(np.searchsorted(c, total * k / world, side="left")) + 1)
-    cuts.append(len(row_cost))
-    cuts = np.maximum.accumulate(np.minimum(cuts, len(row_cost)))
-    return [(int(cuts[k]), int(cuts[k + 1])) for k in range(world)]
-
-
 # ------------------------------------------------------------------------------------------------------------
 def run_b200(args, rank, world):
     from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer, _C
@@ -169,8 +159,7 @@ def run_b200(args, rank, world):
         if world > 1:
             rng = _C.fetch("ranges", scene, fr.geom, fr.binning, fr.img, fr.capacity).view(-1, 2).to(torch.int64)
             inst = (rng[:, 1] - rng[:, 0]).view(gy, -1)
-            cost = need.to(torch.float64).cpu().numpy().sum(1) + 0.25 * inst.to(torch.float64).numpy().sum(1) + 8.0
-            parts.append(balanced_rows(cost, world))
+            parts.append(balanced_rows(sharding.row_cost(need.cpu().numpy(), inst.numpy()), world))
     if world > 1:
         import torch.distributed as dist
 
@@ -181,11 +170,10 @@ def run_b200(args, rank, world):
         else:
             rows = parts[i % nv]
             r0, r1 = rows[rank]
+            fr.color.zero_()
             if r1 > r0:
                 fr.enqueue(v, tile_rows=(r0, r1), slot=slot)
-            for c in range(3):  # grouped broadcast all-gather straight into the final (3,H,W) image
-                outs = [fr.color[c, min(H, a * 16):min(H, b * 16), :] for (a, b) in rows]
-                dist.all_gather(outs, outs[rank])
+            sharding.exchange_image(fr.color, rows, rank)
 
     for i in range(args.warmup):
         frame(i, i)
@@ -274,10 +262,7 @@ def run_b200(args, rank, world):
         else:
             color = torch.zeros((3, H, W), device=dev)
         if world > 1:
-            rows = parts[k]
-            for c in range(3):
-                outs = [color[c, min(H, a * 16):min(H, b * 16), :] for (a, b) in rows]
-                dist.all_gather(outs, outs[rank])
+            sharding.exchange_image(color, parts[k], rank)
         if rank == 0:
             img_host.copy_(color, non_blocking=True)
             torch.cuda.current_stream().synchronize()
@@ -305,7 +290,7 @@ def run_b200(args, rank, world):
                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                "dtype": "f32", "data": "synthetic",
                "config": {"workload": f"{args.workload}: {w['desc']}", "parallelism": "single GPU" if world == 1 else
-                          f"tile-row sharded x{world}, work-balanced rows, grouped all-gather of the image per frame",
+                          f"tile-row sharded x{world}, work-balanced rows, one image collective per frame",
                           "l2_policy": "inputs larger than L2 (160 MB of attributes per frame; consecutive steps render different views)",
                           "mean_num_rendered": float(np.mean(rendered))},
                "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu}

@@ -1,0 +1,262 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Everything goes through the drop-in Python API, i.e.
+through the C ABI of libgsplat_b200.so.  Checkers: the golden vectors produced by the unmodified reference CUDA
+library, the CPU oracle, and -- when oracle/_ref/libgs_ref.so travelled with the snapshot -- the live reference."""
+import numpy as np
+import pytest
+import torch
+
+import scenes
+from conftest import GOLDEN_NAMES
+from make_golden import loss_weights
+
+pytestmark = pytest.mark.gpu
+
+PIX_TOL = 1e-4   # north_star: within 1e-4 max abs (fp32)
+GRAD_RTOL = 1e-3
+
+
+def _dev():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    return torch.device("cuda:0")
+
+
+def _settings(kw, dev, debug=False, prefiltered=False, quirk_shapes=True):
+    from diff_gaussian_rasterization import GaussianRasterizationSettings
+    t = lambda a: torch.as_tensor(np.asarray(a, np.float32)).to(dev)
+    vm, pm, cp = t(kw["viewmatrix"]).reshape(4, 4), t(kw["projmatrix"]).reshape(4, 4), t(kw["campos"]).reshape(3)
+    if quirk_shapes:  # the reference's caller passes (1,4,4) matrices and a (1,1,3) campos
+        vm, pm, cp = vm[None], pm[None], cp[None, None]
+    return GaussianRasterizationSettings(kw["H"], kw["W"], kw["tanfovx"], kw["tanfovy"], t(kw["bg"]), 1.0, vm, pm,
+                                         kw["sh_degree"], cp, prefiltered, debug)
+
+
+def _render(kw, dev, requires_grad=False, tile_rows=None, **skw):
+    from diff_gaussian_rasterization import GaussianRasterizer
+    rs = _settings(kw, dev, **skw)
+    leaves = {}
+    for k in ("means3D", "opacities", "shs", "colors_precomp", "scales", "rotations", "cov3D_precomp"):
+        if k in kw and kw[k] is not None:
+            leaves[k] = torch.as_tensor(kw[k]).to(dev).float().clone().requires_grad_(requires_grad)
+    means2D = torch.zeros_like(leaves["means3D"], requires_grad=requires_grad)
+    color, radii = GaussianRasterizer(rs, tile_rows=tile_rows)(
+        leaves["means3D"], means2D, leaves["opacities"], shs=leaves.get("shs"), colors_precomp=leaves.get("colors_precomp"),
+        scales=leaves.get("scales"), rotations=leaves.get("rotations"), cov3D_precomp=leaves.get("cov3D_precomp"))
+    return color, radii, leaves, means2D
+
+
+GRAD_KEYS = {"means3D": "dL_dmeans3D", "opacities": "dL_dopacity", "shs": "dL_dsh", "colors_precomp": "dL_dcolors",
+             "scales": "dL_dscales", "rotations": "dL_drotations", "cov3D_precomp": "dL_dcov3D"}
+
+
+@pytest.mark.parametrize("name", GOLDEN_NAMES)
+def test_forward_matches_reference_golden(name, golden):
+    dev = _dev()
+    _, kw, g = golden[name]
+    color, radii, _, _ = _render(kw, dev)
+    assert np.array_equal(radii.cpu().numpy(), g["radii"])
+    assert np.abs(color.cpu().numpy() - g["color"]).max() <= PIX_TOL
+
+
+@pytest.mark.parametrize("name", GOLDEN_NAMES)
+def test_backward_matches_reference_golden(name, golden):
+    dev = _dev()
+    _, kw, g = golden[name]
+    color, _, leaves, means2D = _render(kw, dev, requires_grad=True)
+    (color * torch.from_numpy(loss_weights(tuple(color.shape))).to(dev)).sum().backward()
+    for k, t in list(leaves.items()) + [("means2D", means2D)]:
+        ref = g["dL_dmeans2D" if k == "means2D" else GRAD_KEYS[k]].reshape(t.grad.shape)
+        err = np.abs(t.grad.cpu().numpy() - ref).max()
+        assert err <= GRAD_RTOL * (np.abs(ref).max() + 1e-12), (k, err)
+
+
+@pytest.mark.parametrize("name", GOLDEN_NAMES)
+def test_matches_cpu_oracle(name, golden, oracle32):
+    dev = _dev()
+    _, kw, _ = golden[name]
+    f = oracle32.forward(**kw)
+    color, radii, leaves, means2D = _render(kw, dev, requires_grad=True)
+    assert np.array_equal(radii.cpu().numpy(), f["radii"])
+    assert np.abs(color.detach().cpu().numpy() - f["color"]).max() <= PIX_TOL
+    w = loss_weights(tuple(color.shape))
+    (color * torch.from_numpy(w).to(dev)).sum().backward()
+    gr = oracle32.backward(f, w, **{k: v for k, v in kw.items() if k != "opacities"})
+    for k, t in leaves.items():
+        ref = gr[GRAD_KEYS[k]].reshape(t.grad.shape)
+        assert np.abs(t.grad.cpu().numpy() - ref).max() <= GRAD_RTOL * (np.abs(ref).max() + 1e-12), k
+
+
+def test_internal_lists_match_golden(golden):
+    """Per-tile lists, their order (stable depth sort, ties by index) and n_contrib equal the reference's."""
+    dev = _dev()
+    from diff_gaussian_rasterization import _C
+    for name in ("tiny_ties", "human_m13"):
+        _, kw, g = golden[name]
+        rs = _settings(kw, dev)
+        t = lambda k: torch.as_tensor(kw[k]).to(dev).float().contiguous()
+        R, color, radii, gb, bb, ib = _C.rasterize_gaussians(
+            rs.bg, t("means3D"), torch.Tensor([]), t("opacities"), t("scales"), t("rotations"), 1.0, torch.Tensor([]),
+            rs.viewmatrix, rs.projmatrix, kw["tanfovx"], kw["tanfovy"], kw["H"], kw["W"], t("shs"), kw["sh_degree"],
+            rs.campos, False, False)
+        assert R == int(g["num_rendered"])
+        keep = [rs.bg.contiguous(), t("means3D"), t("shs"), t("opacities"), t("scales"), t("rotations"),
+                rs.viewmatrix.contiguous(), rs.projmatrix.contiguous(), rs.campos.contiguous()]
+        scene = _C.make_scene(P=keep[1].shape[0], sh_degree=kw["sh_degree"], sh_stride=keep[2].shape[1], width=kw["W"],
+                              height=kw["H"], tan_fovx=kw["tanfovx"], tan_fovy=kw["tanfovy"], scale_modifier=1.0,
+                              prefiltered=False, debug=False, background=keep[0], means3D=keep[1], shs=keep[2],
+                              colors_precomp=None, opacities=keep[3], scales=keep[4], rotations=keep[5],
+                              cov3D_precomp=None, viewmatrix=keep[6], projmatrix=keep[7], campos=keep[8])
+        lst = _C.fetch("point_list", scene, gb, bb, ib, R).numpy().view(np.uint32)
+        rng = _C.fetch("ranges", scene, gb, bb, ib, R).numpy().view(np.uint32).reshape(-1, 2)
+        ncon = _C.fetch("n_contrib", scene, gb, bb, ib, R).numpy().view(np.uint32)
+        assert np.array_equal(lst, g["point_list"])
+        ne = g["ranges"][:, 0] != g["ranges"][:, 1]
+        assert np.array_equal(rng[ne], g["ranges"][ne]) and np.all(rng[~ne, 0] == rng[~ne, 1])
+        assert np.array_equal(ncon, g["n_contrib"])
+
+
+def test_live_reference_library_bit_parity():
+    """Against the unmodified reference kernels on the same GPU (skipped if oracle/_ref did not travel)."""
+    dev = _dev()
+    from oracle.oracle import ReferenceCUDA
+    if not ReferenceCUDA.available():
+        pytest.skip("oracle/_ref/libgs_ref.so not present")
+    cl = scenes.human_cloud(60000, scale_factor=320.0, seed=5, opacity="uniform")
+    v = scenes.make_view(scenes.orbit_c2w(12)[5], 800, 600)
+    kw = dict(means3D=cl["means3D"], opacities=cl["opacities"], W=800, H=600, viewmatrix=v.viewmatrix,
+              projmatrix=v.projmatrix, campos=v.campos, bg=np.array([1, 1, 1], np.float32), tanfovx=v.tanfovx,
+              tanfovy=v.tanfovy, sh_degree=1, shs=cl["shs"], scales=cl["scales"], rotations=cl["rotations"])
+    color, radii, leaves, means2D = _render(kw, dev, requires_grad=True)
+    ref = ReferenceCUDA()
+    tk = {k: (torch.as_tensor(x).to(dev) if not isinstance(x, (int, float)) else x) for k, x in kw.items()}
+    rc, rr, R = ref.forward(**tk)
+    assert torch.equal(radii, rr)
+    assert float((color.detach() - rc).abs().max()) <= 1e-6  # same expression order -> (near) bit-identical
+    w = torch.from_numpy(loss_weights(tuple(color.shape))).to(dev)
+    (color * w).sum().backward()
+    g = ref.backward(w)
+    for k, t in leaves.items():
+        b = g[GRAD_KEYS[k]].reshape(t.grad.shape)
+        assert float((t.grad - b).abs().max()) <= GRAD_RTOL * (float(b.abs().max()) + 1e-12), k
+
+
+def test_edge_cases_empty_and_api_quirks(golden):
+    dev = _dev()
+    from diff_gaussian_rasterization import GaussianRasterizer
+    _, kw, g = golden["tiny_sh3"]
+    # P == 0: zero-filled outputs, nothing launched (rasterize_points.cu:68-69,81)
+    rs = _settings(kw, dev)
+    e = torch.zeros((0, 3), device=dev)
+    color, radii = GaussianRasterizer(rs)(e, e, torch.zeros((0, 1), device=dev), colors_precomp=e, scales=e,
+                                          rotations=torch.zeros((0, 4), device=dev))
+    assert color.shape == (3, kw["H"], kw["W"]) and float(color.abs().max()) == 0.0 and radii.numel() == 0
+    # plain (4,4)/(3,) shapes and debug=True give the same image as the caller's (1,4,4)/(1,1,3) quirk
+    a = _render(kw, dev)[0]
+    b = _render(kw, dev, quirk_shapes=False, debug=True)[0]
+    assert torch.equal(a, b)
+    # stride-0 rotations (Simple_Render passes default_quaternion.expand(P,4)), fwd + bwd
+    kw2 = dict(kw)
+    q = torch.tensor([[1.0, 0, 0, 0]]).expand(len(kw["means3D"]), 4)
+    kw2["rotations"] = q.contiguous()
+    c1, _, l1, _ = _render(kw2, dev, requires_grad=True)
+    rs2 = _settings(kw2, dev)
+    m = torch.as_tensor(kw["means3D"]).to(dev)
+    scl = torch.as_tensor(kw["scales"]).to(dev).requires_grad_(True)
+    c2, _ = GaussianRasterizer(rs2)(m, torch.zeros_like(m), torch.as_tensor(kw["opacities"]).to(dev),
+                                    shs=torch.as_tensor(kw["shs"]).to(dev), scales=scl,
+                                    rotations=torch.tensor([[1.0, 0, 0, 0]], device=dev).expand(m.shape[0], 4))
+    assert torch.equal(c1, c2)
+    c1.sum().backward()
+    c2.sum().backward()
+    assert torch.allclose(l1["scales"].grad, scl.grad, rtol=1e-4, atol=1e-6)
+
+
+def test_prefiltered_violation_raises(golden):
+    dev = _dev()
+    _, kw, g = golden["cull_edges"]
+    assert (g["radii"] == 0).any()
+    with pytest.raises(RuntimeError, match="prefiltered"):
+        _render(kw, dev, prefiltered=True)
+
+
+def test_mark_visible_matches_oracle(golden, oracle32):
+    dev = _dev()
+    from diff_gaussian_rasterization import GaussianRasterizer
+    _, kw, _ = golden["cull_edges"]
+    vis = GaussianRasterizer(_settings(kw, dev)).markVisible(torch.as_tensor(kw["means3D"]).to(dev))
+    assert vis.dtype == torch.bool
+    assert np.array_equal(vis.cpu().numpy(), oracle32.mark_visible(kw["means3D"], kw["viewmatrix"], kw["projmatrix"]))
+
+
+def test_tile_row_shards_reassemble_bitwise(golden):
+    """Sharded rendering (multi-GPU path) == full frame, bit for bit, for arbitrary row partitions."""
+    dev = _dev()
+    _, kw, _ = golden["human_m13"]  # 160x240: 15 tile rows
+    full, radii_full, _, _ = _render(kw, dev)
+    acc = torch.zeros_like(full)
+    for rows in ((0, 4), (4, 5), (5, 5), (5, 11), (11, 15)):
+        if rows[1] > rows[0]:
+            part, radii, _, _ = _render(kw, dev, tile_rows=rows)
+            assert torch.equal(radii, radii_full)
+            y0, y1 = rows[0] * 16, min(kw["H"], rows[1] * 16)
+            assert float(part[:, :y0].abs().max() if y0 else 0) == 0 and float(part[:, y1:].abs().max() if y1 < kw["H"] else 0) == 0
+            acc += part
+    assert torch.equal(acc, full)
+
+
+def test_nosync_path_equals_dropin_and_handles_overflow():
+    dev = _dev()
+    from renderer import FrameRenderer
+    cl = scenes.human_cloud(30000, scale_factor=256.0, seed=2)
+    v = scenes.make_view(scenes.orbit_c2w(12)[1], 640, 480)
+    kw = dict(means3D=cl["means3D"], opacities=cl["opacities"], W=640, H=480, viewmatrix=v.viewmatrix,
+              projmatrix=v.projmatrix, campos=v.campos, bg=np.ones(3, np.float32), tanfovx=v.tanfovx, tanfovy=v.tanfovy,
+              sh_degree=1, shs=cl["shs"], scales=cl["scales"], rotations=cl["rotations"])
+    ref = _render(kw, dev)[0]
+    fr = FrameRenderer(cl, 640, 480, [1, 1, 1], dev, capacity=1 << 16)  # far too small: forces the overflow path
+    out = fr.render(fr.upload_view(v)).clone()
+    assert fr.status()[2] == 0 and fr.capacity > (1 << 16)
+    assert torch.equal(out, ref)
+    for _ in range(3):  # repeatable, bit-identical
+        assert torch.equal(fr.render(fr.upload_view(v)), ref)
+
+
+def test_full_size_properties():
+    """At BASELINE.json's full size (800K points, 1920x1080) check size-independent properties: the depth order is a
+    stable sort, every tile list is a subsequence of it, ranges tile the list exactly, and the image is repeatable."""
+    dev = _dev()
+    from diff_gaussian_rasterization import _C
+    from renderer import FrameRenderer
+    cl = scenes.human_cloud(799957, scale_factor=448.0, seed=0)
+    v = scenes.make_view(scenes.orbit_c2w(120)[9], 1920, 1080)
+    fr = FrameRenderer(cl, 1920, 1080, [1, 1, 1], dev, capacity=16_000_000)
+    vd = fr.upload_view(v)
+    img = fr.render(vd).clone()
+    R = fr.status()[0]
+    assert 0 < R <= fr.capacity and fr.status()[1] == 799957
+    scene = fr._scene(vd, None)
+    key = _C.fetch("sorted_key", scene, fr.geom, fr.binning, fr.img, fr.capacity).to(dev).view(torch.int32).long() & 0xffffffff
+    idx = _C.fetch("sorted_idx", scene, fr.geom, fr.binning, fr.img, fr.capacity).to(dev).long()
+    assert bool((key[1:] >= key[:-1]).all())                                  # sorted by depth bits
+    tie = key[1:] == key[:-1]
+    assert bool((idx[1:][tie] > idx[:-1][tie]).all())                         # ties keep ascending index (stable)
+    assert torch.equal(torch.sort(idx).values, torch.arange(799957, device=dev))
+    rank = torch.empty_like(idx)
+    rank[idx] = torch.arange(idx.numel(), device=dev)
+    lst = _C.fetch("point_list", scene, fr.geom, fr.binning, fr.img, fr.capacity).to(dev).long()[:R]
+    rng = _C.fetch("ranges", scene, fr.geom, fr.binning, fr.img, fr.capacity).to(dev).long().view(-1, 2)
+    ntile = _C.fetch("tiles_touched", scene, fr.geom, fr.binning, fr.img, fr.capacity).to(dev).long()
+    assert int(ntile.sum()) == R
+    lens = rng[:, 1] - rng[:, 0]
+    assert int(lens.sum()) == R and bool((lens >= 0).all())
+    ne = lens > 0
+    starts = rng[ne, 0]
+    assert int(starts.min()) == 0 and bool((torch.sort(starts).values == torch.cat([torch.zeros(1, device=dev, dtype=torch.long), torch.cumsum(lens[ne], 0)[:-1]])).all())
+    r = rank[lst]
+    inc = r[1:] > r[:-1]
+    boundary = torch.zeros(R, dtype=torch.bool, device=dev)
+    boundary[starts] = True                                                   # rank may only drop at a tile start
+    assert bool((inc | boundary[1:]).all())
+    assert torch.equal(torch.bincount(lst, minlength=799957), ntile)          # every Gaussian appears once per tile
+    assert torch.equal(fr.render(vd), img)                                    # repeatable bit for bit
+    assert float(img.min()) >= 0.0 and float(img.max()) <= 1.0 + 1e-5

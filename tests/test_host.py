@@ -1,0 +1,92 @@
+"""CPU tests of the host-side logic: workload generators, settings construction, tile-row partitioning and the
+multi-rank exchange (world_size 2, gloo) used by the tile-sharded path."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import scenes
+from conftest import ROOT
+
+
+def test_settings_follow_reference_conventions():
+    c2w = scenes.orbit_c2w(12)[3]
+    v = scenes.make_view(c2w, 1920, 1080, super_sample=2)
+    assert (v.image_width, v.image_height) == (3840, 2160)
+    w2c = np.linalg.inv(c2w)
+    assert np.allclose(v.viewmatrix, w2c.T, atol=1e-6)                       # transposed = column-major for the kernels
+    P = scenes.projection_matrix(0.01, 100.0, np.pi / 4, np.pi / 4)
+    assert np.allclose(v.projmatrix, (P @ w2c).T, atol=1e-5)                 # full world->clip, transposed
+    assert np.allclose(v.campos, c2w[:3, 3]) and v.tanfovx == pytest.approx(1.0)
+    p = np.array([0.1, -0.2, 0.05, 1.0], np.float32)                         # kernels compute m[0]x+m[4]y+m[8]z+m[12]
+    assert np.allclose(v.viewmatrix.reshape(16)[[2, 6, 10, 14]] @ p, (w2c @ p)[2], atol=1e-6)
+
+
+def test_workload_generators_are_deterministic_and_shaped():
+    a, b = scenes.human_cloud(5000, seed=0), scenes.human_cloud(5000, seed=0)
+    assert all(torch.equal(a[k], b[k]) for k in ("means3D", "scales", "rotations", "shs"))
+    assert a["shs"].shape == (5000, 13, 3) and a["sh_degree"] == 1 and float(a["shs"][:, 1:].abs().max()) == 0.0
+    assert float(a["opacities"].min()) == 1.0 and float(a["scales"].min()) >= 0.0
+    m = a["means3D"]
+    assert float(m[:, 0].abs().max()) <= 0.54 and float(m[:, 1].abs().max()) <= 1.0 and float(m[:, 2].abs().max()) <= 0.24
+    vox = scenes.human_cloud(5000, seed=0, voxelize=64)
+    assert torch.equal(vox["means3D"] * 64, torch.round(vox["means3D"] * 64))
+    c4 = scenes.random_cloud(1000)
+    assert c4["shs"].shape == (1000, 16, 3) and torch.allclose(c4["rotations"].norm(dim=1), torch.ones(1000), atol=1e-5)
+
+
+def test_balanced_rows_partition():
+    import sharding as bench
+    cost = np.zeros(68)
+    cost[10:50] = np.random.default_rng(0).uniform(1, 100, 40)
+    for world in (1, 2, 4, 8):
+        parts = bench.balanced_rows(cost, world)
+        assert parts[0][0] == 0 and parts[-1][1] == 68
+        assert all(parts[k][1] == parts[k + 1][0] for k in range(world - 1))
+        loads = [cost[a:b].sum() for a, b in parts]
+        assert max(loads) <= cost.sum() / world + cost.max() + 1e-9
+    assert bench.balanced_rows(np.zeros(5), 4)[-1][1] == 5
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import sharding
+    H, W = 100, 48  # 7 tile rows, last one partial (100 = 6*16 + 4)
+    gy = (H + 15) // 16
+    cost = np.array([0, 5, 50, 20, 1, 0, 3], float)
+    rows = sharding.balanced_rows(cost, world)        # every rank derives the same partition locally
+    full = torch.arange(3 * H * W, dtype=torch.float32).view(3, H, W)   # what a single GPU would render
+    color = torch.zeros(3, H, W)
+    a, b = sharding.pixel_rows(rows, H)[rank]
+    color[:, a:b, :] = full[:, a:b, :]                 # this rank's shard; everything else stays zero
+    sharding.exchange_image(color, rows, rank)         # the exchange bench.py uses
+    q.put((rank, bool(torch.equal(color, full)), rows, gy))
+    dist.destroy_process_group()
+
+
+def test_tile_row_shard_exchange_world2_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok, _, _ in res)
+    assert res[0][2] == res[1][2]  # identical partitions on both ranks
