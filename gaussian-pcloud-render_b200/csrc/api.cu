@@ -6,7 +6,8 @@
 //   * num_rendered comes from per-block atomics in preprocess, so the one host read-back (kept in gs_forward for
 //     drop-in buffer sizing, rasterizer_impl.cu:281) overlaps with the depth sort that is already queued;
 //     gs_forward_nosync has no host synchronisation at all;
-//   * scan + 64-bit pair sort + range detection are replaced by the depth sort + two tile passes of binning.cu.
+//   * scan + 64-bit pair sort + range detection are replaced by the depth sort, the plan kernel and the row / column
+//     partition passes of binning.cu.
 #include <atomic>
 #include <cstdio>
 #include <cstring>
@@ -54,12 +55,6 @@ struct Profiler {
 };
 thread_local Profiler t_prof;
 
-int ceil_log2(unsigned v) {
-    int b = 0;
-    while ((1u << b) < v) b++;
-    return b;
-}
-
 int make_frame(const GsScene* s, void* stream, GsFrame& f, bool forward = true) {
     if (!s || s->P < 0 || s->width <= 0 || s->height <= 0) return GS_ERR_INVALID;
     if (s->P > 0) {
@@ -82,11 +77,8 @@ int make_frame(const GsScene* s, void* stream, GsFrame& f, bool forward = true) 
         f.row1 = s->tile_row_end > f.gy ? f.gy : s->tile_row_end;
         if (f.row1 < f.row0) f.row1 = f.row0;
     }
-    if (f.gx > 65535 || f.gy > 65535 || f.Tn > 65536) return GS_ERR_UNSUPPORTED;
-    f.tile_bits = ceil_log2((unsigned)f.Tn);
-    f.hi_bits = f.tile_bits > GS_RADIX_BITS ? f.tile_bits - GS_RADIX_BITS : 1;
-    f.idx_bits = 32 - f.hi_bits;
-    if ((unsigned long long)s->P > (1ull << f.idx_bits)) return GS_ERR_UNSUPPORTED;
+    if (f.gx > GS_MAX_GRID || f.gy > GS_MAX_GRID) return GS_ERR_UNSUPPORTED;  // at most 4096 x 4096 pixels
+    if ((unsigned long long)s->P >= (1ull << 30)) return GS_ERR_UNSUPPORTED;  // look-back counters are 30 bits
     f.focal_y = s->height / (2.0f * s->tan_fovy);  // rasterizer_impl.cu:222-223
     f.focal_x = s->width / (2.0f * s->tan_fovx);
     f.stream = (cudaStream_t)stream;
@@ -131,10 +123,13 @@ int32_t gs_abi_version(void) { return GS_ABI_VERSION; }
 size_t gs_geometry_bytes(int32_t P) { return GsGeom(nullptr, (size_t)(P < 0 ? 0 : P)).bytes; }
 size_t gs_image_bytes(int32_t width, int32_t height) {
     const size_t gx = (width + GS_TILE - 1) / GS_TILE, gy = (height + GS_TILE - 1) / GS_TILE;
-    return GsImage(nullptr, (size_t)width * height, gx * gy).bytes;
+    return GsImage(nullptr, (size_t)width * height, gx, gy).bytes;
 }
-size_t gs_binning_bytes(int64_t cap, int32_t P, int32_t, int32_t) {
-    return GsBinning(nullptr, (size_t)(cap < 0 ? 0 : cap), (size_t)(P < 0 ? 0 : P)).bytes;
+// Row items never outnumber instances, and a Gaussian has at most gy of them.
+static size_t row_capacity(size_t cap, size_t P, size_t gy) { return cap < P * gy ? cap : P * gy; }
+size_t gs_binning_bytes(int64_t cap, int32_t P, int32_t, int32_t height) {
+    const size_t c = (size_t)(cap < 0 ? 0 : cap), gy = (size_t)((height + GS_TILE - 1) / GS_TILE);
+    return GsBinning(nullptr, c, row_capacity(c, (size_t)(P < 0 ? 0 : P), gy)).bytes;
 }
 
 int64_t gs_forward(const GsScene* scene, GsBuffer geometry, GsBuffer binning, GsBuffer image, float* out_color,
@@ -146,32 +141,35 @@ int64_t gs_forward(const GsScene* scene, GsBuffer geometry, GsBuffer binning, Gs
     if (f.s.P == 0) return 0;  // rasterize_points.cu:81 -- nothing is launched, outputs stay zero-filled
     if (!t_ctx.ensure()) { gs_set_error("pinned status slot", cudaGetLastError()); return GS_ERR_CUDA; }
 
+    const size_t N = (size_t)f.s.width * f.s.height;
     char* gptr = geometry.fn(geometry.user, GsGeom(nullptr, f.s.P).bytes);
-    char* iptr = image.fn(image.user, GsImage(nullptr, (size_t)f.s.width * f.s.height, f.Tn).bytes);
+    char* iptr = image.fn(image.user, GsImage(nullptr, N, f.gx, f.gy).bytes);
     if (!gptr || !iptr) return GS_ERR_ALLOC;
     GsGeom g(gptr, f.s.P);
-    GsImage im(iptr, (size_t)f.s.width * f.s.height, f.Tn);
+    GsImage im(iptr, N, f.gx, f.gy);
 
     GS_CU(cudaMemsetAsync(gptr, 0, g.zero_bytes, f.stream));
+    GS_CU(cudaMemsetAsync(iptr, 0, im.zero_bytes, f.stream));
     t_prof.mark(0, f.stream);
-    GS_STAGE(gs_launch_preprocess(f, g, radii));
+    GS_STAGE(gs_launch_preprocess(f, g, im, radii));
     t_prof.mark(1, f.stream);
-    // read num_rendered back while the depth sort (which does not depend on it) is already queued behind it
-    GS_CU(cudaMemcpyAsync(t_ctx.pinned, g.hdr, 16, cudaMemcpyDeviceToHost, f.stream));
+    // read the instance / row-item counts back while the depth sort (which does not depend on them) is already
+    // queued behind the copy
+    GS_CU(cudaMemcpyAsync(t_ctx.pinned, g.hdr, 32, cudaMemcpyDeviceToHost, f.stream));
     GS_CU(cudaEventRecord(t_ctx.ev, f.stream));
-    int side = 0;
-    GS_STAGE(gs_launch_depth_sort(f, g, &side));
+    GS_STAGE(gs_launch_depth_sort(f, g));
     t_prof.mark(2, f.stream);
     GS_CU(cudaEventSynchronize(t_ctx.ev));
     const unsigned long long R = t_ctx.pinned->num_rendered;
+    const size_t rows = t_ctx.pinned->num_row_items;
     if (t_ctx.pinned->code == GS_ERR_PREFILTERED) return GS_ERR_PREFILTERED;
-    if (R > 0x7fffffffull) return GS_ERR_UNSUPPORTED;
+    if (R >= (1ull << 30)) return GS_ERR_UNSUPPORTED;
 
-    char* bptr = binning.fn(binning.user, GsBinning(nullptr, (size_t)R, f.s.P).bytes);
+    char* bptr = binning.fn(binning.user, GsBinning(nullptr, (size_t)R, rows).bytes);
     if (!bptr) return GS_ERR_ALLOC;
-    GsBinning b(bptr, (size_t)R, f.s.P);
-    GS_CU(cudaMemsetAsync(bptr, 0, b.zero_bytes, f.stream));
-    GS_STAGE(gs_launch_tile_binning(f, g, side, b, (size_t)R, im));
+    GsBinning b(bptr, (size_t)R, rows);
+    GS_CU(cudaMemsetAsync(bptr + b.zero_off, 0, b.zero_bytes, f.stream));
+    GS_STAGE(gs_launch_tile_lists(f, g, b, (size_t)R, rows, im));
     t_prof.mark(3, f.stream);
     GS_STAGE(gs_launch_blend_forward(f, g, b, im, out_color));
     t_prof.mark(4, f.stream);
@@ -185,18 +183,20 @@ int32_t gs_forward_nosync(const GsScene* scene, char* geometry, char* binning, i
     if (rc != GS_OK) return rc;
     if (!geometry || !binning || !image || !out_color || cap < 0) return GS_ERR_INVALID;
     if (f.s.P == 0) return GS_OK;
+    const size_t N = (size_t)f.s.width * f.s.height;
+    const size_t rowcap = row_capacity((size_t)cap, (size_t)f.s.P, (size_t)f.gy);
     GsGeom g(geometry, f.s.P);
-    GsImage im(image, (size_t)f.s.width * f.s.height, f.Tn);
-    GsBinning b(binning, (size_t)cap, f.s.P);
+    GsImage im(image, N, f.gx, f.gy);
+    GsBinning b(binning, (size_t)cap, rowcap);
     GS_CU(cudaMemsetAsync(geometry, 0, g.zero_bytes, f.stream));
-    GS_CU(cudaMemsetAsync(binning, 0, b.zero_bytes, f.stream));
+    GS_CU(cudaMemsetAsync(image, 0, im.zero_bytes, f.stream));
+    GS_CU(cudaMemsetAsync(binning + b.zero_off, 0, b.zero_bytes, f.stream));
     t_prof.mark(0, f.stream);
-    GS_STAGE(gs_launch_preprocess(f, g, radii));
+    GS_STAGE(gs_launch_preprocess(f, g, im, radii));
     t_prof.mark(1, f.stream);
-    int side = 0;
-    GS_STAGE(gs_launch_depth_sort(f, g, &side));
+    GS_STAGE(gs_launch_depth_sort(f, g));
     t_prof.mark(2, f.stream);
-    GS_STAGE(gs_launch_tile_binning(f, g, side, b, (size_t)cap, im));
+    GS_STAGE(gs_launch_tile_lists(f, g, b, (size_t)cap, rowcap, im));
     t_prof.mark(3, f.stream);
     GS_STAGE(gs_launch_blend_forward(f, g, b, im, out_color));
     t_prof.mark(4, f.stream);
@@ -233,10 +233,10 @@ int32_t gs_backward(const GsScene* scene, int64_t num_rendered, const int32_t* r
     if (f.s.shs && !dL_dsh) return GS_ERR_INVALID;
     if (f.s.scales && (!dL_dscale || !dL_drot)) return GS_ERR_INVALID;
     GsGeom g(const_cast<char*>(geometry), f.s.P);
-    GsImage im(const_cast<char*>(image), (size_t)f.s.width * f.s.height, f.Tn);
+    GsImage im(const_cast<char*>(image), (size_t)f.s.width * f.s.height, f.gx, f.gy);
     if (num_rendered > 0) {
         if (!binning) return GS_ERR_INVALID;
-        GsBinning b(const_cast<char*>(binning), (size_t)num_rendered, f.s.P);
+        GsBinning b(const_cast<char*>(binning), (size_t)num_rendered, 0);  // only `list` (first array) is used
         GS_STAGE(gs_launch_blend_backward(f, g, b, im, dL_dpix, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor));
     }
     GS_STAGE(gs_launch_preprocess_backward(f, g, radii, dL_dmean2D, dL_dconic, dL_dcolor, dL_dmean3D, dL_dcov3D, dL_dsh,
@@ -261,8 +261,8 @@ int64_t gs_fetch(const GsScene* scene, const char* geometry, const char* binning
     if (!name || !host_dst || !geometry || !image || (num_rendered > 0 && !binning)) return GS_ERR_INVALID;
     const size_t P = f.s.P, N = (size_t)f.s.width * f.s.height, R = (size_t)num_rendered;
     GsGeom g(const_cast<char*>(geometry), P);
-    GsImage im(const_cast<char*>(image), N, f.Tn);
-    GsBinning b(const_cast<char*>(binning), R, P);
+    GsImage im(const_cast<char*>(image), N, f.gx, f.gy);
+    GsBinning b(const_cast<char*>(binning), R, 0);
     const void* src = nullptr;
     size_t n = 0;
     if (!strcmp(name, "records")) { src = g.rec; n = sizeof(GsRec) * P; }

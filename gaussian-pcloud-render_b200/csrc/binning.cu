@@ -4,32 +4,31 @@
 //
 // The reference sorts R = sum(tiles touched) 64-bit keys + 32-bit values: ~152 B of HBM traffic per instance
 // (SURVEY 8a row a10).  Here the same final order -- per tile, ascending depth, ties by ascending Gaussian index
-//  -- is produced by
-//   1. a stable LSD radix sort of the P Gaussians by their 32-bit depth key       (P  x 4 passes, 8 B/elem/pass)
-//   2. tile pass 1: walk the Gaussians in depth order, expand each tile rectangle on the fly and scatter the
-//      instances by the LOW 8 bits of the tile id, writing one packed u32 (tile_hi | gaussian) per instance
-//   3. tile pass 2: stable scatter by the HIGH tile bits, writing the final u32 Gaussian-index list; the tile
-//      ranges fall out of the pass-2 prefix table (no key comparison, no memset of ranges)
-// i.e. ~16 B per instance instead of ~172 B, with no 64-bit keys ever materialised.
-//
-// Every radix pass is count -> scan -> scatter.  The unit of work is a WARP: a warp owns a contiguous slice of the
-// input, ranks its elements with __match_any_sync + a private 256-entry shared-memory counter row (stable by
-// construction: rounds are processed in order, lanes in order), and owns one column of the digit-major histogram
-// table.  The scan over the table is a single-pass decoupled look-back scan with ticketed block ids.
+//  -- is produced without ever materialising a key per instance:
+//   1. depth sort: stable LSD radix sort of the P Gaussians by their 32-bit depth key, 8 bits per pass, each pass a
+//      single "onesweep" kernel (rank in shared memory, chained decoupled look-back across CTAs, direct scatter);
+//   2. plan: preprocess accumulated a 2-D difference array of the tile rectangles; one CTA integrates it into the
+//      exact per-tile instance counts, their exclusive scan (= the tile ranges), the per-row item counts and the
+//      longest-list-first tile queue of the blend kernel.  No instance is touched;
+//   3. row pass: walk the Gaussians in depth order and stably partition one item per (Gaussian, tile row) by row;
+//   4. column pass: walk each row's items (still in depth order) and stably partition one entry per
+//      (item, tile column) by column, writing the final u32 Gaussian index straight into the tile's list.
+// Passes 3 and 4 exploit that a Gaussian covers a contiguous RANGE of rows / columns and contributes at most one
+// element per bin: a warp builds, for 32 items at once, the bitmask of covering items for every bin with two
+// shared-memory atomicXor per item and a prefix-xor over the bins; an element's stable rank is a popcount.
+// Both passes are single kernels with chained look-back (row pass: one chain; column pass: one chain per tile row).
+// HBM traffic: ~8 B per row item written + read, 4 B per instance written: ~8 B per instance instead of ~172 B.
 #include "gs_common.cuh"
 
 namespace {
 
-__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
-    return *reinterpret_cast<const volatile unsigned long long*>(p);
+constexpr unsigned ST_AGG = 1u << 30, ST_INC = 2u << 30, ST_VAL = (1u << 30) - 1u;
+
+__device__ __forceinline__ unsigned ld_volatile_u32(const unsigned* p) {
+    return *reinterpret_cast<const volatile unsigned*>(p);
 }
-__device__ __forceinline__ void st_volatile_u64(unsigned long long* p, unsigned long long v) {
-    *reinterpret_cast<volatile unsigned long long*>(p) = v;
-}
-__device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(GS_FULL, v, o);
-    return v;
+__device__ __forceinline__ void st_volatile_u32(unsigned* p, unsigned v) {
+    *reinterpret_cast<volatile unsigned*>(p) = v;
 }
 __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
 #pragma unroll
@@ -40,370 +39,503 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
     return v;
 }
 
-// Stable rank of this lane's element among the elements of the same digit seen so far by this warp.
-// wcount = this warp's 256 counters in shared memory.  All 32 lanes call it.
-__device__ __forceinline__ uint32_t warp_rank(uint32_t digit, bool valid, uint32_t* wcount, int lane) {
-    const unsigned act = __ballot_sync(GS_FULL, valid);
-    uint32_t off = 0;
-    if (valid) {
-        const unsigned m = __match_any_sync(act, digit);
-        const unsigned rank = __popc(m & ((1u << lane) - 1u));
-        const uint32_t base = wcount[digit];
-        __syncwarp(act);
-        if (rank == 0) wcount[digit] = base + __popc(m);
-        off = base + rank;
-    }
-    __syncwarp();
-    return off;
-}
-
-// ---------------------------------------------------------------------------------------------------
-// Single-pass exclusive scan (in place) of data[0..n), total written to data[n].
-// state[] must not contain this pass's flags on entry (zeroed once per frame; flags are epoch-tagged so several
-// scans can reuse one state array within a frame).
-__global__ void __launch_bounds__(GS_SCAN_THREADS) scan_kernel(uint32_t* __restrict__ data, uint32_t n,
-                                                               unsigned long long* __restrict__ state,
-                                                               unsigned int* __restrict__ ticket, uint32_t epoch) {
-    __shared__ uint32_t s_bid, s_warp[GS_SCAN_THREADS / 32], s_prefix;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_bid = atomicAdd(ticket, 1u);
-    __syncthreads();
-    const uint32_t bid = s_bid;
-    const unsigned long long FLAG_AGG = (unsigned long long)(2 * epoch + 1) << 32;
-    const unsigned long long FLAG_INC = (unsigned long long)(2 * epoch + 2) << 32;
-
-    const size_t base = (size_t)bid * GS_SCAN_TILE + (size_t)tid * GS_SCAN_ITEMS;
-    uint32_t v[GS_SCAN_ITEMS];
-    if (base + GS_SCAN_ITEMS <= n) {
-        const uint4 a = *reinterpret_cast<const uint4*>(data + base);
-        const uint4 b = *reinterpret_cast<const uint4*>(data + base + 4);
-        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-    } else {
+// Decoupled look-back for one bin: sums the aggregates of chunks chunk-1, chunk-2, ... >= first until a chunk with
+// an inclusive prefix is met.  Status words carry flag (2 bits) + count (30 bits), so no fence is needed.
+// All chunks of a pass usually run concurrently (a few hundred CTAs), so walks are long: the predecessors are read
+// GS_LB at a time (independent loads in flight) instead of one L2 round trip per step.
+#define GS_LB 16
+__device__ __forceinline__ unsigned look_back(const unsigned* __restrict__ status, int stride, int chunk, int first,
+                                              int bin) {
+    unsigned excl = 0;
+    for (int c = chunk - 1; c >= first; c -= GS_LB) {
+        unsigned s[GS_LB];
 #pragma unroll
-        for (int k = 0; k < GS_SCAN_ITEMS; k++) v[k] = (base + k < n) ? data[base + k] : 0u;
-    }
-    uint32_t tsum = 0;
+        for (int j = 0; j < GS_LB; j++)
+            s[j] = (c - j >= first) ? ld_volatile_u32(status + (size_t)(c - j) * stride + bin) : ST_INC;
 #pragma unroll
-    for (int k = 0; k < GS_SCAN_ITEMS; k++) tsum += v[k];
-    const uint32_t incl = warp_incl_scan(tsum, lane);
-    if (lane == 31) s_warp[warp] = incl;
-    __syncthreads();
-    uint32_t wpre = 0, btotal = 0;
-#pragma unroll
-    for (int k = 0; k < GS_SCAN_THREADS / 32; k++) {
-        const uint32_t w = s_warp[k];
-        if (k < warp) wpre += w;
-        btotal += w;
-    }
-    if (warp == 0) {
-        if (lane == 0) st_volatile_u64(state + bid, (bid == 0 ? FLAG_INC : FLAG_AGG) | btotal);
-        uint32_t excl = 0;
-        if (bid > 0) {
-            int look = (int)bid - 1;
-            while (true) {
-                const int j = look - lane;
-                unsigned long long st = FLAG_INC;  // positions before block 0 act as "inclusive 0"
-                if (j >= 0) {
-                    do { st = ld_volatile_u64(state + j); } while ((st & ~0xffffffffull) != FLAG_AGG &&
-                                                                 (st & ~0xffffffffull) != FLAG_INC);
-                }
-                const bool inc = (st & ~0xffffffffull) == FLAG_INC;
-                const uint32_t val = (uint32_t)st;
-                const unsigned im = __ballot_sync(GS_FULL, inc);
-                if (im) {
-                    const int first = __ffs(im) - 1;
-                    excl += warp_sum(lane <= first ? val : 0u);
-                    break;
-                }
-                excl += warp_sum(val);
-                look -= 32;
-            }
-            if (lane == 0) st_volatile_u64(state + bid, FLAG_INC | (uint32_t)(excl + btotal));
+        for (int j = 0; j < GS_LB; j++) {
+            while ((s[j] >> 30) == 0) s[j] = ld_volatile_u32(status + (size_t)(c - j) * stride + bin);
+            excl += s[j] & ST_VAL;
+            if (s[j] & ST_INC) return excl;
         }
-        if (lane == 0) s_prefix = excl;
     }
-    __syncthreads();
-    uint32_t run = s_prefix + wpre + (incl - tsum);
-    uint32_t o[GS_SCAN_ITEMS];
+    return excl;
+}
+
+// Row tables, recomputed by warp 0 of every CTA that needs them (<= 257 entries): prefix sum of the row difference
+// array = items per tile row; s_rs = exclusive scan of the items (row_start), s_cf = exclusive scan of the number of
+// column-pass chunks per row (chunks never straddle rows).  Entries 0..gy are written.
+__device__ __forceinline__ void row_tables(const int* __restrict__ rdiff, int gy, uint32_t* s_rs, uint32_t* s_cf,
+                                           int lane) {
+    uint32_t carry_items = 0, carry_chunks = 0;
+    int carry_diff = 0;
+    for (int y0 = 0; y0 <= gy; y0 += 32) {
+        const int y = y0 + lane;
+        int d = (y <= gy) ? rdiff[y] : 0;
 #pragma unroll
-    for (int k = 0; k < GS_SCAN_ITEMS; k++) { o[k] = run; run += v[k]; }
-    if (base + GS_SCAN_ITEMS <= n) {
-        *reinterpret_cast<uint4*>(data + base) = make_uint4(o[0], o[1], o[2], o[3]);
-        *reinterpret_cast<uint4*>(data + base + 4) = make_uint4(o[4], o[5], o[6], o[7]);
-    } else {
-#pragma unroll
-        for (int k = 0; k < GS_SCAN_ITEMS; k++)
-            if (base + k < n) data[base + k] = o[k];
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(GS_FULL, d, o);
+            if (lane >= o) d += t;
+        }
+        d += carry_diff;  // items of row y
+        const uint32_t n = (y < gy) ? (uint32_t)d : 0u;
+        const uint32_t nch = (uint32_t)gs_div_up(n, GS_PART_CHUNK);
+        const uint32_t in = warp_incl_scan(n, lane), ic = warp_incl_scan(nch, lane);
+        if (y <= gy) {
+            s_rs[y] = carry_items + in - n;
+            s_cf[y] = carry_chunks + ic - nch;
+        }
+        carry_items += __shfl_sync(GS_FULL, in, 31);
+        carry_chunks += __shfl_sync(GS_FULL, ic, 31);
+        carry_diff = __shfl_sync(GS_FULL, d, 31);
     }
-    // the block that owns the last element also publishes the grand total at data[n]
-    if (base <= (size_t)n - 1 && (size_t)n - 1 < base + GS_SCAN_ITEMS) data[n] = run;
+}
+// largest row with s_cf[row] <= chunk (rows without items share a value with their successor; the last one owns it)
+__device__ __forceinline__ int chunk_row(const uint32_t* s_cf, int gy, uint32_t chunk) {
+    int lo = 0, hi = gy;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (s_cf[mid] <= chunk) lo = mid; else hi = mid;
+    }
+    return lo;
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Depth sort: stable LSD radix sort of (key = depth bits, value = Gaussian index), 8 bits per pass.
-#define DS_WARPS 4
-#define DS_ROUNDS (GS_DEPTH_UNIT / 32)
+// Depth sort.  Histograms of all four digits in one pass over the keys.
+__global__ void __launch_bounds__(256) depth_hist_kernel(const uint32_t* __restrict__ key, uint32_t P,
+                                                         uint32_t* __restrict__ hist) {
+    __shared__ uint32_t s[4][GS_RADIX];
+    const int tid = threadIdx.x, lane = tid & 31;
+#pragma unroll
+    for (int p = 0; p < 4; p++) s[p][tid] = 0;
+    __syncthreads();
+    const uint32_t stride = gridDim.x * 256u;
+    const uint32_t iters = (uint32_t)gs_div_up(P, stride);
+    for (uint32_t it = 0; it < iters; it++) {  // whole warps iterate together (match needs converged lanes)
+        const uint32_t i = it * stride + blockIdx.x * 256u + tid;
+        const bool valid = i < P;
+        const uint32_t k = valid ? key[i] : 0u;
+        const unsigned act = __ballot_sync(GS_FULL, valid);
+        if (valid) {
+#pragma unroll
+            for (int p = 0; p < 4; p++) {
+                const uint32_t d = (k >> (8 * p)) & 255u;
+                if (p < 2) {
+                    atomicAdd(&s[p][d], 1u);  // low digits: nearly uniform, few conflicts
+                } else {                      // high digits: heavily repeated, aggregate within the warp first
+                    const unsigned m = __match_any_sync(act, d);
+                    if (lane == __ffs(m) - 1) atomicAdd(&s[p][d], (uint32_t)__popc(m));
+                }
+            }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int p = 0; p < 4; p++) {
+        const uint32_t v = s[p][tid];
+        if (v) atomicAdd(&hist[p * GS_RADIX + tid], v);
+    }
+}
 
-template <bool SCATTER>
-__global__ void __launch_bounds__(DS_WARPS * 32) depth_pass_kernel(const uint32_t* __restrict__ key_in,
-                                                                  const uint32_t* __restrict__ idx_in,
-                                                                  uint32_t* __restrict__ key_out,
-                                                                  uint32_t* __restrict__ idx_out,
-                                                                  uint32_t* __restrict__ hist, uint32_t P,
-                                                                  uint32_t units, int shift) {
-    __shared__ uint32_t s_cnt[DS_WARPS][GS_RADIX];
-    __shared__ uint32_t s_base[SCATTER ? DS_WARPS : 1][GS_RADIX];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t unit = blockIdx.x * DS_WARPS + warp;
-    if (unit >= units) return;  // whole warps only; no block-level barrier below
+// One LSD pass, onesweep style: a CTA owns GS_SORT_CHUNK consecutive keys (warp w the w-th 512, round r of a warp
+// the r-th 32), ranks them by digit with __match_any_sync + per-warp counters (stable: rounds in order, lanes in
+// order), obtains the number of equal-digit keys in all earlier chunks by decoupled look-back, and scatters.
+#define SORT_ROUNDS (GS_SORT_CHUNK / 256)
+__global__ void __launch_bounds__(256) depth_pass_kernel(const uint32_t* __restrict__ key_in,
+                                                         const uint32_t* __restrict__ idx_in,
+                                                         uint32_t* __restrict__ key_out, uint32_t* __restrict__ idx_out,
+                                                         const uint32_t* __restrict__ hist,  // this pass' 256 totals
+                                                         unsigned* __restrict__ status,      // [chunks][256]
+                                                         unsigned* __restrict__ ticket, uint32_t P, int shift,
+                                                         int first_pass) {
+    __shared__ uint32_t s_cnt[8][GS_RADIX];
+    __shared__ uint32_t s_base[GS_RADIX];
+    __shared__ uint32_t s_wsum[8];
+    __shared__ uint32_t s_chunk;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_chunk = atomicAdd(ticket, 1u);
+#pragma unroll
+    for (int w = 0; w < 8; w++) s_cnt[w][tid] = 0;
+    __syncthreads();
+    const uint32_t chunk = s_chunk;
+    const uint32_t base = chunk * GS_SORT_CHUNK + warp * (GS_SORT_CHUNK / 8);
+
+    uint32_t k[SORT_ROUNDS];
+    uint16_t rk[SORT_ROUNDS];
     uint32_t* cnt = s_cnt[warp];
 #pragma unroll
-    for (int k = 0; k < GS_RADIX / 32; k++) {
-        cnt[k * 32 + lane] = 0;
-        if (SCATTER) s_base[warp][k * 32 + lane] = hist[(size_t)(k * 32 + lane) * units + unit];
+    for (int r = 0; r < SORT_ROUNDS; r++) {
+        const uint32_t i = base + r * 32 + lane;
+        k[r] = (i < P) ? key_in[i] : 0xFFFFFFFFu;
     }
-    __syncwarp();
-    const uint32_t base = unit * GS_DEPTH_UNIT;
-#pragma unroll 4
-    for (int r = 0; r < DS_ROUNDS; r++) {
+#pragma unroll
+    for (int r = 0; r < SORT_ROUNDS; r++) {
         const uint32_t i = base + r * 32 + lane;
         const bool valid = i < P;
-        const uint32_t k = valid ? key_in[i] : 0u;
-        const uint32_t d = (k >> shift) & (GS_RADIX - 1);
-        const uint32_t off = warp_rank(d, valid, cnt, lane);
-        if (SCATTER && valid) {
-            const uint32_t pos = s_base[warp][d] + off;
-            key_out[pos] = k;
-            idx_out[pos] = idx_in[i];
-        }
-    }
-    if (!SCATTER) {
-#pragma unroll
-        for (int k = 0; k < GS_RADIX / 32; k++) hist[(size_t)(k * 32 + lane) * units + unit] = cnt[k * 32 + lane];
-    }
-}
-
-// ---------------------------------------------------------------------------------------------------
-// Tile pass 1: a warp owns GS_EMIT_UNIT consecutive Gaussians of the depth order, enumerates their tile
-// rectangles row-major (same emission order as rasterizer_impl.cu:98-108) and ranks every instance by the low
-// 8 bits of its tile id.
-#define EM_WARPS 4
-#define EM_PER_LANE (GS_EMIT_UNIT / 32)
-
-template <bool SCATTER>
-__global__ void __launch_bounds__(EM_WARPS * 32) tile_pass1_kernel(const uint32_t* __restrict__ sorted_idx,
-                                                                  const ushort4* __restrict__ rect,
-                                                                  const uint32_t* __restrict__ ntile,
-                                                                  uint32_t* __restrict__ hist,
-                                                                  uint32_t* __restrict__ stage,
-                                                                  GsHeader* __restrict__ hdr, uint32_t P,
-                                                                  uint32_t units, int gx, int idx_bits,
-                                                                  unsigned long long Rcap) {
-    __shared__ uint32_t s_cnt[EM_WARPS][GS_RADIX];
-    __shared__ uint32_t s_base[SCATTER ? EM_WARPS : 1][GS_RADIX];
-    __shared__ uint32_t s_off[EM_WARPS][GS_EMIT_UNIT + 1];
-    __shared__ uint32_t s_gi[EM_WARPS][GS_EMIT_UNIT];
-    __shared__ ushort4 s_rect[EM_WARPS][GS_EMIT_UNIT];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t unit = blockIdx.x * EM_WARPS + warp;
-    if (unit >= units) return;
-    const unsigned long long R = hdr->num_rendered;
-    if (R > Rcap) {  // no-sync mode: the preallocated instance buffers are too small -> frame is skipped
-        if (unit == 0 && lane == 0) hdr->code = GS_ERR_CAPACITY;
-        if (SCATTER) return;
-    }
-    uint32_t* cnt = s_cnt[warp];
-#pragma unroll
-    for (int k = 0; k < GS_RADIX / 32; k++) {
-        cnt[k * 32 + lane] = 0;
-        if (SCATTER) s_base[warp][k * 32 + lane] = hist[(size_t)(k * 32 + lane) * units + unit];
-    }
-    // stage this warp's Gaussians: index, rectangle, exclusive offsets of their tile counts
-    uint32_t carry = 0;
-#pragma unroll
-    for (int k = 0; k < EM_PER_LANE; k++) {
-        const uint32_t i = unit * GS_EMIT_UNIT + k * 32 + lane;
-        uint32_t gi = 0, nt = 0;
-        ushort4 rc = make_ushort4(0, 0, 0, 0);
-        if (i < P) {
-            gi = sorted_idx[i];
-            nt = ntile[gi];
-            rc = rect[gi];
-        }
-        const uint32_t inc = warp_incl_scan(nt, lane);
-        s_off[warp][k * 32 + lane] = carry + inc - nt;
-        s_gi[warp][k * 32 + lane] = gi;
-        s_rect[warp][k * 32 + lane] = rc;
-        carry += __shfl_sync(GS_FULL, inc, 31);
-    }
-    if (lane == 0) s_off[warp][GS_EMIT_UNIT] = carry;
-    __syncwarp();
-    const uint32_t n = (R > Rcap) ? 0u : carry;
-    const uint32_t* off = s_off[warp];
-    for (uint32_t e0 = 0; e0 < n; e0 += 32) {
-        const uint32_t e = e0 + lane;
-        const bool valid = e < n;
-        uint32_t d = 0, packed = 0;
+        const uint32_t d = (k[r] >> shift) & 255u;
+        const unsigned act = __ballot_sync(GS_FULL, valid);
+        uint32_t off = 0;
         if (valid) {
-            // largest g with off[g] <= e  (zero-tile Gaussians are skipped automatically)
-            int g = 0;
-#pragma unroll
-            for (int step = GS_EMIT_UNIT / 2; step > 0; step >>= 1)
-                if (off[g + step] <= e) g += step;
-            const ushort4 rc = s_rect[warp][g];
-            const uint32_t local = e - off[g];
-            const uint32_t w = (uint32_t)rc.z - (uint32_t)rc.x;
-            const uint32_t row = local / w;
-            const uint32_t tile = ((uint32_t)rc.y + row) * (uint32_t)gx + (uint32_t)rc.x + (local - row * w);
-            d = tile & (GS_RADIX - 1);
-            packed = ((tile >> GS_RADIX_BITS) << idx_bits) | s_gi[warp][g];
+            const unsigned m = __match_any_sync(act, d);
+            const unsigned before = __popc(m & ((1u << lane) - 1u));
+            const uint32_t c0 = cnt[d];
+            __syncwarp(act);
+            if (before == 0) cnt[d] = c0 + __popc(m);
+            off = c0 + before;
         }
-        const uint32_t o = warp_rank(d, valid, cnt, lane);
-        if (SCATTER && valid) stage[s_base[warp][d] + o] = packed;
+        __syncwarp();
+        rk[r] = (uint16_t)off;
     }
-    if (!SCATTER) {
-#pragma unroll
-        for (int k = 0; k < GS_RADIX / 32; k++) hist[(size_t)(k * 32 + lane) * units + unit] = cnt[k * 32 + lane];
-    }
-}
-
-// ---------------------------------------------------------------------------------------------------
-// Tile pass 2: warps own <= GS_TILE2_UNIT consecutive instances that all lie inside ONE low-digit bucket, so the
-// pass-2 prefix table, indexed [high digit][unit], is ordered exactly like the final list:
-// (high digit, low digit, position) = (tile id, depth order).
-#define T2_WARPS 4
-#define T2_ROUNDS (GS_TILE2_UNIT / 32)
-
-template <bool SCATTER>
-__global__ void __launch_bounds__(T2_WARPS * 32) tile_pass2_kernel(const uint32_t* __restrict__ stage,
-                                                                  const uint32_t* __restrict__ hist1,
-                                                                  uint32_t units1, uint32_t* __restrict__ hist2,
-                                                                  uint32_t units2, uint32_t* __restrict__ list,
-                                                                  uint32_t* __restrict__ bucket_unit0,
-                                                                  const GsHeader* __restrict__ hdr, int idx_bits,
-                                                                  unsigned long long Rcap) {
-    __shared__ uint32_t s_cnt[T2_WARPS][GS_RADIX];
-    __shared__ uint32_t s_base[SCATTER ? T2_WARPS : 1][GS_RADIX];
-    __shared__ uint32_t s_bstart[GS_RADIX + 1];
-    __shared__ uint32_t s_unit0[GS_RADIX + 1];
-    __shared__ uint32_t s_wsum[T2_WARPS];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const bool over = hdr->num_rendered > Rcap;
-    // bucket boundaries = scanned pass-1 table at the first unit of each digit; total at [256*units1]
-    for (int d = tid; d <= GS_RADIX; d += T2_WARPS * 32) s_bstart[d] = over ? 0u : hist1[(size_t)d * units1];
     __syncthreads();
-    // exclusive scan of the per-bucket unit counts (2 buckets per thread)
-    uint32_t nb0 = 0, nb1 = 0;
-    {
-        const int d0 = 2 * tid, d1 = 2 * tid + 1;
-        nb0 = (uint32_t)gs_div_up(s_bstart[d0 + 1] - s_bstart[d0], GS_TILE2_UNIT);
-        nb1 = (uint32_t)gs_div_up(s_bstart[d1 + 1] - s_bstart[d1], GS_TILE2_UNIT);
+    // thread d: exclusive scan of digit d over the 8 warps, CTA total, look-back, global digit base
+    uint32_t total = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) {
+        const uint32_t t = s_cnt[w][tid];
+        s_cnt[w][tid] = total;
+        total += t;
     }
-    const uint32_t pair = nb0 + nb1;
-    const uint32_t inc = warp_incl_scan(pair, lane);
-    if (lane == 31) s_wsum[warp] = inc;
+    st_volatile_u32(status + (size_t)chunk * GS_RADIX + tid, (chunk == 0 ? ST_INC : ST_AGG) | total);
+    // exclusive scan of the global digit totals over the 256 digits (one per thread)
+    const uint32_t h = hist[tid];
+    const uint32_t incl = warp_incl_scan(h, lane);
+    if (lane == 31) s_wsum[warp] = incl;
     __syncthreads();
     uint32_t wpre = 0;
-    for (int k = 0; k < warp; k++) wpre += s_wsum[k];
-    const uint32_t ex = wpre + inc - pair;
-    s_unit0[2 * tid] = ex;
-    s_unit0[2 * tid + 1] = ex + nb0;
-    if (tid == T2_WARPS * 32 - 1) s_unit0[GS_RADIX] = ex + pair;
+#pragma unroll
+    for (int w = 0; w < 8; w++)
+        if (w < warp) wpre += s_wsum[w];
+    uint32_t excl = 0;
+    if (chunk > 0) {
+        excl = look_back(status, GS_RADIX, (int)chunk, 0, tid);
+        st_volatile_u32(status + (size_t)chunk * GS_RADIX + tid, ST_INC | (excl + total));
+    }
+    s_base[tid] = wpre + incl - h + excl;
     __syncthreads();
-    if (!SCATTER && blockIdx.x == 0)
-        for (int d = tid; d <= GS_RADIX; d += T2_WARPS * 32) bucket_unit0[d] = s_unit0[d];
-
-    const uint32_t unit = blockIdx.x * T2_WARPS + warp;
-    if (unit >= units2) return;
-    uint32_t* cnt = s_cnt[warp];
 #pragma unroll
-    for (int k = 0; k < GS_RADIX / 32; k++) {
-        cnt[k * 32 + lane] = 0;
-        if (SCATTER) s_base[warp][k * 32 + lane] = hist2[(size_t)(k * 32 + lane) * units2 + unit];
-    }
-    __syncwarp();
-    uint32_t begin = 0, end = 0;
-    if (unit < s_unit0[GS_RADIX]) {
-        int b = 0;  // largest bucket with unit0[b] <= unit and at least one unit
-#pragma unroll
-        for (int step = GS_RADIX / 2; step > 0; step >>= 1)
-            if (s_unit0[b + step] <= unit) b += step;
-        begin = s_bstart[b] + (unit - s_unit0[b]) * GS_TILE2_UNIT;
-        end = min(begin + (uint32_t)GS_TILE2_UNIT, s_bstart[b + 1]);
-    }
-    const uint32_t mask = (idx_bits >= 32) ? 0xffffffffu : ((1u << idx_bits) - 1u);
-    for (uint32_t i0 = begin; i0 < end; i0 += 32) {
-        const uint32_t i = i0 + lane;
-        const bool valid = i < end;
-        const uint32_t e = valid ? stage[i] : 0u;
-        const uint32_t d = (idx_bits >= 32) ? 0u : (e >> idx_bits);
-        const uint32_t o = warp_rank(d, valid, cnt, lane);
-        if (SCATTER && valid) list[s_base[warp][d] + o] = e & mask;
-    }
-    if (!SCATTER) {
-#pragma unroll
-        for (int k = 0; k < GS_RADIX / 32; k++) hist2[(size_t)(k * 32 + lane) * units2 + unit] = cnt[k * 32 + lane];
+    for (int r = 0; r < SORT_ROUNDS; r++) {
+        const uint32_t i = base + r * 32 + lane;
+        if (i < P) {
+            const uint32_t d = (k[r] >> shift) & 255u;
+            const uint32_t pos = s_base[d] + cnt[d] + rk[r];
+            key_out[pos] = k[r];
+            idx_out[pos] = first_pass ? i : idx_in[i];
+        }
     }
 }
 
-cudaError_t launch_scan(uint32_t* data, size_t n, unsigned long long* state, unsigned int* ticket, uint32_t epoch,
-                        cudaStream_t stream) {
-    scan_kernel<<<(unsigned)gs_div_up(n, GS_SCAN_TILE), GS_SCAN_THREADS, 0, stream>>>(data, (uint32_t)n, state, ticket,
-                                                                                     epoch);
-    gs_note_launch();
-    return cudaGetLastError();
+// ---------------------------------------------------------------------------------------------------
+// Column histogram: instances per tile = number of row items of the tile's row that cover its column.  A CTA owns
+// one column-pass chunk (items of ONE row), builds the column difference array in shared memory (+1 at x0, -1 at
+// x1 per item), integrates it and adds the non-zero counts to tcount.
+template <int NB>
+__global__ void __launch_bounds__(256) column_hist_kernel(const uint2* __restrict__ items, const int* __restrict__ rdiff,
+                                                          int gx, int gy, unsigned long long RowCap,
+                                                          uint32_t* __restrict__ tcount) {
+    constexpr int G = NB / 32;
+    __shared__ uint32_t s_rs[GS_MAX_GRID + 1], s_cf[GS_MAX_GRID + 1];
+    __shared__ int s_d[NB + 1];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (warp == 0) row_tables(rdiff, gy, s_rs, s_cf, lane);
+    __syncthreads();
+    if ((unsigned long long)s_rs[gy] > RowCap) return;
+    const uint32_t nchunks = s_cf[gy];
+    for (uint32_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+        const int row = chunk_row(s_cf, gy, chunk);
+        const uint32_t ibeg = s_rs[row] + (chunk - s_cf[row]) * GS_PART_CHUNK;
+        const uint32_t iend = min(s_rs[row + 1], ibeg + (uint32_t)GS_PART_CHUNK);
+        for (int i = tid; i <= NB; i += 256) s_d[i] = 0;
+        __syncthreads();
+        for (uint32_t i = ibeg + tid; i < iend; i += 256) {
+            const uint32_t xr = items[i].y;
+            atomicAdd(&s_d[xr & 0xffffu], 1);
+            atomicAdd(&s_d[xr >> 16], -1);
+        }
+        __syncthreads();
+        if (warp == 0) {
+            int v[G], sum = 0;
+#pragma unroll
+            for (int j = 0; j < G; j++) { sum += s_d[lane * G + j]; v[j] = sum; }
+            const int pre = (int)warp_incl_scan((uint32_t)sum, lane) - sum;
+#pragma unroll
+            for (int j = 0; j < G; j++) {
+                const int x = lane * G + j, c = v[j] + pre;
+                if (x < gx && c) atomicAdd(&tcount[row * gx + x], (uint32_t)c);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// Plan (one CTA): exclusive scan of the tile counts in tile-id order = the tile ranges; longest-list-first order of
+// the shard's tiles for the blend queue; instance-capacity check (no-sync mode).
+__global__ void __launch_bounds__(1024) plan_kernel(const uint32_t* __restrict__ tcount, int gx, int gy, int row0,
+                                                    int row1, uint32_t* __restrict__ tile_start,
+                                                    uint2* __restrict__ ranges, uint32_t* __restrict__ order,
+                                                    GsHeader* __restrict__ hdr, unsigned long long Rcap) {
+    __shared__ uint32_t s_wsum[32];
+    __shared__ uint32_t s_cnt[33], s_slot[33];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int Tn = gx * gy;
+    const int per = (Tn + 1023) / 1024;  // each thread owns a contiguous run of tiles
+    const int t_begin = min(Tn, tid * per), t_end = min(Tn, t_begin + per);
+    uint32_t local = 0;
+    for (int t = t_begin; t < t_end; t++) local += tcount[t];
+    const uint32_t incl = warp_incl_scan(local, lane);
+    if (lane == 31) s_wsum[warp] = incl;
+    if (tid < 33) s_cnt[tid] = 0;
+    __syncthreads();
+    uint32_t wpre = 0, total = 0;
+    for (int w = 0; w < 32; w++) {
+        const uint32_t v = s_wsum[w];
+        if (w < warp) wpre += v;
+        total += v;
+    }
+    const bool over = (unsigned long long)total > Rcap || hdr->skip != 0;
+    if (tid == 0 && over) { hdr->skip = 1u; hdr->code = GS_ERR_CAPACITY; }
+    uint32_t run = wpre + incl - local;
+    const int s0 = row0 * gx, s1 = row1 * gx;
+    for (int t = t_begin; t < t_end; t++) {
+        const uint32_t c = tcount[t];
+        tile_start[t] = run;
+        if (t >= s0 && t < s1) {
+            const uint32_t len = over ? 0u : c;
+            ranges[t] = over ? make_uint2(0u, 0u) : make_uint2(run, run + c);
+            const int cls = len ? 32 - __clz(len) : 0;  // 0 = empty, 1..32
+            atomicAdd(&s_cnt[32 - cls], 1u);            // slot 0 = longest class
+        }
+        run += c;
+    }
+    if (tid == 1023) tile_start[Tn] = total;
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t acc = 0;
+        for (int k = 0; k < 33; k++) { s_slot[k] = acc; acc += s_cnt[k]; }
+    }
+    __syncthreads();
+    for (int t = t_begin; t < t_end; t++) {
+        if (t >= s0 && t < s1) {
+            const uint32_t len = over ? 0u : tcount[t];
+            const int cls = len ? 32 - __clz(len) : 0;
+            const uint32_t slot = atomicAdd(&s_slot[32 - cls], 1u);
+            order[slot] = (uint32_t)t;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Range partition (row pass: PASS 1, column pass: PASS 2).
+// Every input item covers the bin range [lo, hi) and emits one output element into each covered bin; elements of a
+// bin keep the input order.  A CTA owns a chunk of GS_PART_CHUNK consecutive items (warp w the w-th 256, round r the
+// r-th 32).  NB = number of bins rounded up to 128 or 256.
+#define PART_ROUNDS (GS_PART_CHUNK / 256)
+
+template <int NB, int PASS>
+__global__ void __launch_bounds__(256) range_partition_kernel(
+    const uint32_t* __restrict__ sorted_idx, const ushort4* __restrict__ rect, uint32_t P,  // PASS 1 input
+    const uint2* __restrict__ items_in,                                                      // PASS 2 input
+    const int* __restrict__ rdiff, int gx, int gy, const uint32_t* __restrict__ tile_start,
+    unsigned long long RowCap, unsigned* __restrict__ status, int stat_stride, unsigned* __restrict__ ticket,
+    GsHeader* __restrict__ hdr, uint2* __restrict__ items_out, uint32_t* __restrict__ list_out) {
+    constexpr int G = NB / 32;  // bins per lane in the warp-wide scans
+    __shared__ int s_cnt[8][NB + 1];        // per-warp: difference array -> counts -> running output positions
+    __shared__ uint32_t s_mask[8][NB + 1];  // per-warp, per round: bit i set = item of lane i covers the bin
+    __shared__ uint32_t s_rs[GS_MAX_GRID + 1], s_cf[GS_MAX_GRID + 1];
+    __shared__ uint32_t s_chunk;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (PASS == 2 && hdr->skip) return;
+    if (warp == 0) row_tables(rdiff, gy, s_rs, s_cf, lane);
+    __syncthreads();
+    if ((unsigned long long)s_rs[gy] > RowCap) {  // no-sync mode: row-item buffer too small -> frame is skipped
+        if (PASS == 1 && blockIdx.x == 0 && tid == 0) { hdr->skip = 1u; hdr->code = GS_ERR_CAPACITY; }
+        return;
+    }
+    const uint32_t nchunks = (PASS == 1) ? (uint32_t)gs_div_up(P, GS_PART_CHUNK) : s_cf[gy];
+    int* cnt = s_cnt[warp];
+    uint32_t* msk = s_mask[warp];
+    const unsigned lt = (1u << lane) - 1u, bit = 1u << lane;
+
+    while (true) {
+        __syncthreads();  // previous chunk's shared state is dead
+        if (tid == 0) s_chunk = atomicAdd(ticket, 1u);
+        for (int i = tid; i < 8 * (NB + 1); i += 256) (&s_cnt[0][0])[i] = 0;
+        __syncthreads();
+        const uint32_t chunk = s_chunk;
+        if (chunk >= nchunks) break;
+
+        // chunk -> item range and head of its look-back chain
+        uint32_t ibeg, iend;
+        int first = 0, row = 0;
+        if (PASS == 1) {
+            ibeg = chunk * GS_PART_CHUNK;
+            iend = min(P, ibeg + (uint32_t)GS_PART_CHUNK);
+        } else {
+            row = chunk_row(s_cf, gy, chunk);
+            first = (int)s_cf[row];
+            ibeg = s_rs[row] + (chunk - (uint32_t)first) * GS_PART_CHUNK;
+            iend = min(s_rs[row + 1], ibeg + (uint32_t)GS_PART_CHUNK);
+        }
+
+        // ---- phase A: load items, per-warp difference arrays
+        uint32_t pay[PART_ROUNDS], rng[PART_ROUNDS];  // payload (gaussian), lo | hi << 16
+        uint32_t xr[PASS == 1 ? PART_ROUNDS : 1];
+#pragma unroll
+        for (int r = 0; r < PART_ROUNDS; r++) {
+            const uint32_t i = ibeg + warp * (GS_PART_CHUNK / 8) + r * 32 + lane;
+            uint32_t lo = 0, hi = 0;
+            pay[r] = 0;
+            if (i < iend) {
+                if (PASS == 1) {
+                    const uint32_t gi = sorted_idx[i];
+                    const ushort4 rc = rect[gi];
+                    pay[r] = gi;
+                    xr[r] = (uint32_t)rc.x | ((uint32_t)rc.z << 16);
+                    lo = rc.y; hi = rc.w;
+                } else {
+                    const uint2 it = items_in[i];
+                    pay[r] = it.x;
+                    lo = it.y & 0xffffu; hi = it.y >> 16;
+                }
+                if (hi <= lo) { lo = 0; hi = 0; }
+            }
+            rng[r] = lo | (hi << 16);
+            if (hi > lo) {
+                atomicAdd(&cnt[lo], 1);
+                atomicAdd(&cnt[hi], -1);
+            }
+        }
+        __syncwarp();
+        {   // per-warp prefix sum over the bins: difference array -> number of this warp's items covering each bin
+            int v[G], sum = 0;
+#pragma unroll
+            for (int j = 0; j < G; j++) { sum += cnt[lane * G + j]; v[j] = sum; }
+            const int pre = (int)warp_incl_scan((uint32_t)sum, lane) - sum;
+#pragma unroll
+            for (int j = 0; j < G; j++) cnt[lane * G + j] = v[j] + pre;
+        }
+        __syncthreads();
+        // ---- phase B: thread b = bin b: scan over warps, chunk aggregate, look-back, output base
+        if (tid < NB) {
+            const int nb_used = (PASS == 1) ? gy : gx;
+            uint32_t total = 0;
+#pragma unroll
+            for (int w = 0; w < 8; w++) {
+                const uint32_t t = (uint32_t)s_cnt[w][tid];
+                s_cnt[w][tid] = (int)total;
+                total += t;
+            }
+            uint32_t basev = 0;
+            if (tid < nb_used) {
+                unsigned* st = status + (size_t)chunk * stat_stride + tid;
+                const bool head = (int)chunk == first;
+                st_volatile_u32(st, (head ? ST_INC : ST_AGG) | total);
+                uint32_t excl = 0;
+                if (!head) {
+                    excl = look_back(status, stat_stride, (int)chunk, first, tid);
+                    st_volatile_u32(st, ST_INC | (excl + total));
+                }
+                basev = excl + ((PASS == 1) ? s_rs[tid] : tile_start[row * gx + tid]);
+            }
+#pragma unroll
+            for (int w = 0; w < 8; w++) s_cnt[w][tid] += (int)basev;
+        }
+        __syncthreads();
+        // ---- phase C: round by round, bitmask of covering items per bin -> stable ranks -> scatter
+#pragma unroll
+        for (int r = 0; r < PART_ROUNDS; r++) {
+#pragma unroll
+            for (int j = 0; j < G; j++) msk[lane * G + j] = 0;
+            if (lane == 0) msk[NB] = 0;
+            __syncwarp();
+            const uint32_t lo = rng[r] & 0xffffu, hi = rng[r] >> 16;
+            if (hi > lo) {
+                atomicXor(&msk[lo], bit);
+                atomicXor(&msk[hi], bit);
+            }
+            __syncwarp();
+            uint32_t m[G], acc = 0;
+#pragma unroll
+            for (int j = 0; j < G; j++) { acc ^= msk[lane * G + j]; m[j] = acc; }
+            uint32_t sc = acc;  // inclusive xor-scan of the lane totals
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(GS_FULL, sc, o);
+                if (lane >= o) sc ^= t;
+            }
+            const uint32_t pre = sc ^ acc;
+#pragma unroll
+            for (int j = 0; j < G; j++) { m[j] ^= pre; msk[lane * G + j] = m[j]; }
+            __syncwarp();
+            for (uint32_t b = lo; b < hi; b++) {
+                const uint32_t pos = (uint32_t)cnt[b] + __popc(msk[b] & lt);
+                if (PASS == 1) items_out[pos] = make_uint2(pay[r], xr[PASS == 1 ? r : 0]);
+                else list_out[pos] = pay[r];
+            }
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < G; j++) cnt[lane * G + j] += __popc(m[j]);
+        }
+    }
 }
 
 }  // namespace
 
 #define GS_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return e_; } while (0)
 
-cudaError_t gs_launch_depth_sort(const GsFrame& f, const GsGeom& g, int* sorted_side) {
+cudaError_t gs_launch_depth_sort(const GsFrame& f, const GsGeom& g) {
     const uint32_t P = (uint32_t)f.s.P;
-    const uint32_t units = (uint32_t)g.depth_units;
-    const unsigned blocks = (unsigned)gs_div_up(units, DS_WARPS);
+    const unsigned chunks = (unsigned)g.sort_chunks;
+    depth_hist_kernel<<<(unsigned)min((size_t)296, gs_div_up(P, 2048)), 256, 0, f.stream>>>(g.key[0], P, g.dhist);
+    gs_note_launch();
+    GS_TRY(cudaGetLastError());
     int side = 0;
     for (int pass = 0; pass < 4; pass++) {
-        const int shift = pass * GS_RADIX_BITS;
-        depth_pass_kernel<false><<<blocks, DS_WARPS * 32, 0, f.stream>>>(g.key[side], g.idx[side], nullptr, nullptr,
-                                                                        g.dhist, P, units, shift);
-        gs_note_launch();
-        GS_TRY(cudaGetLastError());
-        GS_TRY(launch_scan(g.dhist, (size_t)GS_RADIX * units, g.dstate, &g.hdr->tickets[pass], (uint32_t)pass,
-                           f.stream));
-        depth_pass_kernel<true><<<blocks, DS_WARPS * 32, 0, f.stream>>>(g.key[side], g.idx[side], g.key[side ^ 1],
-                                                                       g.idx[side ^ 1], g.dhist, P, units, shift);
+        depth_pass_kernel<<<chunks, 256, 0, f.stream>>>(g.key[side], g.idx[side], g.key[side ^ 1], g.idx[side ^ 1],
+                                                       g.dhist + pass * GS_RADIX,
+                                                       g.dstat + (size_t)pass * chunks * GS_RADIX,
+                                                       &g.hdr->tickets[pass], P, pass * GS_RADIX_BITS, pass == 0);
         gs_note_launch();
         GS_TRY(cudaGetLastError());
         side ^= 1;
     }
-    *sorted_side = side;
-    return cudaSuccess;
+    return cudaSuccess;  // four passes: the sorted order is back in key[0] / idx[0]
 }
 
-cudaError_t gs_launch_tile_binning(const GsFrame& f, const GsGeom& g, int sorted_side, const GsBinning& b,
-                                   size_t Rcap, const GsImage& im) {
+static int g_part_grid = 0;
+
+cudaError_t gs_launch_tile_lists(const GsFrame& f, const GsGeom& g, const GsBinning& b, size_t Rcap, size_t RowCap,
+                                 const GsImage& im) {
     const uint32_t P = (uint32_t)f.s.P;
-    const uint32_t units1 = (uint32_t)b.emit_units, units2 = (uint32_t)b.units2;
-    const unsigned blocks1 = (unsigned)gs_div_up(units1, EM_WARPS), blocks2 = (unsigned)gs_div_up(units2, T2_WARPS);
-    const uint32_t* sidx = g.idx[sorted_side];
-    tile_pass1_kernel<false><<<blocks1, EM_WARPS * 32, 0, f.stream>>>(sidx, g.rect, g.ntile, b.hist1, b.stage, g.hdr,
-                                                                     P, units1, f.gx, f.idx_bits, Rcap);
+    if (g_part_grid == 0) {
+        int dev = 0, sms = 0;
+        GS_TRY(cudaGetDevice(&dev));
+        GS_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        g_part_grid = sms * 8;
+    }
+    const unsigned grid1 = (unsigned)min((size_t)g_part_grid, g.row_chunks);
+    const unsigned grid2 = (unsigned)min((size_t)g_part_grid, b.col_chunks);
+    const unsigned long long rowcap = RowCap;
+#define LAUNCH_PART(NB, PASS, GRID)                                                                               \
+    range_partition_kernel<NB, PASS><<<GRID, 256, 0, f.stream>>>(                                                 \
+        g.idx[0], g.rect, P, b.items, im.rdiff, f.gx, f.gy, im.tile_start, rowcap, (PASS == 1) ? g.rstat : b.cstat, \
+        GS_MAX_GRID, &g.hdr->tickets[3 + PASS], g.hdr, b.items, b.list)
+    // row pass: Gaussians in depth order -> row items grouped by tile row
+    if (f.gy <= 128) LAUNCH_PART(128, 1, grid1); else LAUNCH_PART(256, 1, grid1);
     gs_note_launch();
     GS_TRY(cudaGetLastError());
-    GS_TRY(launch_scan(b.hist1, (size_t)GS_RADIX * units1, b.state1, &g.hdr->tickets[4], 0u, f.stream));
-    tile_pass1_kernel<true><<<blocks1, EM_WARPS * 32, 0, f.stream>>>(sidx, g.rect, g.ntile, b.hist1, b.stage, g.hdr, P,
-                                                                    units1, f.gx, f.idx_bits, Rcap);
+    // column histogram -> per-tile counts, then the plan (ranges, tile_start, blend queue)
+    if (f.gx <= 128) column_hist_kernel<128><<<grid2, 256, 0, f.stream>>>(b.items, im.rdiff, f.gx, f.gy, rowcap, im.tcount);
+    else column_hist_kernel<256><<<grid2, 256, 0, f.stream>>>(b.items, im.rdiff, f.gx, f.gy, rowcap, im.tcount);
     gs_note_launch();
     GS_TRY(cudaGetLastError());
-    tile_pass2_kernel<false><<<blocks2, T2_WARPS * 32, 0, f.stream>>>(b.stage, b.hist1, units1, b.hist2, units2, b.list,
-                                                                     b.bucket_unit0, g.hdr, f.idx_bits, Rcap);
+    plan_kernel<<<1, 1024, 0, f.stream>>>(im.tcount, f.gx, f.gy, f.row0, f.row1, im.tile_start, im.ranges, im.order,
+                                         g.hdr, (unsigned long long)Rcap);
     gs_note_launch();
     GS_TRY(cudaGetLastError());
-    GS_TRY(launch_scan(b.hist2, (size_t)GS_RADIX * units2, b.state2, &g.hdr->tickets[5], 0u, f.stream));
-    tile_pass2_kernel<true><<<blocks2, T2_WARPS * 32, 0, f.stream>>>(b.stage, b.hist1, units1, b.hist2, units2, b.list,
-                                                                    b.bucket_unit0, g.hdr, f.idx_bits, Rcap);
+    // column pass: row items -> final per-tile lists
+    if (f.gx <= 128) LAUNCH_PART(128, 2, grid2); else LAUNCH_PART(256, 2, grid2);
     gs_note_launch();
     GS_TRY(cudaGetLastError());
-    return gs_launch_tile_order(f, g, b, Rcap, im);  // ranges + longest-first blend queue (blend_forward.cu)
+#undef LAUNCH_PART
+    return cudaSuccess;
 }

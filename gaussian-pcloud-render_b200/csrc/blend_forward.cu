@@ -25,47 +25,6 @@ namespace {
 
 #define BF_WARPS 8
 
-// ---------------------------------------------------------------------------------------------------
-// Tile ranges + longest-first tile order, one block.  ranges come straight from the scanned pass-2 table
-// (binning.cu); order[] lists the shard's tiles by descending log2(list length).
-__global__ void __launch_bounds__(1024) tile_order_kernel(const uint32_t* __restrict__ hist2, uint32_t units2,
-                                                          const uint32_t* __restrict__ bucket_unit0,
-                                                          uint2* __restrict__ ranges, uint32_t* __restrict__ order,
-                                                          int gx, int row0, int row1,
-                                                          const GsHeader* __restrict__ hdr, unsigned long long Rcap) {
-    __shared__ uint32_t s_cnt[33], s_start[33];
-    const int tid = threadIdx.x;
-    if (tid < 33) s_cnt[tid] = 0;
-    __syncthreads();
-    const bool over = hdr->num_rendered > Rcap;
-    const int t0 = row0 * gx, t1 = row1 * gx;
-    for (int t = t0 + tid; t < t1; t += 1024) {
-        uint32_t s = 0, e = 0;
-        if (!over) {
-            const uint32_t lo = t & (GS_RADIX - 1), hi = (uint32_t)t >> GS_RADIX_BITS;
-            s = hist2[(size_t)hi * units2 + bucket_unit0[lo]];
-            e = hist2[(size_t)hi * units2 + bucket_unit0[lo + 1]];
-        }
-        ranges[t] = make_uint2(s, e);
-        const uint32_t len = e - s;
-        const int cls = len ? 32 - __clz(len) : 0;  // 0 = empty, 1..32
-        atomicAdd(&s_cnt[32 - cls], 1u);            // slot 0 = longest class
-    }
-    __syncthreads();
-    if (tid == 0) {
-        uint32_t acc = 0;
-        for (int k = 0; k < 33; k++) { s_start[k] = acc; acc += s_cnt[k]; }
-    }
-    __syncthreads();
-    for (int t = t0 + tid; t < t1; t += 1024) {
-        const uint2 r = ranges[t];
-        const uint32_t len = r.y - r.x;
-        const int cls = len ? 32 - __clz(len) : 0;
-        const uint32_t slot = atomicAdd(&s_start[32 - cls], 1u);
-        order[slot] = (uint32_t)t;
-    }
-}
-
 // Upper bound of power(d) = -0.5 (A dx^2 + C dy^2) - B dx dy over the box [xlo,xhi] x [ylo,yhi] of d = mean - pixel,
 // plus a rounding allowance.  Exact box maximum of a concave quadratic: 0 if the box contains the origin, otherwise
 // the best of the 1-D maxima on the (at most two) box edges that face the origin.  nBA = -B/A, nBC = -B/C
@@ -202,14 +161,6 @@ __global__ void __launch_bounds__(BF_WARPS * 32, 4) blend_forward_kernel(
 int g_blend_grid = 0;
 
 }  // namespace
-
-cudaError_t gs_launch_tile_order(const GsFrame& f, const GsGeom& g, const GsBinning& b, size_t Rcap,
-                                 const GsImage& im) {
-    tile_order_kernel<<<1, 1024, 0, f.stream>>>(b.hist2, (uint32_t)b.units2, b.bucket_unit0, im.ranges, im.order, f.gx,
-                                               f.row0, f.row1, g.hdr, Rcap);
-    gs_note_launch();
-    return cudaGetLastError();
-}
 
 cudaError_t gs_launch_blend_forward(const GsFrame& f, const GsGeom& g, const GsBinning& b, const GsImage& im,
                                     float* out_color) {

@@ -3,6 +3,9 @@
 // Data layout in HBM (all carved from the three caller-owned byte buffers, 256-B aligned sub-arrays):
 //   geometry buffer (per Gaussian, P entries)
 //     GsHeader            status block + counters (256 B)
+//     dhist [4][256] u32  digit histograms of the depth keys           } zeroed at the start of every frame
+//     dstat [4][C][256]   decoupled look-back state of the depth sort   } (C = ceil(P / 4096) chunks)
+//     rstat [C1][256]     look-back state of the row pass               } (C1 = ceil(P / 2048) chunks)
 //     rec   [P] GsRec     48-B packed record read by the blend kernels (3 x float4)
 //     key   [2][P] u32    depth-sort keys (float bits of view-space z; 0xFFFFFFFF = culled), ping/pong
 //     idx   [2][P] u32    depth-sort values (Gaussian index), ping/pong
@@ -10,13 +13,16 @@
 //     ntile [P] u32       tiles touched
 //     cov3D [P][6] f32    world covariance (only when computed from scale/rotation)
 //     clamp [P] u8        bit c set = SH colour channel c was clamped at 0
-//     sort scratch        per-warp digit histograms + look-back state of the depth sort
 //   binning buffer (per instance, R entries)
-//     stage [R] u32       instances after tile pass 1: (tile_hi << idx_bits) | gaussian
-//     list  [R] u32       final per-tile, depth-ordered Gaussian index list ("point_list")
-//     hist1/hist2 + look-back state of the two tile passes, bucket table
+//     list  [R] u32       final per-tile, depth-ordered Gaussian index list ("point_list"); FIRST, so that backward
+//                         finds it from num_rendered alone
+//     cstat [C2][NBX]     look-back state of the column pass (zeroed every frame)
+//     items [Rrow] uint2  row items after the row pass: (gaussian, x0 | x1 << 16), grouped by tile row, depth order
 //   image buffer
-//     final_T [N] f32, n_contrib [N] u32, ranges [Tn] uint2, order [Tn] u32 (longest-list-first tile queue)
+//     rdiff [gy+1] i32    difference array of the row ranges -> row-item counts     } zeroed every
+//     tcount [Tn] u32     instances per tile (column histogram of the row items)   } frame
+//     final_T [N] f32, n_contrib [N] u32, ranges [Tn] uint2, order [Tn] u32 (longest-list-first tile queue),
+//     tile_start [Tn+1] u32
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -38,8 +44,12 @@ struct GsHeader {  // lives at offset 0 of the geometry buffer
     unsigned long long num_rendered;  // sum of tiles touched (atomicAdd from preprocess)
     unsigned int num_visible;
     int code;  // GS_OK / GS_ERR_*
-    unsigned int tickets[16];  // dynamic block ids of the look-back scans
-    unsigned int pad[44];
+    unsigned int num_row_items;  // sum of tile rows touched (atomicAdd from preprocess)
+    unsigned int reserved0;
+    unsigned int skip;           // 1 = instance / row-item capacity exceeded (no-sync mode): the frame is skipped
+    unsigned int pad0;
+    unsigned int tickets[16];    // 0-3 depth-sort passes, 4 row pass, 5 column pass, 6 blend work queue
+    unsigned int pad[40];
 };
 static_assert(sizeof(GsHeader) == 256, "header is one aligned slot");
 
@@ -57,21 +67,20 @@ struct GsCarver {
     }
 };
 
-// radix machinery: one WARP is the unit of work of every radix pass.
+// chunk sizes of the binning kernels (one CTA of 256 threads per chunk)
 #define GS_RADIX_BITS 8
 #define GS_RADIX 256
-#define GS_SCAN_ITEMS 8           // scan kernel: items per thread
-#define GS_SCAN_THREADS 256
-#define GS_SCAN_TILE (GS_SCAN_ITEMS * GS_SCAN_THREADS)
-#define GS_DEPTH_UNIT 512         // keys per warp in a depth-sort pass
-#define GS_EMIT_UNIT 128          // depth-sorted Gaussians per warp in tile pass 1
-#define GS_TILE2_UNIT 2048        // instances per warp in tile pass 2
+#define GS_SORT_CHUNK 4096   // depth keys per CTA and pass
+#define GS_PART_CHUNK 2048   // items per CTA of the row / column partition passes
+#define GS_MAX_GRID 256      // at most 256 x 256 tiles (4096 x 4096 pixels)
 
 static inline __host__ __device__ size_t gs_div_up(size_t a, size_t b) { return (a + b - 1) / b; }
 
 struct GsGeom {
     GsHeader* hdr;
-    unsigned long long* dstate;  // look-back state of the depth-sort scans (directly after hdr: one memset)
+    uint32_t* dhist;   // [4][256]
+    uint32_t* dstat;   // [4][sort_chunks][256]
+    uint32_t* rstat;   // [row_chunks][256]
     GsRec* rec;
     uint32_t* key[2];
     uint32_t* idx[2];
@@ -79,16 +88,16 @@ struct GsGeom {
     uint32_t* ntile;
     float* cov3D;
     uint8_t* clamp;
-    uint32_t* dhist;             // [256][depth_units] (+1)
-    size_t depth_units, dhist_len, dstate_len, zero_bytes, bytes;
+    size_t sort_chunks, row_chunks, zero_bytes, bytes;
     __host__ __device__ GsGeom(char* base, size_t P) {
         GsCarver c(base);
         hdr = c.take<GsHeader>(1);
-        depth_units = gs_div_up(P, GS_DEPTH_UNIT);
-        dhist_len = GS_RADIX * depth_units + 1;
-        dstate_len = gs_div_up(dhist_len, GS_SCAN_TILE) + 1;
-        dstate = c.take<unsigned long long>(dstate_len);
-        zero_bytes = c.off;  // header + scan state are zeroed at the start of every frame
+        sort_chunks = gs_div_up(P, GS_SORT_CHUNK);
+        row_chunks = gs_div_up(P, GS_PART_CHUNK);
+        dhist = c.take<uint32_t>(4 * GS_RADIX);
+        dstat = c.take<uint32_t>(4 * sort_chunks * GS_RADIX);
+        rstat = c.take<uint32_t>(row_chunks * GS_MAX_GRID);
+        zero_bytes = c.off;  // header + histograms + look-back state are zeroed at the start of every frame
         rec = c.take<GsRec>(P);
         key[0] = c.take<uint32_t>(P); key[1] = c.take<uint32_t>(P);
         idx[0] = c.take<uint32_t>(P); idx[1] = c.take<uint32_t>(P);
@@ -96,52 +105,48 @@ struct GsGeom {
         ntile = c.take<uint32_t>(P);
         cov3D = c.take<float>(6 * P);
         clamp = c.take<uint8_t>(P);
-        dhist = c.take<uint32_t>(dhist_len);
         bytes = c.off + GS_ALIGN;
     }
 };
 
 struct GsBinning {
-    unsigned long long* state1;  // look-back state of the two tile-pass scans (first: one memset)
-    unsigned long long* state2;
-    uint32_t* stage;
-    uint32_t* list;
-    uint32_t* hist1;  // [256][emit_units] (+1): per-warp low-digit histogram of tile pass 1
-    uint32_t* hist2;  // [256][units2]     (+1): per-warp high-digit histogram of tile pass 2
-    uint32_t* bucket_unit0;  // [257] first pass-2 unit of each low-digit bucket
-    size_t emit_units, units2, hist1_len, hist2_len, state1_len, state2_len, zero_bytes, bytes;
-    __host__ __device__ GsBinning(char* base, size_t Rcap, size_t P) {
+    uint32_t* list;    // [Rcap]
+    uint32_t* cstat;   // [col_chunks][GS_MAX_GRID]
+    uint2* items;      // [RowCap]
+    size_t col_chunks, zero_off, zero_bytes, bytes;
+    // Rcap = instance capacity, RowCap = row-item capacity (<= Rcap always holds for the true counts)
+    __host__ __device__ GsBinning(char* base, size_t Rcap, size_t RowCap) {
         GsCarver c(base);
-        emit_units = gs_div_up(P, GS_EMIT_UNIT);
-        hist1_len = GS_RADIX * emit_units + 1;
-        units2 = gs_div_up(Rcap, GS_TILE2_UNIT) + GS_RADIX;
-        hist2_len = GS_RADIX * units2 + 1;
-        state1_len = gs_div_up(hist1_len, GS_SCAN_TILE) + 1;
-        state2_len = gs_div_up(hist2_len, GS_SCAN_TILE) + 1;
-        state1 = c.take<unsigned long long>(state1_len);
-        state2 = c.take<unsigned long long>(state2_len);
-        zero_bytes = c.off;
-        stage = c.take<uint32_t>(Rcap);
         list = c.take<uint32_t>(Rcap);
-        hist1 = c.take<uint32_t>(hist1_len);
-        hist2 = c.take<uint32_t>(hist2_len);
-        bucket_unit0 = c.take<uint32_t>(GS_RADIX + 1);
+        col_chunks = gs_div_up(RowCap, GS_PART_CHUNK) + GS_MAX_GRID;
+        cstat = c.take<uint32_t>(col_chunks * GS_MAX_GRID);
+        zero_off = (size_t)(reinterpret_cast<char*>(cstat) - base);
+        zero_bytes = c.off - zero_off;
+        items = c.take<uint2>(RowCap);
         bytes = c.off + GS_ALIGN;
     }
 };
 
 struct GsImage {
+    int* rdiff;        // [gy+1]
+    uint32_t* tcount;  // [Tn]
     float* final_T;
     uint32_t* n_contrib;
     uint2* ranges;
     uint32_t* order;  // tiles of the shard, longest instance list first (blend work queue)
-    size_t bytes;
-    __host__ __device__ GsImage(char* base, size_t N, size_t Tn) {
+    uint32_t* tile_start;   // [Tn+1]
+    size_t zero_bytes, bytes;
+    __host__ __device__ GsImage(char* base, size_t N, size_t gx, size_t gy) {
         GsCarver c(base);
+        const size_t Tn = gx * gy;
+        rdiff = c.take<int>(gy + 1);
+        tcount = c.take<uint32_t>(Tn);
+        zero_bytes = c.off;
         final_T = c.take<float>(N);
         n_contrib = c.take<uint32_t>(N);
         ranges = c.take<uint2>(Tn);
         order = c.take<uint32_t>(Tn);
+        tile_start = c.take<uint32_t>(Tn + 1);
         bytes = c.off + GS_ALIGN;
     }
 };
@@ -154,17 +159,16 @@ struct GsFrame {  // host-side derived quantities handed to every launcher
     GsScene s;
     int gx, gy, Tn;        // tile grid
     int row0, row1;        // tile-row shard
-    int tile_bits, hi_bits, idx_bits;
     float focal_x, focal_y;
     cudaStream_t stream;
 };
 
 // stage launchers (each in its own translation unit)
-cudaError_t gs_launch_preprocess(const GsFrame& f, const GsGeom& g, int32_t* radii);
-cudaError_t gs_launch_depth_sort(const GsFrame& f, const GsGeom& g, int* sorted_side);
-cudaError_t gs_launch_tile_binning(const GsFrame& f, const GsGeom& g, int sorted_side, const GsBinning& b,
-                                   size_t Rcap, const GsImage& im);
-cudaError_t gs_launch_tile_order(const GsFrame& f, const GsGeom& g, const GsBinning& b, size_t Rcap, const GsImage& im);
+cudaError_t gs_launch_preprocess(const GsFrame& f, const GsGeom& g, const GsImage& im, int32_t* radii);
+cudaError_t gs_launch_depth_sort(const GsFrame& f, const GsGeom& g);  // result in g.key[0] / g.idx[0]
+// row pass -> column histogram -> plan (ranges, tile_start, blend queue) -> column pass
+cudaError_t gs_launch_tile_lists(const GsFrame& f, const GsGeom& g, const GsBinning& b, size_t Rcap, size_t RowCap,
+                                 const GsImage& im);
 cudaError_t gs_launch_blend_forward(const GsFrame& f, const GsGeom& g, const GsBinning& b, const GsImage& im,
                                     float* out_color);
 cudaError_t gs_launch_blend_backward(const GsFrame& f, const GsGeom& g, const GsBinning& b, const GsImage& im,

@@ -20,7 +20,8 @@ struct PreArgs {
     const float* means; const float* scales; const float* rots; const float* opac; const float* shs;
     const float* cov3D_pre; const float* colors_pre; const float* view; const float* proj; const float* campos;
     int32_t* radii;
-    GsRec* rec; uint32_t* key; uint32_t* idx; ushort4* rect; uint32_t* ntile; float* cov3D; uint8_t* clamp;
+    GsRec* rec; uint32_t* key; ushort4* rect; uint32_t* ntile; float* cov3D; uint8_t* clamp;
+    int* rdiff;
     GsHeader* hdr;
 };
 
@@ -61,8 +62,11 @@ __device__ __forceinline__ float3 sh_to_rgb(int deg, const float* __restrict__ s
 
 __global__ void __launch_bounds__(256) preprocess_kernel(const PreArgs a) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned my_tiles = 0, my_vis = 0;
+    unsigned my_tiles = 0, my_vis = 0, my_rows = 0;
     bool bad = false;
+    __shared__ int s_rd[GS_MAX_GRID + 1];  // this block's share of the row difference array
+    for (int y = threadIdx.x; y <= a.gy; y += 256) s_rd[y] = 0;
+    __syncthreads();
     if (i < a.P) {
         int radius_out = 0;
         uint32_t key = 0xFFFFFFFFu;  // culled Gaussians sort to the end of the depth order
@@ -136,35 +140,44 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreArgs a) {
             if (y1 > y0) {
                 rect = make_ushort4((unsigned short)x0, (unsigned short)y0, (unsigned short)x1, (unsigned short)y1);
                 my_tiles = (unsigned)((y1 - y0) * (x1 - x0));
+                my_rows = (unsigned)(y1 - y0);
+                // row difference array, integrated by the row pass (binning.cu) into items per tile row
+                atomicAdd(&s_rd[y0], 1);
+                atomicAdd(&s_rd[y1], -1);
             }
             key = __float_as_uint(p_view.z);
             my_vis = 1;
         } while (false);
         if (a.radii) a.radii[i] = radius_out;
         a.key[i] = key;
-        a.idx[i] = (uint32_t)i;
         a.rect[i] = rect;
         a.ntile[i] = my_tiles;
     }
     // block reduction of the instance / visible counts -> two atomics per block
-    __shared__ unsigned s_t[8], s_v[8];
-    unsigned t = my_tiles, v = my_vis;
+    __shared__ unsigned s_t[8], s_v[8], s_r[8];
+    unsigned t = my_tiles, v = my_vis, r = my_rows;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         t += __shfl_xor_sync(GS_FULL, t, o);
         v += __shfl_xor_sync(GS_FULL, v, o);
+        r += __shfl_xor_sync(GS_FULL, r, o);
     }
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-    if (l == 0) { s_t[w] = t; s_v[w] = v; }
+    if (l == 0) { s_t[w] = t; s_v[w] = v; s_r[w] = r; }
     if (__syncthreads_or(bad)) {
         if (threadIdx.x == 0) a.hdr->code = GS_ERR_PREFILTERED;
     }
     if (threadIdx.x == 0) {
         unsigned long long tt = 0;
-        unsigned vv = 0;
-        for (int k = 0; k < 8; k++) { tt += s_t[k]; vv += s_v[k]; }
+        unsigned vv = 0, rr = 0;
+        for (int k = 0; k < 8; k++) { tt += s_t[k]; vv += s_v[k]; rr += s_r[k]; }
         if (tt) atomicAdd(&a.hdr->num_rendered, tt);
         if (vv) atomicAdd(&a.hdr->num_visible, vv);
+        if (rr) atomicAdd(&a.hdr->num_row_items, rr);
+    }
+    for (int y = threadIdx.x; y <= a.gy; y += 256) {  // the __syncthreads_or above ordered the shared atomics
+        const int d = s_rd[y];
+        if (d) atomicAdd(&a.rdiff[y], d);
     }
 }
 
@@ -178,7 +191,7 @@ __global__ void mark_visible_kernel(int P, const float* __restrict__ means, cons
 
 }  // namespace
 
-cudaError_t gs_launch_preprocess(const GsFrame& f, const GsGeom& g, int32_t* radii) {
+cudaError_t gs_launch_preprocess(const GsFrame& f, const GsGeom& g, const GsImage& im, int32_t* radii) {
     const GsScene& s = f.s;
     PreArgs a;
     a.P = s.P; a.D = s.sh_degree; a.M = s.sh_stride; a.W = s.width; a.H = s.height; a.gx = f.gx; a.gy = f.gy;
@@ -189,8 +202,8 @@ cudaError_t gs_launch_preprocess(const GsFrame& f, const GsGeom& g, int32_t* rad
     a.cov3D_pre = s.cov3D_precomp; a.colors_pre = s.colors_precomp; a.view = s.viewmatrix; a.proj = s.projmatrix;
     a.campos = s.campos;
     a.radii = radii;
-    a.rec = g.rec; a.key = g.key[0]; a.idx = g.idx[0]; a.rect = g.rect; a.ntile = g.ntile; a.cov3D = g.cov3D;
-    a.clamp = g.clamp; a.hdr = g.hdr;
+    a.rec = g.rec; a.key = g.key[0]; a.rect = g.rect; a.ntile = g.ntile; a.cov3D = g.cov3D;
+    a.clamp = g.clamp; a.rdiff = im.rdiff; a.hdr = g.hdr;
     preprocess_kernel<<<(unsigned)gs_div_up(s.P, 256), 256, 0, f.stream>>>(a);
     gs_note_launch();
     return cudaGetLastError();
