@@ -39,11 +39,26 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
     return v;
 }
 
+// Lanes of `act` holding the same BITS-bit value as this lane.  MATCH.ANY serialises over the distinct values in
+// the warp (measured on B200: ~10x slower when all 32 lanes differ, which is the common case for radix digits and
+// tile rows), BITS ballots cost the same for every input.
+template <int BITS>
+__device__ __forceinline__ unsigned match_bits(unsigned act, unsigned v) {
+    unsigned m = act;
+#pragma unroll
+    for (int b = 0; b < BITS; b++) {
+        const bool bit = (v >> b) & 1u;
+        const unsigned bal = __ballot_sync(act, bit);
+        m &= bit ? bal : ~bal;
+    }
+    return m;
+}
+
 // Decoupled look-back for one bin: sums the aggregates of chunks chunk-1, chunk-2, ... >= first until a chunk with
 // an inclusive prefix is met.  Status words carry flag (2 bits) + count (30 bits), so no fence is needed.
 // All chunks of a pass usually run concurrently (a few hundred CTAs), so walks are long: the predecessors are read
-// GS_LB at a time (independent loads in flight) instead of one L2 round trip per step.
-#define GS_LB 16
+// LB at a time (independent loads in flight) instead of one L2 round trip per step.
+template <int GS_LB>
 __device__ __forceinline__ unsigned look_back(const unsigned* __restrict__ status, int stride, int chunk, int first,
                                               int bin) {
     unsigned excl = 0;
@@ -102,71 +117,78 @@ __device__ __forceinline__ int chunk_row(const uint32_t* s_cf, int gy, uint32_t 
 
 // ---------------------------------------------------------------------------------------------------
 // Depth sort.  Histograms of all four digits in one pass over the keys.
-__global__ void __launch_bounds__(256) depth_hist_kernel(const uint32_t* __restrict__ key, uint32_t P,
-                                                         uint32_t* __restrict__ hist) {
+__global__ void __launch_bounds__(1024) depth_hist_kernel(const uint32_t* __restrict__ key, uint32_t P,
+                                                          uint32_t* __restrict__ hist) {
     __shared__ uint32_t s[4][GS_RADIX];
     const int tid = threadIdx.x, lane = tid & 31;
-#pragma unroll
-    for (int p = 0; p < 4; p++) s[p][tid] = 0;
+    (&s[0][0])[tid] = 0;
     __syncthreads();
-    const uint32_t stride = gridDim.x * 256u;
+    const uint32_t stride = gridDim.x * 1024u;
     const uint32_t iters = (uint32_t)gs_div_up(P, stride);
-    for (uint32_t it = 0; it < iters; it++) {  // whole warps iterate together (match needs converged lanes)
-        const uint32_t i = it * stride + blockIdx.x * 256u + tid;
-        const bool valid = i < P;
-        const uint32_t k = valid ? key[i] : 0u;
-        const unsigned act = __ballot_sync(GS_FULL, valid);
-        if (valid) {
+    for (uint32_t it0 = 0; it0 < iters; it0 += 4) {  // whole warps iterate together; 4 independent loads in flight
+        uint32_t k[4];
+        bool valid[4];
 #pragma unroll
-            for (int p = 0; p < 4; p++) {
-                const uint32_t d = (k >> (8 * p)) & 255u;
-                if (p < 2) {
-                    atomicAdd(&s[p][d], 1u);  // low digits: nearly uniform, few conflicts
-                } else {                      // high digits: heavily repeated, aggregate within the warp first
-                    const unsigned m = __match_any_sync(act, d);
-                    if (lane == __ffs(m) - 1) atomicAdd(&s[p][d], (uint32_t)__popc(m));
+        for (int u = 0; u < 4; u++) {
+            const uint32_t i = (it0 + u) * stride + blockIdx.x * 1024u + tid;
+            valid[u] = (it0 + u) < iters && i < P;
+            k[u] = valid[u] ? key[i] : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const unsigned act = __ballot_sync(GS_FULL, valid[u]);
+            if (valid[u]) {
+#pragma unroll
+                for (int p = 0; p < 4; p++) {
+                    const uint32_t d = (k[u] >> (8 * p)) & 255u;
+                    if (p < 2) {
+                        atomicAdd(&s[p][d], 1u);  // low digits: nearly uniform, few conflicts
+                    } else {                      // high digits: heavily repeated, aggregate within the warp first
+                        const unsigned m = match_bits<8>(act, d);
+                        if (lane == __ffs(m) - 1) atomicAdd(&s[p][d], (uint32_t)__popc(m));
+                    }
                 }
             }
         }
     }
     __syncthreads();
-#pragma unroll
-    for (int p = 0; p < 4; p++) {
-        const uint32_t v = s[p][tid];
-        if (v) atomicAdd(&hist[p * GS_RADIX + tid], v);
-    }
+    const uint32_t v = (&s[0][0])[tid];
+    if (v) atomicAdd(&hist[tid], v);
 }
 
 // One LSD pass, onesweep style: a CTA owns GS_SORT_CHUNK consecutive keys (warp w the w-th 512, round r of a warp
-// the r-th 32), ranks them by digit with __match_any_sync + per-warp counters (stable: rounds in order, lanes in
+// the r-th 32), ranks them by digit with a ballot-based match + per-warp counters (stable: rounds in order, lanes in
 // order), obtains the number of equal-digit keys in all earlier chunks by decoupled look-back, and scatters.
-#define SORT_ROUNDS (GS_SORT_CHUNK / 256)
-__global__ void __launch_bounds__(256) depth_pass_kernel(const uint32_t* __restrict__ key_in,
-                                                         const uint32_t* __restrict__ idx_in,
-                                                         uint32_t* __restrict__ key_out, uint32_t* __restrict__ idx_out,
-                                                         const uint32_t* __restrict__ hist,  // this pass' 256 totals
-                                                         unsigned* __restrict__ status,      // [chunks][256]
-                                                         unsigned* __restrict__ ticket, uint32_t P, int shift,
-                                                         int first_pass) {
-    __shared__ uint32_t s_cnt[8][GS_RADIX];
+#define SORT_THREADS 512
+#define SORT_WARPS (SORT_THREADS / 32)
+#define SORT_ROUNDS (GS_SORT_CHUNK / SORT_THREADS)
+__global__ void __launch_bounds__(SORT_THREADS) depth_pass_kernel(const uint32_t* __restrict__ key_in,
+                                                                  const uint32_t* __restrict__ idx_in,
+                                                                  uint32_t* __restrict__ key_out,
+                                                                  uint32_t* __restrict__ idx_out,
+                                                                  const uint32_t* __restrict__ hist,  // 256 totals
+                                                                  unsigned* __restrict__ status,  // [chunks][256]
+                                                                  unsigned* __restrict__ ticket, uint32_t P, int shift,
+                                                                  int first_pass) {
+    __shared__ uint32_t s_cnt[SORT_WARPS][GS_RADIX];
     __shared__ uint32_t s_base[GS_RADIX];
     __shared__ uint32_t s_wsum[8];
     __shared__ uint32_t s_chunk;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_chunk = atomicAdd(ticket, 1u);
-#pragma unroll
-    for (int w = 0; w < 8; w++) s_cnt[w][tid] = 0;
+    for (int i = tid; i < SORT_WARPS * GS_RADIX; i += SORT_THREADS) (&s_cnt[0][0])[i] = 0;
     __syncthreads();
     const uint32_t chunk = s_chunk;
-    const uint32_t base = chunk * GS_SORT_CHUNK + warp * (GS_SORT_CHUNK / 8);
+    const uint32_t base = chunk * GS_SORT_CHUNK + warp * (GS_SORT_CHUNK / SORT_WARPS);
 
-    uint32_t k[SORT_ROUNDS];
+    uint32_t k[SORT_ROUNDS], v[SORT_ROUNDS];
     uint16_t rk[SORT_ROUNDS];
     uint32_t* cnt = s_cnt[warp];
 #pragma unroll
     for (int r = 0; r < SORT_ROUNDS; r++) {
         const uint32_t i = base + r * 32 + lane;
         k[r] = (i < P) ? key_in[i] : 0xFFFFFFFFu;
+        v[r] = (first_pass || i >= P) ? i : idx_in[i];
     }
 #pragma unroll
     for (int r = 0; r < SORT_ROUNDS; r++) {
@@ -176,7 +198,7 @@ __global__ void __launch_bounds__(256) depth_pass_kernel(const uint32_t* __restr
         const unsigned act = __ballot_sync(GS_FULL, valid);
         uint32_t off = 0;
         if (valid) {
-            const unsigned m = __match_any_sync(act, d);
+            const unsigned m = match_bits<8>(act, d);
             const unsigned before = __popc(m & ((1u << lane) - 1u));
             const uint32_t c0 = cnt[d];
             __syncwarp(act);
@@ -187,30 +209,32 @@ __global__ void __launch_bounds__(256) depth_pass_kernel(const uint32_t* __restr
         rk[r] = (uint16_t)off;
     }
     __syncthreads();
-    // thread d: exclusive scan of digit d over the 8 warps, CTA total, look-back, global digit base
-    uint32_t total = 0;
+    // thread d < 256: exclusive scan of digit d over the warps, CTA total, look-back, global digit base
+    if (tid < GS_RADIX) {
+        uint32_t total = 0;
 #pragma unroll
-    for (int w = 0; w < 8; w++) {
-        const uint32_t t = s_cnt[w][tid];
-        s_cnt[w][tid] = total;
-        total += t;
-    }
-    st_volatile_u32(status + (size_t)chunk * GS_RADIX + tid, (chunk == 0 ? ST_INC : ST_AGG) | total);
-    // exclusive scan of the global digit totals over the 256 digits (one per thread)
-    const uint32_t h = hist[tid];
-    const uint32_t incl = warp_incl_scan(h, lane);
-    if (lane == 31) s_wsum[warp] = incl;
-    __syncthreads();
-    uint32_t wpre = 0;
+        for (int w = 0; w < SORT_WARPS; w++) {
+            const uint32_t t = s_cnt[w][tid];
+            s_cnt[w][tid] = total;
+            total += t;
+        }
+        st_volatile_u32(status + (size_t)chunk * GS_RADIX + tid, (chunk == 0 ? ST_INC : ST_AGG) | total);
+        // exclusive scan of the global digit totals over the 256 digits (one per thread)
+        const uint32_t h = hist[tid];
+        const uint32_t incl = warp_incl_scan(h, lane);
+        if (lane == 31) s_wsum[warp] = incl;
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // only the first 8 warps take part
+        uint32_t wpre = 0;
 #pragma unroll
-    for (int w = 0; w < 8; w++)
-        if (w < warp) wpre += s_wsum[w];
-    uint32_t excl = 0;
-    if (chunk > 0) {
-        excl = look_back(status, GS_RADIX, (int)chunk, 0, tid);
-        st_volatile_u32(status + (size_t)chunk * GS_RADIX + tid, ST_INC | (excl + total));
+        for (int w = 0; w < 8; w++)
+            if (w < warp) wpre += s_wsum[w];
+        uint32_t excl = 0;
+        if (chunk > 0) {
+            excl = look_back<16>(status, GS_RADIX, (int)chunk, 0, tid);
+            st_volatile_u32(status + (size_t)chunk * GS_RADIX + tid, ST_INC | (excl + total));
+        }
+        s_base[tid] = wpre + incl - h + excl;
     }
-    s_base[tid] = wpre + incl - h + excl;
     __syncthreads();
 #pragma unroll
     for (int r = 0; r < SORT_ROUNDS; r++) {
@@ -219,7 +243,7 @@ __global__ void __launch_bounds__(256) depth_pass_kernel(const uint32_t* __restr
             const uint32_t d = (k[r] >> shift) & 255u;
             const uint32_t pos = s_base[d] + cnt[d] + rk[r];
             key_out[pos] = k[r];
-            idx_out[pos] = first_pass ? i : idx_in[i];
+            idx_out[pos] = v[r];
         }
     }
 }
@@ -302,7 +326,8 @@ __global__ void __launch_bounds__(1024) plan_kernel(const uint32_t* __restrict__
             const uint32_t len = over ? 0u : c;
             ranges[t] = over ? make_uint2(0u, 0u) : make_uint2(run, run + c);
             const int cls = len ? 32 - __clz(len) : 0;  // 0 = empty, 1..32
-            atomicAdd(&s_cnt[32 - cls], 1u);            // slot 0 = longest class
+            const unsigned m = match_bits<6>(__activemask(), (unsigned)cls);  // most tiles are empty: aggregate per warp
+            if (lane == __ffs(m) - 1) atomicAdd(&s_cnt[32 - cls], (uint32_t)__popc(m));  // slot 0 = longest class
         }
         run += c;
     }
@@ -317,7 +342,11 @@ __global__ void __launch_bounds__(1024) plan_kernel(const uint32_t* __restrict__
         if (t >= s0 && t < s1) {
             const uint32_t len = over ? 0u : tcount[t];
             const int cls = len ? 32 - __clz(len) : 0;
-            const uint32_t slot = atomicAdd(&s_slot[32 - cls], 1u);
+            const unsigned m = match_bits<6>(__activemask(), (unsigned)cls);
+            const int leader = __ffs(m) - 1;
+            uint32_t slot = 0;
+            if (lane == leader) slot = atomicAdd(&s_slot[32 - cls], (uint32_t)__popc(m));
+            slot = __shfl_sync(m, slot, leader) + __popc(m & ((1u << lane) - 1u));
             order[slot] = (uint32_t)t;
         }
     }
@@ -328,18 +357,25 @@ __global__ void __launch_bounds__(1024) plan_kernel(const uint32_t* __restrict__
 // Every input item covers the bin range [lo, hi) and emits one output element into each covered bin; elements of a
 // bin keep the input order.  A CTA owns a chunk of GS_PART_CHUNK consecutive items (warp w the w-th 256, round r the
 // r-th 32).  NB = number of bins rounded up to 128 or 256.
+//
+// Ranking without a key per element: for a round of 32 items, T[b] = (lanes whose range starts at b) xor (lanes whose
+// range ends at b); the prefix-xor of T over the bins is, for every bin, the bitmask of lanes covering it, so the
+// stable rank of lane i's element in bin b is popc(mask[b] & lanes_below_i) + the elements of earlier rounds /
+// warps / chunks.  T is built with two ballot-based matches per round (group leaders store; no shared-memory atomics).
 #define PART_ROUNDS (GS_PART_CHUNK / 256)
 
 template <int NB, int PASS>
-__global__ void __launch_bounds__(256) range_partition_kernel(
+__global__ void __launch_bounds__(256, (NB == 128) ? 4 : 2) range_partition_kernel(
     const uint32_t* __restrict__ sorted_idx, const ushort4* __restrict__ rect, uint32_t P,  // PASS 1 input
     const uint2* __restrict__ items_in,                                                      // PASS 2 input
     const int* __restrict__ rdiff, int gx, int gy, const uint32_t* __restrict__ tile_start,
     unsigned long long RowCap, unsigned* __restrict__ status, int stat_stride, unsigned* __restrict__ ticket,
     GsHeader* __restrict__ hdr, uint2* __restrict__ items_out, uint32_t* __restrict__ list_out) {
-    constexpr int G = NB / 32;  // bins per lane in the warp-wide scans
-    __shared__ int s_cnt[8][NB + 1];        // per-warp: difference array -> counts -> running output positions
-    __shared__ uint32_t s_mask[8][NB + 1];  // per-warp, per round: bit i set = item of lane i covers the bin
+    constexpr int G = NB / 32;    // bins per lane in the warp-wide scans
+    constexpr int MS = NB + 4;    // mask row stride (words), multiple of 4 for the vectorised clear
+    extern __shared__ __align__(16) uint32_t s_dyn[];
+    uint32_t* s_mask = s_dyn;                                         // [8 warps][PART_ROUNDS][MS]
+    int* s_cnt = reinterpret_cast<int*>(s_dyn + 8 * PART_ROUNDS * MS);  // [8 warps][NB]: counts -> output positions
     __shared__ uint32_t s_rs[GS_MAX_GRID + 1], s_cf[GS_MAX_GRID + 1];
     __shared__ uint32_t s_chunk;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -351,14 +387,17 @@ __global__ void __launch_bounds__(256) range_partition_kernel(
         return;
     }
     const uint32_t nchunks = (PASS == 1) ? (uint32_t)gs_div_up(P, GS_PART_CHUNK) : s_cf[gy];
-    int* cnt = s_cnt[warp];
-    uint32_t* msk = s_mask[warp];
-    const unsigned lt = (1u << lane) - 1u, bit = 1u << lane;
+    int* cnt = s_cnt + warp * NB;
+    uint32_t* msk = s_mask + warp * (PART_ROUNDS * MS);
+    const unsigned lt = (1u << lane) - 1u;
 
     while (true) {
         __syncthreads();  // previous chunk's shared state is dead
         if (tid == 0) s_chunk = atomicAdd(ticket, 1u);
-        for (int i = tid; i < 8 * (NB + 1); i += 256) (&s_cnt[0][0])[i] = 0;
+        {   // clear this warp's toggle rows
+            uint4* z = reinterpret_cast<uint4*>(msk);
+            for (int i = lane; i < PART_ROUNDS * MS / 4; i += 32) z[i] = make_uint4(0u, 0u, 0u, 0u);
+        }
         __syncthreads();
         const uint32_t chunk = s_chunk;
         if (chunk >= nchunks) break;
@@ -376,7 +415,7 @@ __global__ void __launch_bounds__(256) range_partition_kernel(
             iend = min(s_rs[row + 1], ibeg + (uint32_t)GS_PART_CHUNK);
         }
 
-        // ---- phase A: load items, per-warp difference arrays
+        // ---- phase A: load items; toggle rows; masks; per-warp counts
         uint32_t pay[PART_ROUNDS], rng[PART_ROUNDS];  // payload (gaussian), lo | hi << 16
         uint32_t xr[PASS == 1 ? PART_ROUNDS : 1];
 #pragma unroll
@@ -399,19 +438,59 @@ __global__ void __launch_bounds__(256) range_partition_kernel(
                 if (hi <= lo) { lo = 0; hi = 0; }
             }
             rng[r] = lo | (hi << 16);
+        }
+#pragma unroll
+        for (int r = 0; r < PART_ROUNDS; r++) {  // range starts: one store per distinct start bin
+            const uint32_t lo = rng[r] & 0xffffu, hi = rng[r] >> 16;
+            const unsigned act = __ballot_sync(GS_FULL, hi > lo);
             if (hi > lo) {
-                atomicAdd(&cnt[lo], 1);
-                atomicAdd(&cnt[hi], -1);
+                const unsigned m = match_bits<(NB == 128) ? 8 : 9>(act, lo);
+                if ((m & lt) == 0) msk[r * MS + lo] = m;
             }
         }
         __syncwarp();
-        {   // per-warp prefix sum over the bins: difference array -> number of this warp's items covering each bin
-            int v[G], sum = 0;
 #pragma unroll
-            for (int j = 0; j < G; j++) { sum += cnt[lane * G + j]; v[j] = sum; }
-            const int pre = (int)warp_incl_scan((uint32_t)sum, lane) - sum;
+        for (int r = 0; r < PART_ROUNDS; r++) {  // range ends: xor into the row (one writer per distinct end bin)
+            const uint32_t lo = rng[r] & 0xffffu, hi = rng[r] >> 16;
+            const unsigned act = __ballot_sync(GS_FULL, hi > lo);
+            if (hi > lo) {
+                const unsigned m = match_bits<(NB == 128) ? 8 : 9>(act, hi);
+                if ((m & lt) == 0) msk[r * MS + hi] ^= m;
+            }
+        }
+        __syncwarp();
+        {
+            int csum[G];
 #pragma unroll
-            for (int j = 0; j < G; j++) cnt[lane * G + j] = v[j] + pre;
+            for (int j = 0; j < G; j++) csum[j] = 0;
+#pragma unroll
+            for (int r = 0; r < PART_ROUNDS; r++) {  // prefix-xor over the bins -> covering masks
+                uint32_t m[G], acc = 0;
+                if (G == 4) {
+                    const uint4 q = *reinterpret_cast<const uint4*>(&msk[r * MS + lane * 4]);
+                    m[0] = q.x; m[1] = q.y; m[2] = q.z; m[3] = q.w;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < G; j++) m[j] = msk[r * MS + lane * G + j];
+                }
+#pragma unroll
+                for (int j = 0; j < G; j++) { acc ^= m[j]; m[j] = acc; }
+                uint32_t sc = acc;  // inclusive xor-scan of the lane totals
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t t = __shfl_up_sync(GS_FULL, sc, o);
+                    if (lane >= o) sc ^= t;
+                }
+                const uint32_t pre = sc ^ acc;
+#pragma unroll
+                for (int j = 0; j < G; j++) {
+                    m[j] ^= pre;
+                    msk[r * MS + lane * G + j] = m[j];
+                    csum[j] += __popc(m[j]);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < G; j++) cnt[lane * G + j] = csum[j];
         }
         __syncthreads();
         // ---- phase B: thread b = bin b: scan over warps, chunk aggregate, look-back, output base
@@ -420,8 +499,8 @@ __global__ void __launch_bounds__(256) range_partition_kernel(
             uint32_t total = 0;
 #pragma unroll
             for (int w = 0; w < 8; w++) {
-                const uint32_t t = (uint32_t)s_cnt[w][tid];
-                s_cnt[w][tid] = (int)total;
+                const uint32_t t = (uint32_t)s_cnt[w * NB + tid];
+                s_cnt[w * NB + tid] = (int)total;
                 total += t;
             }
             uint32_t basev = 0;
@@ -431,49 +510,28 @@ __global__ void __launch_bounds__(256) range_partition_kernel(
                 st_volatile_u32(st, (head ? ST_INC : ST_AGG) | total);
                 uint32_t excl = 0;
                 if (!head) {
-                    excl = look_back(status, stat_stride, (int)chunk, first, tid);
+                    excl = look_back<8>(status, stat_stride, (int)chunk, first, tid);
                     st_volatile_u32(st, ST_INC | (excl + total));
                 }
                 basev = excl + ((PASS == 1) ? s_rs[tid] : tile_start[row * gx + tid]);
             }
 #pragma unroll
-            for (int w = 0; w < 8; w++) s_cnt[w][tid] += (int)basev;
+            for (int w = 0; w < 8; w++) s_cnt[w * NB + tid] += (int)basev;
         }
         __syncthreads();
-        // ---- phase C: round by round, bitmask of covering items per bin -> stable ranks -> scatter
+        // ---- phase C: scatter, round by round (positions of a bin advance by the round's population)
 #pragma unroll
         for (int r = 0; r < PART_ROUNDS; r++) {
-#pragma unroll
-            for (int j = 0; j < G; j++) msk[lane * G + j] = 0;
-            if (lane == 0) msk[NB] = 0;
-            __syncwarp();
             const uint32_t lo = rng[r] & 0xffffu, hi = rng[r] >> 16;
-            if (hi > lo) {
-                atomicXor(&msk[lo], bit);
-                atomicXor(&msk[hi], bit);
-            }
-            __syncwarp();
-            uint32_t m[G], acc = 0;
-#pragma unroll
-            for (int j = 0; j < G; j++) { acc ^= msk[lane * G + j]; m[j] = acc; }
-            uint32_t sc = acc;  // inclusive xor-scan of the lane totals
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t t = __shfl_up_sync(GS_FULL, sc, o);
-                if (lane >= o) sc ^= t;
-            }
-            const uint32_t pre = sc ^ acc;
-#pragma unroll
-            for (int j = 0; j < G; j++) { m[j] ^= pre; msk[lane * G + j] = m[j]; }
-            __syncwarp();
             for (uint32_t b = lo; b < hi; b++) {
-                const uint32_t pos = (uint32_t)cnt[b] + __popc(msk[b] & lt);
+                const uint32_t pos = (uint32_t)cnt[b] + __popc(msk[r * MS + b] & lt);
                 if (PASS == 1) items_out[pos] = make_uint2(pay[r], xr[PASS == 1 ? r : 0]);
                 else list_out[pos] = pay[r];
             }
             __syncwarp();
 #pragma unroll
-            for (int j = 0; j < G; j++) cnt[lane * G + j] += __popc(m[j]);
+            for (int j = 0; j < G; j++) cnt[lane * G + j] += __popc(msk[r * MS + lane * G + j]);
+            __syncwarp();
         }
     }
 }
@@ -485,12 +543,12 @@ __global__ void __launch_bounds__(256) range_partition_kernel(
 cudaError_t gs_launch_depth_sort(const GsFrame& f, const GsGeom& g) {
     const uint32_t P = (uint32_t)f.s.P;
     const unsigned chunks = (unsigned)g.sort_chunks;
-    depth_hist_kernel<<<(unsigned)min((size_t)296, gs_div_up(P, 2048)), 256, 0, f.stream>>>(g.key[0], P, g.dhist);
+    depth_hist_kernel<<<(unsigned)min((size_t)64, gs_div_up(P, 8192)), 1024, 0, f.stream>>>(g.key[0], P, g.dhist);
     gs_note_launch();
     GS_TRY(cudaGetLastError());
     int side = 0;
     for (int pass = 0; pass < 4; pass++) {
-        depth_pass_kernel<<<chunks, 256, 0, f.stream>>>(g.key[side], g.idx[side], g.key[side ^ 1], g.idx[side ^ 1],
+        depth_pass_kernel<<<chunks, SORT_THREADS, 0, f.stream>>>(g.key[side], g.idx[side], g.key[side ^ 1], g.idx[side ^ 1],
                                                        g.dhist + pass * GS_RADIX,
                                                        g.dstat + (size_t)pass * chunks * GS_RADIX,
                                                        &g.hdr->tickets[pass], P, pass * GS_RADIX_BITS, pass == 0);
@@ -501,6 +559,7 @@ cudaError_t gs_launch_depth_sort(const GsFrame& f, const GsGeom& g) {
     return cudaSuccess;  // four passes: the sorted order is back in key[0] / idx[0]
 }
 
+#define PART_SMEM(NB) ((8 * PART_ROUNDS * ((NB) + 4) + 8 * (NB)) * 4)
 static int g_part_grid = 0;
 
 cudaError_t gs_launch_tile_lists(const GsFrame& f, const GsGeom& g, const GsBinning& b, size_t Rcap, size_t RowCap,
@@ -510,13 +569,15 @@ cudaError_t gs_launch_tile_lists(const GsFrame& f, const GsGeom& g, const GsBinn
         int dev = 0, sms = 0;
         GS_TRY(cudaGetDevice(&dev));
         GS_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        g_part_grid = sms * 8;
+        GS_TRY(cudaFuncSetAttribute(range_partition_kernel<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PART_SMEM(256)));
+        GS_TRY(cudaFuncSetAttribute(range_partition_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, PART_SMEM(256)));
+        g_part_grid = sms * 4;
     }
     const unsigned grid1 = (unsigned)min((size_t)g_part_grid, g.row_chunks);
     const unsigned grid2 = (unsigned)min((size_t)g_part_grid, b.col_chunks);
     const unsigned long long rowcap = RowCap;
 #define LAUNCH_PART(NB, PASS, GRID)                                                                               \
-    range_partition_kernel<NB, PASS><<<GRID, 256, 0, f.stream>>>(                                                 \
+    range_partition_kernel<NB, PASS><<<GRID, 256, PART_SMEM(NB), f.stream>>>(                                     \
         g.idx[0], g.rect, P, b.items, im.rdiff, f.gx, f.gy, im.tile_start, rowcap, (PASS == 1) ? g.rstat : b.cstat, \
         GS_MAX_GRID, &g.hdr->tickets[3 + PASS], g.hdr, b.items, b.list)
     // row pass: Gaussians in depth order -> row items grouped by tile row

@@ -4,7 +4,7 @@
 //   geometry buffer (per Gaussian, P entries)
 //     GsHeader            status block + counters (256 B)
 //     dhist [4][256] u32  digit histograms of the depth keys           } zeroed at the start of every frame
-//     dstat [4][C][256]   decoupled look-back state of the depth sort   } (C = ceil(P / 4096) chunks)
+//     dstat [4][C][256]   decoupled look-back state of the depth sort   } (C = ceil(P / 8192) chunks)
 //     rstat [C1][256]     look-back state of the row pass               } (C1 = ceil(P / 2048) chunks)
 //     rec   [P] GsRec     48-B packed record read by the blend kernels (3 x float4)
 //     key   [2][P] u32    depth-sort keys (float bits of view-space z; 0xFFFFFFFF = culled), ping/pong
@@ -70,7 +70,7 @@ struct GsCarver {
 // chunk sizes of the binning kernels (one CTA of 256 threads per chunk)
 #define GS_RADIX_BITS 8
 #define GS_RADIX 256
-#define GS_SORT_CHUNK 4096   // depth keys per CTA and pass
+#define GS_SORT_CHUNK 8192   // depth keys per CTA and pass
 #define GS_PART_CHUNK 2048   // items per CTA of the row / column partition passes
 #define GS_MAX_GRID 256      // at most 256 x 256 tiles (4096 x 4096 pixels)
 
