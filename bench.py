@@ -13,8 +13,12 @@ instance lists; the per-frame input set, 160 MB of Gaussian attributes, exceeds 
   roofline     : the blend-forward kernel; algorithmic bytes 40*sum(need_t) + 20*N + 8*Tn,
                  kernel time from CUDA events recorded inside the library on the launching stream.
   cpu_baseline : the C/OpenMP oracle port (oracle/gs_oracle.c) on this host's cores, bounded sample.
-N > 1: tile-row sharding of every frame: each rank bins + blends a work-balanced contiguous range
-of tile rows and the ranks assemble the image with one collective per frame ("scaling": "strong").
+N > 1, two ways to shard:
+  --parallel views (default): the frames of the orbit are independent units; rank r renders views r, r+N, r+2N, ...
+          with no data-path collective, every rank times K steps ("scaling": "weak", value = N*K frames / max time);
+  --parallel tiles: every frame is split by screen-space tile rows: each rank bins + blends a work-balanced
+          contiguous range of tile rows and one collective per frame assembles the image ("scaling": "strong").
+Frames are independent, so `--streams S` keeps S frames in flight on S CUDA streams (renderer.FramePipeline).
 --impl reference runs the UNMODIFIED reference CUDA rasterizer (oracle/_ref/libgs_ref.so, built from
 /root/reference by oracle/Makefile; the reference has no CPU implementation of this path) on the same workload.
 """
@@ -135,18 +139,20 @@ def algorithmic_blend_bytes(n_contrib_hw: torch.Tensor, W, H):
 # ------------------------------------------------------------------------------------------------------------
 def run_b200(args, rank, world):
     from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer, _C
-    from renderer import FrameRenderer
+    from renderer import FramePipeline, FrameRenderer
     dev = torch.device("cuda", torch.cuda.current_device())
     cloud, views, w = make_workload(args.workload)
     W, H = w["W"], w["H"]
     gy = (H + 15) // 16
     L = _C.lib()
-    fr = FrameRenderer(cloud, W, H, [1.0, 1.0, 1.0], dev)
+    tiles_mode = world > 1 and args.parallel == "tiles"
+    pipe = FramePipeline(cloud, W, H, [1.0, 1.0, 1.0], dev, depth=1 if tiles_mode else args.streams)
+    fr = pipe.lanes[0]
     vdev = [fr.upload_view(v) for v in views]
     nv = len(vdev)
 
     # calibration (untimed): instance capacity, per-view blend bytes, and per-view balanced row partitions
-    fr.calibrate(vdev[:: max(1, nv // 12)])
+    pipe.calibrate(vdev[:: max(1, nv // 12)])
     blend_bytes, parts, rendered = [], [], []
     for v in vdev:
         fr.render(v)
@@ -156,7 +162,7 @@ def run_b200(args, rank, world):
         ncon = _C.fetch("n_contrib", scene, fr.geom, fr.binning, fr.img, fr.capacity).view(H, W).to(dev)
         b, need = algorithmic_blend_bytes(ncon, W, H)
         blend_bytes.append(b)
-        if world > 1:
+        if tiles_mode:
             rng = _C.fetch("ranges", scene, fr.geom, fr.binning, fr.img, fr.capacity).view(-1, 2).to(torch.int64)
             inst = (rng[:, 1] - rng[:, 0]).view(gy, -1)
             parts.append(balanced_rows(sharding.row_cost(need.cpu().numpy(), inst.numpy()), world))
@@ -164,10 +170,10 @@ def run_b200(args, rank, world):
         import torch.distributed as dist
 
     def frame(i, slot):
-        v = vdev[i % nv]
-        if world == 1:
-            fr.enqueue(v, slot=slot)
+        if not tiles_mode:  # view-parallel: this rank's i-th frame is view rank + i*world of the orbit
+            pipe.enqueue(vdev[(rank + i * world) % nv], slot=slot)
         else:
+            v = vdev[i % nv]
             rows = parts[i % nv]
             r0, r1 = rows[rank]
             fr.color.zero_()
@@ -175,10 +181,11 @@ def run_b200(args, rank, world):
                 fr.enqueue(v, tile_rows=(r0, r1), slot=slot)
             sharding.exchange_image(fr.color, rows, rank)
 
+    pipe.begin()
     for i in range(args.warmup):
         frame(i, i)
+    pipe.end()
     barrier(world)
-    L.gs_profile_enable(1 if world == 1 else 0)
     clocks = ClockSampler(torch.cuda.current_device())
     if rank == 0:
         clocks.start()
@@ -188,15 +195,10 @@ def run_b200(args, rank, world):
     barrier(world)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    if world == 1 and args.stage_timing:
-        ms4 = (torch.zeros(4, dtype=torch.float32)).numpy()
-        for i in range(args.steps):
-            frame(args.warmup + i, i)
-            L.gs_profile_read(ms4.ctypes.data)
-            stage_ms += ms4
-    else:
-        for i in range(args.steps):
-            frame(args.warmup + i, i)
+    pipe.begin()
+    for i in range(args.steps):
+        frame(args.warmup + i, i)
+    pipe.end()
     e1.record()
     barrier(world)
     ms = e0.elapsed_time(e1)
@@ -204,11 +206,13 @@ def run_b200(args, rank, world):
     clk = clocks.stop() if rank == 0 else None
     L.gs_profile_enable(0)
     for i in range(min(args.steps, fr.SLOTS)):
-        code = fr.status(i)[2]
-        if code != 0 and not (world > 1 and fr.status(i)[0] == 0):
+        ln = pipe.lanes[(args.warmup + i) % pipe.depth] if not tiles_mode else fr
+        code = ln.status(i)[2]
+        if code != 0 and not (tiles_mode and ln.status(i)[0] == 0):
             raise RuntimeError(f"frame {i} failed with status {code}")
     ms = max_over_ranks(ms, world, dev)
-    value = args.steps / (ms / 1e3)
+    frames_total = args.steps * (1 if tiles_mode else world)
+    value = frames_total / (ms / 1e3)
 
     # blend-kernel time: a separate, per-frame-synchronised pass (reading the events needs a sync per frame and
     # would serialise the main loop), same frames
@@ -240,58 +244,72 @@ def run_b200(args, rank, world):
                              "tile_binning": float(stage_avg[2]), "blend_forward": float(stage_avg[3])},
                 "note": "blend is FP32-issue/MUFU bound, not HBM bound (SURVEY.md 8d); HBM figure reported as the metric asks"}
 
-    # ---- e2e: drop-in API, host buffers ----
+    # ---- e2e: drop-in API, host buffers (every step: all inputs pinned host -> device, image device -> host) ----
     host = {k: cloud[k].contiguous().pin_memory() for k in ("means3D", "opacities", "scales", "rotations", "shs")}
     hviews = [(torch.from_numpy(v.viewmatrix).pin_memory(), torch.from_numpy(v.projmatrix).pin_memory(),
                torch.from_numpy(v.campos).pin_memory()) for v in views]
     bg = torch.ones(3, device=dev)
     img_host = torch.empty((3, H, W), dtype=torch.float32).pin_memory()
+    ddev = {k: torch.empty_like(t, device=dev) for k, t in host.items()}  # preallocated: no allocator noise
+    vdev2 = [torch.empty(4, 4, device=dev), torch.empty(4, 4, device=dev), torch.empty(3, device=dev)]
     h2d = sum(t.numel() * 4 for t in host.values()) + (16 + 16 + 3) * 4
     d2h = 3 * H * W * 4
 
-    def e2e_frame(i):
-        k = i % nv
-        d = {n: t.to(dev, non_blocking=True) for n, t in host.items()}
-        vm, pm, cp = (t.to(dev, non_blocking=True) for t in hviews[k])
-        rs = GaussianRasterizationSettings(H, W, views[k].tanfovx, views[k].tanfovy, bg, 1.0, vm, pm,
-                                           cloud["sh_degree"], cp, False, False)
-        tr = None if world == 1 else parts[k][rank]
+    def e2e_frame(i, upload_cloud=True):
+        k = (i % nv) if tiles_mode else ((rank + i * world) % nv)
+        if upload_cloud:
+            for n, t in host.items():
+                ddev[n].copy_(t, non_blocking=True)
+        for dst, src in zip(vdev2, hviews[k]):
+            dst.copy_(src, non_blocking=True)
+        rs = GaussianRasterizationSettings(H, W, views[k].tanfovx, views[k].tanfovy, bg, 1.0, vdev2[0], vdev2[1],
+                                           cloud["sh_degree"], vdev2[2], False, False)
+        tr = parts[k][rank] if tiles_mode else None
         if tr is None or tr[1] > tr[0]:
-            color, _ = GaussianRasterizer(rs, tile_rows=tr)(d["means3D"], None, d["opacities"], shs=d["shs"],
-                                                            scales=d["scales"], rotations=d["rotations"])
+            color, _ = GaussianRasterizer(rs, tile_rows=tr)(ddev["means3D"], None, ddev["opacities"], shs=ddev["shs"],
+                                                            scales=ddev["scales"], rotations=ddev["rotations"])
         else:
             color = torch.zeros((3, H, W), device=dev)
-        if world > 1:
+        if tiles_mode:
             sharding.exchange_image(color, parts[k], rank)
-        if rank == 0:
+        if rank == 0 or not tiles_mode:
             img_host.copy_(color, non_blocking=True)
             torch.cuda.current_stream().synchronize()
 
+    def e2e_run(steps, **kw):
+        with torch.no_grad():
+            for i in range(3):
+                e2e_frame(i, **kw)
+            barrier(world)
+            e0.record()
+            for i in range(steps):
+                e2e_frame(3 + i, **kw)
+            e1.record()
+            barrier(world)
+        t = max_over_ranks(e0.elapsed_time(e1), world, dev)
+        return steps * (1 if tiles_mode else world) / (t / 1e3)
+
     e2e_steps = max(3, min(args.steps, 40))
-    with torch.no_grad():
-        for i in range(3):
-            e2e_frame(i)
-        barrier(world)
-        e0.record()
-        for i in range(e2e_steps):
-            e2e_frame(3 + i)
-        e1.record()
-        barrier(world)
-    e2e_ms = max_over_ranks(e0.elapsed_time(e1), world, dev)
-    e2e = {"value": e2e_steps / (e2e_ms / 1e3), "unit": "frames/s", "h2d_bytes_per_step": h2d,
+    e2e = {"value": e2e_run(e2e_steps), "unit": "frames/s", "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-           "api": "diff_gaussian_rasterization.GaussianRasterizer (drop-in), pinned host inputs -> device -> host image"}
+           "api": "diff_gaussian_rasterization.GaussianRasterizer (drop-in), pinned host inputs -> device -> host image",
+           # for information: the reference's callers keep the Gaussians on the device and upload only the camera
+           # per view (simple_raw_render.py:79-112, 261-277); same API, camera up + image down every step
+           "resident_cloud": {"value": e2e_run(e2e_steps, upload_cloud=False), "unit": "frames/s",
+                              "h2d_bytes_per_step": (16 + 16 + 3) * 4, "d2h_bytes_per_step": d2h}}
 
     out = None
     if rank == 0:
         cpu = cpu_baseline(cloud, views, w) if (world == 1 and not args.no_cpu_baseline) else None
         out = {"metric": "frames/sec at 1080p, 800K Gaussians" if args.workload == "C2" else f"frames/sec ({args.workload})",
                "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-               "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-               "dtype": "f32", "data": "synthetic",
+               "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if tiles_mode else "weak",
+               "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                "config": {"workload": f"{args.workload}: {w['desc']}", "parallelism": "single GPU" if world == 1 else
-                          f"tile-row sharded x{world}, work-balanced rows, one image collective per frame",
+                          (f"tile-row sharded x{world}, work-balanced rows, one image collective per frame" if tiles_mode
+                           else f"view-parallel x{world}: rank r renders views r, r+{world}, ... (no collective)"),
                           "l2_policy": "inputs larger than L2 (160 MB of attributes per frame; consecutive steps render different views)",
+                          "frames_in_flight": pipe.depth,
                           "mean_num_rendered": float(np.mean(rendered))},
                "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu}
     return out
@@ -361,10 +379,15 @@ def run_reference(args, rank, world):
     hviews = [tuple(torch.from_numpy(a).pin_memory() for a in (v.viewmatrix, v.projmatrix, v.campos)) for v in views]
     img_host = torch.empty((3, H, W), dtype=torch.float32).pin_memory()
 
+    ddev = {k: torch.empty_like(t, device=dev) for k, t in host.items()}  # same harness as the b200 arm
+    vdev2 = (torch.empty(4, 4, device=dev), torch.empty(4, 4, device=dev), torch.empty(3, device=dev))
+
     def e2e_frame(i):
-        dd = {n: t.to(dev, non_blocking=True) for n, t in host.items()}
-        vv = tuple(t.to(dev, non_blocking=True) for t in hviews[i % nv])
-        color = frame(i, dd, vv)
+        for n, t in host.items():
+            ddev[n].copy_(t, non_blocking=True)
+        for dst, src in zip(vdev2, hviews[i % nv]):
+            dst.copy_(src, non_blocking=True)
+        color = frame(i, ddev, vdev2)
         img_host.copy_(color, non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
@@ -412,6 +435,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference", "cpu-port"])
     ap.add_argument("--workload", default="C2", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--streams", type=int, default=4, help="frames in flight (one CUDA stream + workspace each)")
+    ap.add_argument("--parallel", default="views", choices=["views", "tiles"], help="multi-GPU sharding (N > 1)")
     ap.add_argument("--stage-timing", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

@@ -22,7 +22,8 @@ from typing import Optional, Tuple
 import torch
 
 _PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-_SO = os.path.join(_PKG, "libgsplat_b200.so")
+# GSPLAT_B200_LIB: developer override used by the profiling tools to load an instrumented build of the same library
+_SO = os.environ.get("GSPLAT_B200_LIB") or os.path.join(_PKG, "libgsplat_b200.so")
 
 GS_ERRORS = {-1: "invalid argument", -2: "CUDA error", -3: "buffer allocation failed",
              -4: "instance capacity exceeded", -5: "unsupported size (more than 65536 tiles or too many Gaussians)",
