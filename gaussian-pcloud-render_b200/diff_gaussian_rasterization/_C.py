@@ -119,17 +119,35 @@ def _prep(t: Optional[torch.Tensor], dtype=torch.float32) -> Optional[torch.Tens
 
 
 class _Growable:
-    """A uint8 CUDA tensor that the library resizes through a C callback (resizeFunctional, rasterize_points.cu:27-33)."""
+    """A uint8 CUDA tensor that the library resizes through a C callback (resizeFunctional, rasterize_points.cu:27-33).
+    Sizes are rounded up to 1/8-octave buckets so that PyTorch's caching allocator finds a block of the same size
+    again on the next frame (the instance count, hence the binning buffer, changes from view to view)."""
 
     def __init__(self, device):
         self.t = torch.empty(0, dtype=torch.uint8, device=device)
 
         def _resize(_user, nbytes):
-            self.t.resize_(int(nbytes))
+            n = int(nbytes)
+            if n > self.t.numel():
+                step = max(1 << 20, 1 << max(0, n.bit_length() - 4))
+                self.t = torch.empty(((n + step - 1) // step) * step, dtype=torch.uint8, device=self.t.device)
             return self.t.data_ptr()
 
         self._cb = RESIZE_FN(_resize)
         self.buf = GsBuffer(self._cb, None)
+
+
+# Workspaces that may be recycled from call to call: only used when the caller states that no backward pass will
+# consume the buffers of this forward (see _RasterizeGaussians.forward); grow-only, one set per device.
+_WORKSPACE_POOL = {}
+
+
+def _pooled_workspaces(dev):
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    ws = _WORKSPACE_POOL.get(key)
+    if ws is None:
+        ws = _WORKSPACE_POOL[key] = (_Growable(dev), _Growable(dev), _Growable(dev))
+    return ws
 
 
 def make_scene(*, P, sh_degree, sh_stride, width, height, tan_fovx, tan_fovy, scale_modifier, prefiltered, debug,
@@ -144,7 +162,8 @@ def make_scene(*, P, sh_degree, sh_stride, width, height, tan_fovx, tan_fovy, sc
 
 def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp,
                         viewmatrix, projmatrix, tan_fovx, tan_fovy, image_height, image_width, sh, degree, campos,
-                        prefiltered, debug, tile_rows: Optional[Tuple[int, int]] = None, out_color=None):
+                        prefiltered, debug, tile_rows: Optional[Tuple[int, int]] = None, out_color=None,
+                        reuse_workspace: bool = False):
     if means3D.dim() != 2 or means3D.size(1) != 3:
         raise RuntimeError("means3D must have dimensions (num_points, 3)")
     if not means3D.is_cuda:
@@ -160,7 +179,9 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
         if out_color is None:
             out_color = torch.zeros((3, H, W), dtype=torch.float32, device=dev)
         radii = torch.zeros((P,), dtype=torch.int32, device=dev)
-        geom, binning, img = _Growable(dev), _Growable(dev), _Growable(dev)
+        # reuse_workspace: the three scratch buffers come from a grow-only per-device pool instead of being
+        # allocated per call; valid only if nothing (no backward) reads them after the next forward on this device
+        geom, binning, img = _pooled_workspaces(dev) if reuse_workspace else (_Growable(dev), _Growable(dev), _Growable(dev))
         rendered = 0
         if P != 0:
             scene = make_scene(P=P, sh_degree=int(degree), sh_stride=M, width=W, height=H, tan_fovx=float(tan_fovx),

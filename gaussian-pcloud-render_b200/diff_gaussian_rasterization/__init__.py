@@ -41,16 +41,19 @@ class _RasterizeGaussians(torch.autograd.Function):
         args = (rs.bg, means3D, colors_precomp, opacities, scales, rotations, rs.scale_modifier, cov3Ds_precomp,
                 rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, rs.image_height, rs.image_width, sh,
                 rs.sh_degree, rs.campos, rs.prefiltered, rs.debug)
+        # no input needs a gradient (e.g. the benchmark's torch.no_grad() rendering, simple_benchmark.py:198):
+        # backward will never run, so the scratch buffers can be recycled instead of allocated per frame
+        reuse = not any(ctx.needs_input_grad)
         if rs.debug:
             cpu_args = cpu_deep_copy_tuple(args)  # copy before anything can corrupt them
             try:
-                out = _C.rasterize_gaussians(*args, tile_rows=tile_rows)
+                out = _C.rasterize_gaussians(*args, tile_rows=tile_rows, reuse_workspace=reuse)
             except Exception as ex:
                 torch.save(cpu_args, "snapshot_fw.dump")
                 print("\nAn error occured in forward. Please forward snapshot_fw.dump for debugging.")
                 raise ex
         else:
-            out = _C.rasterize_gaussians(*args, tile_rows=tile_rows)
+            out = _C.rasterize_gaussians(*args, tile_rows=tile_rows, reuse_workspace=reuse)
         num_rendered, color, radii, geomBuffer, binningBuffer, imgBuffer = out
         ctx.raster_settings = rs
         ctx.num_rendered = num_rendered

@@ -160,6 +160,29 @@ class FramePipeline:
             out = self.lanes[k].enqueue(view_dev, tile_rows=tile_rows, slot=slot)
         return k, out
 
+    def enqueue_host(self, host_cloud: dict, host_view, tanfov, out_host: torch.Tensor, slot: int = 0) -> int:
+        """One frame whose inputs live in (pinned) HOST memory: uploads the Gaussian attributes and the camera of
+        this frame on the lane's stream, renders, and downloads the image into `out_host` (pinned, (3,H,W)).
+        Copies of one frame overlap the kernels of the frames on the other lanes.  Returns the lane index; the
+        image is valid once the lane's stream (or `end()` + the current stream) has been synchronised."""
+        k = self.count % len(self.lanes)
+        self.count += 1
+        ln = self.lanes[k]
+        if not getattr(ln, "_own_inputs", False):  # private device copies of the inputs for this lane
+            for n in ("means3D", "opacities", "scales", "rotations", "shs"):
+                setattr(ln, n, torch.empty_like(getattr(ln, n)))
+            ln._view_dev = (torch.empty(4, 4, device=self.dev), torch.empty(4, 4, device=self.dev),
+                            torch.empty(3, device=self.dev))
+            ln._own_inputs = True
+        with torch.cuda.stream(self.streams[k]):
+            for n in ("means3D", "opacities", "scales", "rotations", "shs"):
+                getattr(ln, n).copy_(host_cloud[n], non_blocking=True)
+            for dst, src in zip(ln._view_dev, host_view):
+                dst.copy_(src, non_blocking=True)
+            out = ln.enqueue(ln._view_dev + (tanfov[0], tanfov[1]), slot=slot)
+            out_host.copy_(out, non_blocking=True)
+        return k
+
     def end(self) -> None:
         """Orders the current stream behind every lane (call before recording the closing event)."""
         cur = torch.cuda.current_stream(self.dev)
