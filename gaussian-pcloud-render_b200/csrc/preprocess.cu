@@ -60,8 +60,66 @@ __device__ __forceinline__ float3 sh_to_rgb(int deg, const float* __restrict__ s
     return make_float3(res[0], res[1], res[2]);
 }
 
+// ---- TMA bulk staging (sm_90+/sm_100a): one elected thread issues 1-D bulk copies global -> shared that complete
+// on an mbarrier; the inputs of a block are five contiguous slabs of the caller's AoS arrays.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // make the init visible to the async proxy
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n.reg .pred p;\nWAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}"
+        ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// STAGED: the block's inputs (256 means / scales / quaternions / opacities / SH rows) are brought into shared memory
+// with TMA bulk copies and read from there: the 12-B / 16-B / (12 M)-B strided per-thread reads hit shared-memory
+// banks (conflict-free for the benchmark's M = 13) instead of fetching partial sectors through L1.
+template <bool STAGED>
 __global__ void __launch_bounds__(256) preprocess_kernel(const PreArgs a) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    extern __shared__ __align__(128) unsigned char s_stage[];
+    const float* mp = a.means + 3 * (size_t)i;
+    const float* sp = a.scales ? a.scales + 3 * (size_t)i : nullptr;
+    const float* rp = a.rots ? a.rots + 4 * (size_t)i : nullptr;
+    const float* op_ptr = a.opac + i;
+    const float* shp = a.shs ? a.shs + (size_t)i * a.M * 3 : nullptr;
+    if (STAGED && (blockIdx.x + 1) * 256 <= a.P) {  // full blocks only; the last partial block reads global memory
+        __shared__ __align__(8) unsigned long long s_bar;
+        float* s_means = reinterpret_cast<float*>(s_stage);
+        float* s_scales = s_means + 3 * 256;
+        float* s_rots = s_scales + 3 * 256;
+        float* s_opac = s_rots + 4 * 256;
+        float* s_sh = s_opac + 256;
+        const unsigned sh_bytes = 256u * (unsigned)a.M * 12u;
+        if (threadIdx.x == 0) mbar_init(&s_bar, 1);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const size_t b0 = (size_t)blockIdx.x * 256;
+            mbar_expect_tx(&s_bar, 3072u + 3072u + 4096u + 1024u + sh_bytes);
+            bulk_g2s(s_means, a.means + 3 * b0, 3072u, &s_bar);
+            bulk_g2s(s_scales, a.scales + 3 * b0, 3072u, &s_bar);
+            bulk_g2s(s_rots, a.rots + 4 * b0, 4096u, &s_bar);
+            bulk_g2s(s_opac, a.opac + b0, 1024u, &s_bar);
+            bulk_g2s(s_sh, a.shs + b0 * a.M * 3, sh_bytes, &s_bar);
+        }
+        mbar_wait(&s_bar, 0);
+        mp = s_means + 3 * threadIdx.x;
+        sp = s_scales + 3 * threadIdx.x;
+        rp = s_rots + 4 * threadIdx.x;
+        op_ptr = s_opac + threadIdx.x;
+        shp = s_sh + (size_t)threadIdx.x * a.M * 3;
+    }
     unsigned my_tiles = 0, my_vis = 0, my_rows = 0;
     bool bad = false;
     __shared__ int s_rd[GS_MAX_GRID + 1];  // this block's share of the row difference array
@@ -72,7 +130,7 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreArgs a) {
         uint32_t key = 0xFFFFFFFFu;  // culled Gaussians sort to the end of the depth order
         ushort4 rect = make_ushort4(0, 0, 0, 0);
         do {
-            const float3 mean = make_float3(a.means[3 * i], a.means[3 * i + 1], a.means[3 * i + 2]);
+            const float3 mean = make_float3(mp[0], mp[1], mp[2]);
             const float3 p_view = xform43(a.view, mean);
             if (p_view.z <= 0.2f) {  // near plane only (auxiliary.h:154)
                 bad = a.prefiltered != 0;
@@ -87,8 +145,8 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreArgs a) {
 #pragma unroll
                 for (int k = 0; k < 6; k++) c6[k] = a.cov3D_pre[6 * (size_t)i + k];
             } else {
-                const float3 sc = make_float3(a.scales[3 * i], a.scales[3 * i + 1], a.scales[3 * i + 2]);
-                const float4 q = reinterpret_cast<const float4*>(a.rots)[i];
+                const float3 sc = make_float3(sp[0], sp[1], sp[2]);
+                const float4 q = *reinterpret_cast<const float4*>(rp);
                 cov3d_from_scale_rot(sc, a.mod, q, c6);
 #pragma unroll
                 for (int k = 0; k < 6; k++) a.cov3D[6 * (size_t)i + k] = c6[k];
@@ -112,13 +170,12 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreArgs a) {
             float3 rgb = make_float3(0.f, 0.f, 0.f);
             unsigned clamp_bits = 0;
             if (a.colors_pre == nullptr) {
-                rgb = sh_to_rgb(a.D, a.shs + (size_t)i * a.M * 3, mean, make_float3(a.campos[0], a.campos[1], a.campos[2]),
-                                clamp_bits);
+                rgb = sh_to_rgb(a.D, shp, mean, make_float3(a.campos[0], a.campos[1], a.campos[2]), clamp_bits);
                 a.clamp[i] = (uint8_t)clamp_bits;
             } else {
                 rgb = make_float3(a.colors_pre[3 * i], a.colors_pre[3 * i + 1], a.colors_pre[3 * i + 2]);
             }
-            const float op = a.opac[i];
+            const float op = *op_ptr;
             // Conservative cut-off on `power`: below it, op*exp(power) < (1/255)(1 - 1e-3), so the blend kernels
             // may skip the exponential with no change to the result (alpha < 1/255 is skipped anyway).
             const float thr = -logf(255.0f * op) - 1.0e-3f;
@@ -204,7 +261,25 @@ cudaError_t gs_launch_preprocess(const GsFrame& f, const GsGeom& g, const GsImag
     a.radii = radii;
     a.rec = g.rec; a.key = g.key[0]; a.rect = g.rect; a.ntile = g.ntile; a.cov3D = g.cov3D;
     a.clamp = g.clamp; a.rdiff = im.rdiff; a.hdr = g.hdr;
-    preprocess_kernel<<<(unsigned)gs_div_up(s.P, 256), 256, 0, f.stream>>>(a);
+    // TMA-staged variant: scale/rotation + SH inputs, every slab 16-B aligned, and the staging buffer fits
+    const size_t stage_bytes = (size_t)(3 + 3 + 4 + 1) * 256 * 4 + (size_t)256 * s.sh_stride * 12;
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+    // ... and at least half of every SH row is actually read (bulk copies fetch whole rows; the pcrender shape reads 4
+    // of its 13 coefficients, there the direct path moves fewer bytes).  Measured on B200: neutral at C2 and C4 --
+    // the kernel is bound by its scattered 48-B record stores and per-thread latency, not by the input reads.
+    const bool sh_dense = 2 * (s.sh_degree + 1) * (s.sh_degree + 1) > s.sh_stride;
+    const bool staged = sh_dense && s.P >= 256 && s.scales && s.rotations && s.shs && !s.cov3D_precomp && !s.colors_precomp &&
+                        stage_bytes <= 100 * 1024 && al16(s.means3D) && al16(s.scales) && al16(s.rotations) &&
+                        al16(s.opacities) && al16(s.shs);
+    static bool attr_set = false;
+    if (staged && !attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(preprocess_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             100 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    if (staged) preprocess_kernel<true><<<(unsigned)gs_div_up(s.P, 256), 256, stage_bytes, f.stream>>>(a);
+    else preprocess_kernel<false><<<(unsigned)gs_div_up(s.P, 256), 256, 0, f.stream>>>(a);
     gs_note_launch();
     return cudaGetLastError();
 }

@@ -19,6 +19,12 @@ import torch.distributed as dist
 TILE = 16
 
 
+def views_of_rank(rank: int, world: int, num_views: int) -> List[int]:
+    """View-parallel sharding: frames of an orbit are independent, rank r renders views
+    r, r + world, r + 2*world, ...; no data-path collective is needed."""
+    return list(range(rank, num_views, world))
+
+
 def balanced_rows(row_cost: np.ndarray, world: int) -> List[Tuple[int, int]]:
     """Contiguous tile-row ranges [a,b) with ~equal summed cost.  Deterministic, so every rank can derive the same
     partition locally from the same cost vector; empty ranges are possible when rows are few or cost is zero."""

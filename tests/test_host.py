@@ -90,3 +90,31 @@ def test_tile_row_shard_exchange_world2_gloo():
         p.join(timeout=60)
     assert all(ok for _, ok, _, _ in res)
     assert res[0][2] == res[1][2]  # identical partitions on both ranks
+
+
+def _views_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import sharding
+    mine = sharding.views_of_rank(rank, world, 13)
+    flags = torch.zeros(13, dtype=torch.int32)
+    flags[mine] = 1
+    dist.all_reduce(flags)  # test-only collective: every view must be rendered by exactly one rank
+    q.put((rank, mine, flags.tolist()))
+    dist.destroy_process_group()
+
+
+def test_view_parallel_sharding_world2_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_views_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res[0][1] == [0, 2, 4, 6, 8, 10, 12] and res[1][1] == [1, 3, 5, 7, 9, 11]
+    assert res[0][2] == [1] * 13 and res[1][2] == [1] * 13
