@@ -237,8 +237,15 @@ def run_b200(args, rank, world):
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         ach = (bsum / nprof) / (stage_avg[3] * 1e-3) / 1e9
+        ncu = {}
+        try:  # DRAM bytes of one launch from the committed `ncu --set full` capture of this kernel (same workload)
+            ncu = json.load(open(os.path.join(ROOT, "profiles", "blend_forward_traffic.json")))
+        except Exception:  # noqa: BLE001
+            pass
         roof = {"bound": "hbm", "kernel": "blend_forward_kernel", "achieved": ach, "peak": peak, "unit": "GB/s",
-                "frac": ach / peak, "traffic": None, "peak_source": "measured" if peaks else "fallback",
+                "frac": ach / peak, "traffic": ncu.get("traffic") if args.workload == "C2" else None,
+                "peak_source": "measured" if peaks else "fallback",
+                "ncu": {k: ncu.get(k) for k in ("issue_active_pct", "l2_hit_pct", "warp_instructions", "source")} if ncu else None,
                 "kernel_ms": float(stage_avg[3]), "algorithmic_bytes": bsum / nprof,
                 "stage_ms": {"preprocess": float(stage_avg[0]), "depth_sort": float(stage_avg[1]),
                              "tile_binning": float(stage_avg[2]), "blend_forward": float(stage_avg[3])},
