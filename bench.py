@@ -17,7 +17,7 @@ N > 1, two ways to shard:
   --parallel views (default): the frames of the orbit are independent units; rank r renders views r, r+N, r+2N, ...
           with no data-path collective, every rank times K steps ("scaling": "weak", value = N*K frames / max time);
   --parallel tiles: every frame is split by screen-space tile rows: each rank bins + blends a work-balanced
-          contiguous range of tile rows and one collective per frame assembles the image ("scaling": "strong").
+          contiguous range of tile rows and one NCCL all-gather per frame assembles the image ("scaling": "strong").
 Frames are independent, so `--streams S` keeps S frames in flight on S CUDA streams (renderer.FramePipeline).
 --impl reference runs the UNMODIFIED reference CUDA rasterizer (oracle/_ref/libgs_ref.so, built from
 /root/reference by oracle/Makefile; the reference has no CPU implementation of this path) on the same workload.
@@ -176,7 +176,6 @@ def run_b200(args, rank, world):
             v = vdev[i % nv]
             rows = parts[i % nv]
             r0, r1 = rows[rank]
-            fr.color.zero_()
             if r1 > r0:
                 fr.enqueue(v, tile_rows=(r0, r1), slot=slot)
             sharding.exchange_image(fr.color, rows, rank)

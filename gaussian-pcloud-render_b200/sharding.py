@@ -50,9 +50,26 @@ def pixel_rows(rows: Sequence[Tuple[int, int]], H: int) -> List[Tuple[int, int]]
 
 
 def exchange_image(color: torch.Tensor, rows: Sequence[Tuple[int, int]], rank: int, group=None) -> torch.Tensor:
-    """In-place assembly of the full image on every rank.  `color` is (3,H,W), zero outside this rank's rows
-    (the rasterizer never touches pixels outside its shard), so the assembly is one sum all-reduce: every pixel
-    receives exactly one non-zero contribution, i.e. x + 0 + ... + 0 = x bit-exactly."""
-    if dist.is_initialized() and dist.get_world_size(group) > 1:
-        dist.all_reduce(color, op=dist.ReduceOp.SUM, group=group)
+    """In-place assembly of the full image on every rank with ONE all-gather.
+
+    `color` is (3,H,W); this rank rendered pixel rows pixel_rows(rows)[rank].  Row ranges are work-balanced and
+    therefore unequal, so every rank contributes a slab padded to the tallest range; after the collective each
+    rank copies the other ranks' slabs into place (plain device copies).  Bit-exact: pixels are only moved."""
+    if not (dist.is_initialized() and dist.get_world_size(group) > 1):
+        return color
+    world = dist.get_world_size(group)
+    H, W = int(color.shape[1]), int(color.shape[2])
+    prow = pixel_rows(rows, H)
+    tallest = max(b - a for a, b in prow)
+    if tallest == 0:
+        return color
+    send = torch.zeros((3, tallest, W), dtype=color.dtype, device=color.device)
+    a, b = prow[rank]
+    if b > a:
+        send[:, : b - a, :] = color[:, a:b, :]
+    slabs = [torch.empty_like(send) for _ in range(world)]
+    dist.all_gather(slabs, send, group=group)
+    for r, (a, b) in enumerate(prow):
+        if r != rank and b > a:
+            color[:, a:b, :] = slabs[r][:, : b - a, :]
     return color
