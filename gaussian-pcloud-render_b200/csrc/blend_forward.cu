@@ -401,6 +401,212 @@ __global__ void __launch_bounds__(BF_WARPS * 32, 5) blend_forward_kernel(
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Two pixels per lane (BF_PX2): the warp blends an 8x8 block, lane (lx, ly) owns pixels (lx, ly) and (lx, ly + 4).
+// The two pixels share dx, so the exponent of both costs 3 scalar + 6 packed FP32x2 instructions (FADD2 / FMUL2 /
+// FFMA2 of sm_100: one issue slot, two IEEE-rn results), the colour accumulation 6 packed ones; every packed
+// operation is, per half, the scalar operation the reference executes (same operands, same order, same fused
+// multiply-adds), so results stay bit-identical.  Per-batch work (gather, cull) is shared by 64 pixels.
+typedef unsigned long long f2;
+__device__ __forceinline__ f2 pk(float lo, float hi) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ f2 bc(float v) { return pk(v, v); }
+__device__ __forceinline__ float lo(f2 v) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); (void)b; return a; }
+__device__ __forceinline__ float hi(f2 v) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); (void)a; return b; }
+__device__ __forceinline__ f2 sub2(f2 a, f2 b) { f2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) { f2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { f2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+
+__global__ void __launch_bounds__(BF_WARPS * 32, 4) blend_forward_px2_kernel(
+    const uint2* __restrict__ ranges, const uint32_t* __restrict__ order, const uint32_t* __restrict__ list,
+    const GsRec* __restrict__ rec, int W, int H, int gx, uint32_t num_tiles, GsHeader* __restrict__ hdr,
+    const float* __restrict__ bg, float* __restrict__ final_T, uint32_t* __restrict__ n_contrib,
+    float* __restrict__ out_color) {
+    __shared__ BfStage s_ring[BF_WARPS][BF_STAGES];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lx = lane & 7, ly = lane >> 3;
+    const float bg0 = bg[0], bg1 = bg[1], bg2 = bg[2];
+    const size_t plane = (size_t)H * W;
+    BfStage* __restrict__ ring = s_ring[warp];
+    unsigned* const q_fresh = &hdr->tickets[6];
+    const uint32_t nonempty = hdr->nonempty_tiles;
+    const uint32_t blend_units = nonempty * 4u;
+    const uint32_t num_units = blend_units + (num_tiles - nonempty);
+
+    while (true) {
+        uint32_t unit = 0;
+        if (lane == 0) unit = atomicAdd(q_fresh, 1u);
+        unit = __shfl_sync(GS_FULL, unit, 0);
+        if (unit >= num_units) break;
+        if (unit >= blend_units) {  // ---- empty tile: colour = background, T = 1, no contributor
+            const uint32_t tile = order[nonempty + (unit - blend_units)];
+            const int x0 = (int)(tile % gx) * GS_TILE, y0 = (int)(tile / gx) * GS_TILE;
+            if ((W & 3) == 0 && x0 + GS_TILE <= W) {
+                const int px = x0 + (lane & 3) * 4;
+#pragma unroll
+                for (int r = 0; r < 2; r++) {
+                    const int py = y0 + r * 8 + (lane >> 2);
+                    if (py < H) {
+                        const size_t pid = (size_t)W * py + px;
+                        *reinterpret_cast<float4*>(out_color + pid) = make_float4(bg0, bg0, bg0, bg0);
+                        *reinterpret_cast<float4*>(out_color + plane + pid) = make_float4(bg1, bg1, bg1, bg1);
+                        *reinterpret_cast<float4*>(out_color + 2 * plane + pid) = make_float4(bg2, bg2, bg2, bg2);
+                        *reinterpret_cast<float4*>(final_T + pid) = make_float4(1.f, 1.f, 1.f, 1.f);
+                        *reinterpret_cast<uint4*>(n_contrib + pid) = make_uint4(0u, 0u, 0u, 0u);
+                    }
+                }
+            } else {
+                for (int r = 0; r < 8; r++) {
+                    const int px = x0 + (lane & 15), py = y0 + r * 2 + (lane >> 4);
+                    if (px < W && py < H) {
+                        const size_t pid = (size_t)W * py + px;
+                        out_color[pid] = bg0; out_color[plane + pid] = bg1; out_color[2 * plane + pid] = bg2;
+                        final_T[pid] = 1.f; n_contrib[pid] = 0u;
+                    }
+                }
+            }
+            continue;
+        }
+        const uint32_t tile = order[unit >> 2];
+        const int sub = unit & 3;
+        const int tile_x = tile % gx, tile_y = tile / gx;
+        const int bx0 = tile_x * GS_TILE + (sub & 1) * 8, by0 = tile_y * GS_TILE + (sub >> 1) * 8;
+        if (bx0 >= W || by0 >= H) continue;  // block entirely outside the image
+        const int px = bx0 + lx, pyA = by0 + ly, pyB = by0 + ly + 4;
+        const bool insA = px < W && pyA < H, insB = px < W && pyB < H;
+        const float pfx = (float)px;
+        const f2 pfy2 = pk((float)pyA, (float)pyB);
+        float fx0 = (float)bx0, fx1 = (float)(bx0 + 7), fy0 = (float)by0, fy1 = (float)(by0 + 7);
+
+        const uint2 range = ranges[tile];
+        const uint32_t total = range.y - range.x;
+        const uint32_t* __restrict__ lst = list + range.x;
+
+        bool doneA = !insA, doneB = !insB;
+        f2 T2 = bc(1.0f), C0 = bc(0.f), C1 = bc(0.f), C2 = bc(0.f);
+        uint32_t lastA = 0, lastB = 0;
+
+        __syncwarp();
+#pragma unroll
+        for (int p = 0; p < 2; p++) {
+            if (p * 32 + lane < total) {
+                const GsRec* r = rec + lst[p * 32 + lane];
+                cp_async16(&ring[p].a[lane], &r->a);
+                cp_async16(&ring[p].b[lane], &r->b);
+                cp_async16(&ring[p].c[lane], &r->c);
+            }
+            cp_async_commit();
+        }
+        uint32_t id_next = (64 + lane < total) ? lst[64 + lane] : 0u;
+
+        int stage = 0;
+        uint32_t next_check = BF_CHECK * 32;
+        for (uint32_t base = 0; base < total; base += 32) {
+            if (base == next_check) {  // shrink the cull box to the pixels that are still live
+                next_check += BF_CHECK * 32;
+                const unsigned aliveA = __ballot_sync(GS_FULL, !doneA), aliveB = __ballot_sync(GS_FULL, !doneB);
+                const unsigned both = aliveA | aliveB;
+                const unsigned cols = (both | (both >> 8) | (both >> 16) | (both >> 24)) & 0xffu;
+                unsigned rows = 0;
+#pragma unroll
+                for (int r = 0; r < 4; r++) {
+                    rows |= ((aliveA >> (8 * r)) & 0xffu) ? (1u << r) : 0u;
+                    rows |= ((aliveB >> (8 * r)) & 0xffu) ? (16u << r) : 0u;
+                }
+                fx0 = (float)(bx0 + __ffs(cols) - 1); fx1 = (float)(bx0 + 31 - __clz(cols));
+                fy0 = (float)(by0 + __ffs(rows) - 1); fy1 = (float)(by0 + 31 - __clz(rows));
+            }
+            cp_async_wait<1>();
+            __syncwarp();
+            {
+                int nst = stage + 2; if (nst >= BF_STAGES) nst -= BF_STAGES;
+                if (base + 64 + lane < total) {
+                    const GsRec* r = rec + id_next;
+                    cp_async16(&ring[nst].a[lane], &r->a);
+                    cp_async16(&ring[nst].b[lane], &r->b);
+                    cp_async16(&ring[nst].c[lane], &r->c);
+                }
+                cp_async_commit();
+                if (base + 96 + lane < total) id_next = lst[base + 96 + lane];
+            }
+            const BfStage& st = ring[stage];
+            stage = (stage + 1 == BF_STAGES) ? 0 : stage + 1;
+
+            bool hit = false;
+            if (base + lane < total) {
+                const float4 a = st.a[lane], b = st.b[lane];
+                const float nBA = st.c[lane].w;
+                const float bound = box_max_power(a.z, a.w, b.x, nBA, b.w, a.x - fx1, a.x - fx0, a.y - fy1, a.y - fy0);
+                hit = !(bound < b.z);
+            }
+            unsigned mask = __ballot_sync(GS_FULL, hit);
+            while (mask) {
+                const int j = __ffs(mask) - 1;
+                mask &= mask - 1;
+                const float4 ga = st.a[j], gb = st.b[j];
+                // power of both pixels, operation for operation as forward.cu:336-338 compiles:
+                //   power = fma(fma(dx, A*dx, dy*(C*dy)), -0.5, -(dy*(B*dx)))
+                const float dx = ga.x - pfx;
+                const f2 dy2 = sub2(bc(ga.y), pfy2);
+                f2 t1 = mul2(bc(gb.x), dy2);
+                t1 = mul2(dy2, t1);
+                const float t2 = ga.z * dx, t3n = (-ga.w) * dx;
+                const f2 t3 = mul2(dy2, bc(t3n));
+                const f2 sm = fma2(bc(dx), bc(t2), t1);
+                const f2 p2 = fma2(sm, bc(-0.5f), t3);
+                const float pA = lo(p2), pB = hi(p2);
+                float alphaA = fminf(0.99f, gb.y * expf(pA)), alphaB = fminf(0.99f, gb.y * expf(pB));
+                bool okA = !doneA && !(pA > 0.0f) && !(pA < gb.z) && !(alphaA < 1.0f / 255.0f);
+                bool okB = !doneB && !(pB > 0.0f) && !(pB < gb.z) && !(alphaB < 1.0f / 255.0f);
+                if (!__any_sync(GS_FULL, okA || okB)) continue;
+                alphaA = okA ? alphaA : 0.0f;  // alpha 0 leaves T and the colour exactly unchanged
+                alphaB = okB ? alphaB : 0.0f;
+                const f2 tt2 = mul2(T2, sub2(bc(1.0f), pk(alphaA, alphaB)));
+                const bool stopA = okA && lo(tt2) < 0.0001f, stopB = okB && hi(tt2) < 0.0001f;
+                doneA = doneA || stopA;
+                doneB = doneB || stopB;
+                alphaA = stopA ? 0.0f : alphaA;
+                alphaB = stopB ? 0.0f : alphaB;
+                const f2 a2 = pk(alphaA, alphaB);
+                const float4 gc = st.c[j];
+                C0 = fma2(mul2(bc(gc.x), a2), T2, C0);
+                C1 = fma2(mul2(bc(gc.y), a2), T2, C1);
+                C2 = fma2(mul2(bc(gc.z), a2), T2, C2);
+                T2 = pk(stopA ? lo(T2) : lo(tt2), stopB ? hi(T2) : hi(tt2));
+                if (okA && !stopA) lastA = base + (uint32_t)j + 1u;
+                if (okB && !stopB) lastB = base + (uint32_t)j + 1u;
+                if (__all_sync(GS_FULL, doneA && doneB)) break;
+            }
+            if (__all_sync(GS_FULL, doneA && doneB)) break;
+        }
+        cp_async_wait<0>();
+
+        if (insA) {
+            const size_t pid = (size_t)W * pyA + px;
+            const float T = lo(T2);
+            final_T[pid] = T;
+            n_contrib[pid] = lastA;
+            out_color[pid] = lo(C0) + T * bg0;
+            out_color[plane + pid] = lo(C1) + T * bg1;
+            out_color[2 * plane + pid] = lo(C2) + T * bg2;
+        }
+        if (insB) {
+            const size_t pid = (size_t)W * pyB + px;
+            const float T = hi(T2);
+            final_T[pid] = T;
+            n_contrib[pid] = lastB;
+            out_color[pid] = hi(C0) + T * bg0;
+            out_color[plane + pid] = hi(C1) + T * bg1;
+            out_color[2 * plane + pid] = hi(C2) + T * bg2;
+        }
+    }
+}
+
+// BF_PX2 1 (default): the two-pixels-per-lane kernel.  Measured on B200 (C2): +8.5 % frames/s with frames in flight
+// (1717 vs 1583) for +3 % single-frame blend time (coarser units lengthen the tail), bit-identical output.
+#ifndef BF_PX2
+#define BF_PX2 1
+#endif
+
 int g_blend_grid = 0;
 
 }  // namespace
@@ -422,11 +628,17 @@ cudaError_t gs_launch_blend_forward(const GsFrame& f, const GsGeom& g, const GsB
         if (e != cudaSuccess) return e;
         e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (e != cudaSuccess) return e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, blend_forward_kernel, BF_WARPS * 32, 0);
+        if (BF_PX2) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, blend_forward_px2_kernel, BF_WARPS * 32, 0);
+        else e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, blend_forward_kernel, BF_WARPS * 32, 0);
         if (e != cudaSuccess) return e;
         g_blend_grid = sms * (per_sm > 0 ? per_sm : 1);
     }
     const unsigned grid = (unsigned)min((uint32_t)g_blend_grid, num_tiles);
+    if (BF_PX2)
+        blend_forward_px2_kernel<<<grid, BF_WARPS * 32, 0, f.stream>>>(im.ranges, im.order, b.list, g.rec, f.s.width,
+                                                                      f.s.height, f.gx, num_tiles, g.hdr, f.s.background,
+                                                                      im.final_T, im.n_contrib, out_color);
+    else
     blend_forward_kernel<<<grid, BF_WARPS * 32, 0, f.stream>>>(im.ranges, im.order, b.list, g.rec, f.s.width, f.s.height,
                                                               f.gx, num_tiles, g.hdr, im.bf_task, im.bf_state,
                                                               f.s.background, im.final_T, im.n_contrib, out_color);
