@@ -415,6 +415,7 @@ __device__ __forceinline__ float hi(f2 v) { float a, b; asm("mov.b64 {%0, %1}, %
 __device__ __forceinline__ f2 sub2(f2 a, f2 b) { f2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ f2 mul2(f2 a, f2 b) { f2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { f2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ void fma2_acc(f2& acc, f2 a, f2 b) { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b)); }
 
 __global__ void __launch_bounds__(BF_WARPS * 32, 4) blend_forward_px2_kernel(
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ order, const uint32_t* __restrict__ list,
@@ -554,6 +555,8 @@ __global__ void __launch_bounds__(BF_WARPS * 32, 4) blend_forward_px2_kernel(
                 const f2 sm = fma2(bc(dx), bc(t2), t1);
                 const f2 p2 = fma2(sm, bc(-0.5f), t3);
                 const float pA = lo(p2), pB = hi(p2);
+                // (a packed FP32x2 transcription of libdevice's expf was bit-identical but not faster: FP32x2
+                // instructions save issue slots, not FMA-pipe cycles)
                 float alphaA = fminf(0.99f, gb.y * expf(pA)), alphaB = fminf(0.99f, gb.y * expf(pB));
                 bool okA = !doneA && !(pA > 0.0f) && !(pA < gb.z) && !(alphaA < 1.0f / 255.0f);
                 bool okB = !doneB && !(pB > 0.0f) && !(pB < gb.z) && !(alphaB < 1.0f / 255.0f);
@@ -568,9 +571,9 @@ __global__ void __launch_bounds__(BF_WARPS * 32, 4) blend_forward_px2_kernel(
                 alphaB = stopB ? 0.0f : alphaB;
                 const f2 a2 = pk(alphaA, alphaB);
                 const float4 gc = st.c[j];
-                C0 = fma2(mul2(bc(gc.x), a2), T2, C0);
-                C1 = fma2(mul2(bc(gc.y), a2), T2, C1);
-                C2 = fma2(mul2(bc(gc.z), a2), T2, C2);
+                fma2_acc(C0, mul2(bc(gc.x), a2), T2);
+                fma2_acc(C1, mul2(bc(gc.y), a2), T2);
+                fma2_acc(C2, mul2(bc(gc.z), a2), T2);
                 T2 = pk(stopA ? lo(T2) : lo(tt2), stopB ? hi(T2) : hi(tt2));
                 if (okA && !stopA) lastA = base + (uint32_t)j + 1u;
                 if (okB && !stopB) lastB = base + (uint32_t)j + 1u;

@@ -297,3 +297,4 @@ def test_frame_pipeline_matches_dropin_bitwise():
     torch.cuda.synchronize()
     for a, b in zip(himg, refs):
         assert torch.equal(a, b.cpu())
+
