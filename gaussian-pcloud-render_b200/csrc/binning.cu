@@ -22,7 +22,17 @@
 
 namespace {
 
-constexpr unsigned ST_AGG = 1u << 30, ST_INC = 2u << 30, ST_VAL = (1u << 30) - 1u;
+#ifdef GS_TIMELINE  // developer build: per-CTA phase timestamps (globaltimer, ns) of the binning kernels
+__device__ unsigned long long* g_bin_timeline = nullptr;
+__device__ __forceinline__ unsigned long long bin_gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define BIN_MARK(slot, k) do { if (g_bin_timeline && threadIdx.x == 0) g_bin_timeline[(size_t)(slot) * 8 + (k)] = bin_gtime(); } while (0)
+#else
+#define BIN_MARK(slot, k) do {} while (0)
+#endif
 
 __device__ __forceinline__ unsigned ld_volatile_u32(const unsigned* p) {
     return *reinterpret_cast<const volatile unsigned*>(p);
@@ -54,27 +64,72 @@ __device__ __forceinline__ unsigned match_bits(unsigned act, unsigned v) {
     return m;
 }
 
-// Decoupled look-back for one bin: sums the aggregates of chunks chunk-1, chunk-2, ... >= first until a chunk with
-// an inclusive prefix is met.  Status words carry flag (2 bits) + count (30 bits), so no fence is needed.
-// All chunks of a pass usually run concurrently (a few hundred CTAs), so walks are long: the predecessors are read
-// LB at a time (independent loads in flight) instead of one L2 round trip per step.
-template <int GS_LB>
-__device__ __forceinline__ unsigned look_back(const unsigned* __restrict__ status, int stride, int chunk, int first,
-                                              int bin) {
-    unsigned excl = 0;
-    for (int c = chunk - 1; c >= first; c -= GS_LB) {
-        unsigned s[GS_LB];
-#pragma unroll
-        for (int j = 0; j < GS_LB; j++)
-            s[j] = (c - j >= first) ? ld_volatile_u32(status + (size_t)(c - j) * stride + bin) : ST_INC;
-#pragma unroll
-        for (int j = 0; j < GS_LB; j++) {
-            while ((s[j] >> 30) == 0) s[j] = ld_volatile_u32(status + (size_t)(c - j) * stride + bin);
-            excl += s[j] & ST_VAL;
-            if (s[j] & ST_INC) return excl;
-        }
+// Chained prefix over the chunks of one pass (decoupled look-back, restated for the regime this pipeline runs in:
+// a few hundred chunks that are almost all resident at the same time, so a chunk usually finds NO predecessor with a
+// finished inclusive prefix and has to add up everything before it).  Per chunk a state word (0 / 1 = aggregates
+// published / 2 = inclusive prefixes published) guards two rows of nb counters.  A chunk publishes its aggregates,
+// finds the nearest predecessor whose inclusive prefix is ready (one coalesced read of up to NT state words), and
+// sums that prefix plus the aggregates in between with ALL its threads: thread = (4 bins, slice of the
+// predecessors), 16-byte loads, independent iterations -- a handful of L2 round trips instead of one per
+// predecessor.  Called by every thread of the CTA (blockDim.x == NT); s_tot[nb] in, s_excl[nb] out (shared).
+template <int NT>
+__device__ __forceinline__ void chain_prefix(const GsChain ch, int chunk, int first, int nb,
+                                             const uint32_t* s_tot, uint32_t* s_excl, uint32_t* s_part /*[4 NT]*/,
+                                             int* s_pstar) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    const bool head = chunk == first;
+    const size_t row = (size_t)chunk * GS_MAX_GRID;
+    for (int b = tid; b < nb; b += NT) {
+        __stcg(ch.agg + row + b, s_tot[b]);
+        if (head) __stcg(ch.inc + row + b, s_tot[b]);
     }
-    return excl;
+    __threadfence();
+    if (tid == 0) *s_pstar = first - 1;
+    __syncthreads();
+    if (tid == 0) st_volatile_u32(ch.state + chunk, head ? 2u : 1u);
+    if (head) {
+        for (int b = tid; b < nb; b += NT) s_excl[b] = 0;
+        __syncthreads();
+        return;
+    }
+    // nearest predecessor with an inclusive prefix; every predecessor after it is waited for (aggregate published)
+    for (int hi = chunk - 1; hi >= first; hi -= NT) {
+        const int pos = hi - tid;
+        unsigned st = 0;
+        if (pos >= first) {
+            do { st = ld_volatile_u32(ch.state + pos); } while (st == 0u);
+        }
+        const unsigned inc_lanes = __ballot_sync(GS_FULL, st == 2u);
+        if (inc_lanes != 0u && lane == __ffs(inc_lanes) - 1) atomicMax(s_pstar, pos);  // lanes descend in position
+        __syncthreads();
+        const int found = *s_pstar;
+        __syncthreads();  // nobody may update s_pstar (next window) before everybody has read it
+        if (found >= first) break;
+    }
+    __threadfence();
+    const int pstar = *s_pstar;
+    const int nq = (nb + 3) >> 2, S = NT / nq;
+    const int q = tid % nq, sl = tid / nq;
+    uint4 acc = make_uint4(0u, 0u, 0u, 0u);
+    if (sl < S) {
+        if (sl == 0 && pstar >= first) acc = __ldcg(reinterpret_cast<const uint4*>(ch.inc + (size_t)pstar * GS_MAX_GRID) + q);
+#pragma unroll 4
+        for (int p = chunk - 1 - sl; p > pstar; p -= S) {
+            const uint4 v = __ldcg(reinterpret_cast<const uint4*>(ch.agg + (size_t)p * GS_MAX_GRID) + q);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        reinterpret_cast<uint4*>(s_part)[sl * nq + q] = acc;
+    }
+    __syncthreads();
+    for (int b = tid; b < nb; b += NT) {
+        uint32_t e = 0;
+        for (int k = 0; k < S; k++) e += s_part[(k * nq + (b >> 2)) * 4 + (b & 3)];
+        s_excl[b] = e;
+        __stcg(ch.inc + row + b, e + s_tot[b]);
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) st_volatile_u32(ch.state + chunk, 2u);
 }
 
 // Row tables, recomputed by warp 0 of every CTA that needs them (<= 257 entries): prefix sum of the row difference
@@ -158,32 +213,52 @@ __global__ void __launch_bounds__(1024) depth_hist_kernel(const uint32_t* __rest
 
 // One LSD pass, onesweep style: a CTA owns GS_SORT_CHUNK consecutive keys (warp w the w-th 512, round r of a warp
 // the r-th 32), ranks them by digit with a ballot-based match + per-warp counters (stable: rounds in order, lanes in
-// order), obtains the number of equal-digit keys in all earlier chunks by decoupled look-back, and scatters.
+// order), obtains the number of equal-digit keys in all earlier chunks from the chunk chain, reorders its keys by
+// digit in shared memory and writes them out as contiguous runs (a direct scatter of 4-byte elements is limited to
+// about one 32-byte sector per clock and SM, measured 18 us per pass; runs are coalesced).
+#ifndef SORT_MATCH_HW
+#define SORT_MATCH_HW 0
+#endif
+#if SORT_MATCH_HW
+#define SORT_MATCH(act, v) __match_any_sync(act, v)
+#else
+#define SORT_MATCH(act, v) match_bits<8>(act, v)
+#endif
 #define SORT_THREADS 512
 #define SORT_WARPS (SORT_THREADS / 32)
 #define SORT_ROUNDS (GS_SORT_CHUNK / SORT_THREADS)
+#define SORT_SMEM ((2 * GS_SORT_CHUNK + SORT_WARPS * GS_RADIX + 4 * GS_RADIX + 4 * SORT_THREADS) * 4 + 64)
 __global__ void __launch_bounds__(SORT_THREADS) depth_pass_kernel(const uint32_t* __restrict__ key_in,
                                                                   const uint32_t* __restrict__ idx_in,
                                                                   uint32_t* __restrict__ key_out,
                                                                   uint32_t* __restrict__ idx_out,
                                                                   const uint32_t* __restrict__ hist,  // 256 totals
-                                                                  unsigned* __restrict__ status,  // [chunks][256]
-                                                                  unsigned* __restrict__ ticket, uint32_t P, int shift,
-                                                                  int first_pass) {
-    __shared__ uint32_t s_cnt[SORT_WARPS][GS_RADIX];
-    __shared__ uint32_t s_base[GS_RADIX];
-    __shared__ uint32_t s_wsum[8];
+                                                                  const GsChain chain, unsigned* __restrict__ ticket,
+                                                                  uint32_t P, int shift, int first_pass) {
+    extern __shared__ __align__(16) uint32_t s_sort[];
+    uint32_t* s_key = s_sort;                                // [GS_SORT_CHUNK] keys in digit order
+    uint32_t* s_val = s_key + GS_SORT_CHUNK;                 // [GS_SORT_CHUNK]
+    uint32_t* s_cnt = s_val + GS_SORT_CHUNK;                 // [SORT_WARPS][256]
+    uint32_t* s_tot = s_cnt + SORT_WARPS * GS_RADIX;         // [256] keys of this chunk per digit
+    uint32_t* s_excl = s_tot + GS_RADIX;                     // [256] keys of earlier chunks per digit
+    uint32_t* s_lstart = s_excl + GS_RADIX;                  // [256] first local position of each digit
+    uint32_t* s_gbase = s_lstart + GS_RADIX;                 // [256] global position of the chunk's first key of a digit
+    uint32_t* s_part = s_gbase + GS_RADIX;                   // [4 * SORT_THREADS] chain scratch
+    __shared__ uint32_t s_wsum[8], s_wsum2[8];
     __shared__ uint32_t s_chunk;
+    __shared__ int s_pstar;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_chunk = atomicAdd(ticket, 1u);
-    for (int i = tid; i < SORT_WARPS * GS_RADIX; i += SORT_THREADS) (&s_cnt[0][0])[i] = 0;
+    for (int i = tid; i < SORT_WARPS * GS_RADIX; i += SORT_THREADS) s_cnt[i] = 0;
     __syncthreads();
     const uint32_t chunk = s_chunk;
     const uint32_t base = chunk * GS_SORT_CHUNK + warp * (GS_SORT_CHUNK / SORT_WARPS);
+    const uint32_t tl_slot = (uint32_t)(shift / 8) * 1024u + chunk;
+    BIN_MARK(tl_slot, 0);
 
     uint32_t k[SORT_ROUNDS], v[SORT_ROUNDS];
     uint16_t rk[SORT_ROUNDS];
-    uint32_t* cnt = s_cnt[warp];
+    uint32_t* cnt = s_cnt + warp * GS_RADIX;
 #pragma unroll
     for (int r = 0; r < SORT_ROUNDS; r++) {
         const uint32_t i = base + r * 32 + lane;
@@ -198,7 +273,7 @@ __global__ void __launch_bounds__(SORT_THREADS) depth_pass_kernel(const uint32_t
         const unsigned act = __ballot_sync(GS_FULL, valid);
         uint32_t off = 0;
         if (valid) {
-            const unsigned m = match_bits<8>(act, d);
+            const unsigned m = SORT_MATCH(act, d);
             const unsigned before = __popc(m & ((1u << lane) - 1u));
             const uint32_t c0 = cnt[d];
             __syncwarp(act);
@@ -209,43 +284,56 @@ __global__ void __launch_bounds__(SORT_THREADS) depth_pass_kernel(const uint32_t
         rk[r] = (uint16_t)off;
     }
     __syncthreads();
-    // thread d < 256: exclusive scan of digit d over the warps, CTA total, look-back, global digit base
+    BIN_MARK(tl_slot, 1);
+    // thread d < 256: exclusive scan of digit d over the warps, chunk total; exclusive scans over the digits of the
+    // chunk totals (local digit starts) and of the global digit totals (global digit starts)
     if (tid < GS_RADIX) {
         uint32_t total = 0;
 #pragma unroll
         for (int w = 0; w < SORT_WARPS; w++) {
-            const uint32_t t = s_cnt[w][tid];
-            s_cnt[w][tid] = total;
+            const uint32_t t = s_cnt[w * GS_RADIX + tid];
+            s_cnt[w * GS_RADIX + tid] = total;
             total += t;
         }
-        st_volatile_u32(status + (size_t)chunk * GS_RADIX + tid, (chunk == 0 ? ST_INC : ST_AGG) | total);
-        // exclusive scan of the global digit totals over the 256 digits (one per thread)
+        s_tot[tid] = total;
         const uint32_t h = hist[tid];
-        const uint32_t incl = warp_incl_scan(h, lane);
-        if (lane == 31) s_wsum[warp] = incl;
+        const uint32_t incl_h = warp_incl_scan(h, lane), incl_t = warp_incl_scan(total, lane);
+        if (lane == 31) { s_wsum[warp] = incl_h; s_wsum2[warp] = incl_t; }
         asm volatile("bar.sync 1, 256;" ::: "memory");  // only the first 8 warps take part
-        uint32_t wpre = 0;
+        uint32_t wpre_h = 0, wpre_t = 0;
 #pragma unroll
         for (int w = 0; w < 8; w++)
-            if (w < warp) wpre += s_wsum[w];
-        uint32_t excl = 0;
-        if (chunk > 0) {
-            excl = look_back<16>(status, GS_RADIX, (int)chunk, 0, tid);
-            st_volatile_u32(status + (size_t)chunk * GS_RADIX + tid, ST_INC | (excl + total));
-        }
-        s_base[tid] = wpre + incl - h + excl;
+            if (w < warp) { wpre_h += s_wsum[w]; wpre_t += s_wsum2[w]; }
+        s_gbase[tid] = wpre_h + incl_h - h;
+        s_lstart[tid] = wpre_t + incl_t - total;
     }
     __syncthreads();
+    BIN_MARK(tl_slot, 2);
+    chain_prefix<SORT_THREADS>(chain, (int)chunk, 0, GS_RADIX, s_tot, s_excl, s_part, &s_pstar);
+    BIN_MARK(tl_slot, 3);
+    // reorder by digit in shared memory
 #pragma unroll
     for (int r = 0; r < SORT_ROUNDS; r++) {
         const uint32_t i = base + r * 32 + lane;
         if (i < P) {
             const uint32_t d = (k[r] >> shift) & 255u;
-            const uint32_t pos = s_base[d] + cnt[d] + rk[r];
-            key_out[pos] = k[r];
-            idx_out[pos] = v[r];
+            const uint32_t lp = s_lstart[d] + cnt[d] + rk[r];
+            s_key[lp] = k[r];
+            s_val[lp] = v[r];
         }
     }
+    __syncthreads();
+    BIN_MARK(tl_slot, 4);
+    const uint32_t n = min((uint32_t)GS_SORT_CHUNK, P - chunk * GS_SORT_CHUNK);
+#pragma unroll 4
+    for (uint32_t t = tid; t < n; t += SORT_THREADS) {
+        const uint32_t kk = s_key[t];
+        const uint32_t d = (kk >> shift) & 255u;
+        const uint32_t pos = s_gbase[d] + s_excl[d] + (t - s_lstart[d]);
+        key_out[pos] = kk;
+        idx_out[pos] = s_val[t];
+    }
+    BIN_MARK(tl_slot, 5);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -365,13 +453,23 @@ __global__ void __launch_bounds__(1024) plan_kernel(const uint32_t* __restrict__
 // stable rank of lane i's element in bin b is popc(mask[b] & lanes_below_i) + the elements of earlier rounds /
 // warps / chunks.  T is built with two ballot-based matches per round (group leaders store; no shared-memory atomics).
 #define PART_ROUNDS (GS_PART_CHUNK / 256)
+// Hardware MATCH.ANY vs 8-9 ballots: same latency here, but one issue slot instead of ~25; with several frames in
+// flight the binning kernels compete with the blend kernels of other frames for issue slots (+1.5 % frames/s).
+#ifndef PART_MATCH_HW
+#define PART_MATCH_HW 1
+#endif
+#if PART_MATCH_HW
+#define PART_MATCH(act, v) __match_any_sync(act, v)
+#else
+#define PART_MATCH(act, v) match_bits<(NB == 128) ? 8 : 9>(act, v)
+#endif
 
 template <int NB, int PASS>
 __global__ void __launch_bounds__(256, (NB == 128) ? 4 : 2) range_partition_kernel(
     const uint32_t* __restrict__ sorted_idx, const ushort4* __restrict__ rect, uint32_t P,  // PASS 1 input
     const uint2* __restrict__ items_in,                                                      // PASS 2 input
     const int* __restrict__ rdiff, int gx, int gy, const uint32_t* __restrict__ tile_start,
-    unsigned long long RowCap, unsigned* __restrict__ status, int stat_stride, unsigned* __restrict__ ticket,
+    unsigned long long RowCap, const GsChain chain, unsigned* __restrict__ ticket,
     GsHeader* __restrict__ hdr, uint2* __restrict__ items_out, uint32_t* __restrict__ list_out) {
     constexpr int G = NB / 32;    // bins per lane in the warp-wide scans
     constexpr int MS = NB + 4;    // mask row stride (words), multiple of 4 for the vectorised clear
@@ -379,7 +477,10 @@ __global__ void __launch_bounds__(256, (NB == 128) ? 4 : 2) range_partition_kern
     uint32_t* s_mask = s_dyn;                                         // [8 warps][PART_ROUNDS][MS]
     int* s_cnt = reinterpret_cast<int*>(s_dyn + 8 * PART_ROUNDS * MS);  // [8 warps][NB]: counts -> output positions
     __shared__ uint32_t s_rs[GS_MAX_GRID + 1], s_cf[GS_MAX_GRID + 1];
+    __shared__ uint32_t s_tot[NB], s_excl[NB];
+    __shared__ __align__(16) uint32_t s_part[4 * 256];
     __shared__ uint32_t s_chunk;
+    __shared__ int s_pstar;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (PASS == 2 && hdr->skip) return;
     if (warp == 0) row_tables(rdiff, gy, s_rs, s_cf, lane);
@@ -403,6 +504,8 @@ __global__ void __launch_bounds__(256, (NB == 128) ? 4 : 2) range_partition_kern
         __syncthreads();
         const uint32_t chunk = s_chunk;
         if (chunk >= nchunks) break;
+        const uint32_t tl_slot = 4096u + (uint32_t)(PASS - 1) * 16384u + chunk;
+        BIN_MARK(tl_slot, 0);
 
         // chunk -> item range and head of its look-back chain
         uint32_t ibeg, iend;
@@ -446,7 +549,7 @@ __global__ void __launch_bounds__(256, (NB == 128) ? 4 : 2) range_partition_kern
             const uint32_t lo = rng[r] & 0xffffu, hi = rng[r] >> 16;
             const unsigned act = __ballot_sync(GS_FULL, hi > lo);
             if (hi > lo) {
-                const unsigned m = match_bits<(NB == 128) ? 8 : 9>(act, lo);
+                const unsigned m = PART_MATCH(act, lo);
                 if ((m & lt) == 0) msk[r * MS + lo] = m;
             }
         }
@@ -456,7 +559,7 @@ __global__ void __launch_bounds__(256, (NB == 128) ? 4 : 2) range_partition_kern
             const uint32_t lo = rng[r] & 0xffffu, hi = rng[r] >> 16;
             const unsigned act = __ballot_sync(GS_FULL, hi > lo);
             if (hi > lo) {
-                const unsigned m = match_bits<(NB == 128) ? 8 : 9>(act, hi);
+                const unsigned m = PART_MATCH(act, hi);
                 if ((m & lt) == 0) msk[r * MS + hi] ^= m;
             }
         }
@@ -495,9 +598,10 @@ __global__ void __launch_bounds__(256, (NB == 128) ? 4 : 2) range_partition_kern
             for (int j = 0; j < G; j++) cnt[lane * G + j] = csum[j];
         }
         __syncthreads();
-        // ---- phase B: thread b = bin b: scan over warps, chunk aggregate, look-back, output base
+        BIN_MARK(tl_slot, 1);
+        // ---- phase B: thread b = bin b: scan over warps, chunk aggregate; chunk chain; output base
+        const int nb_used = (PASS == 1) ? gy : gx;
         if (tid < NB) {
-            const int nb_used = (PASS == 1) ? gy : gx;
             uint32_t total = 0;
 #pragma unroll
             for (int w = 0; w < 8; w++) {
@@ -505,18 +609,14 @@ __global__ void __launch_bounds__(256, (NB == 128) ? 4 : 2) range_partition_kern
                 s_cnt[w * NB + tid] = (int)total;
                 total += t;
             }
-            uint32_t basev = 0;
-            if (tid < nb_used) {
-                unsigned* st = status + (size_t)chunk * stat_stride + tid;
-                const bool head = (int)chunk == first;
-                st_volatile_u32(st, (head ? ST_INC : ST_AGG) | total);
-                uint32_t excl = 0;
-                if (!head) {
-                    excl = look_back<8>(status, stat_stride, (int)chunk, first, tid);
-                    st_volatile_u32(st, ST_INC | (excl + total));
-                }
-                basev = excl + ((PASS == 1) ? s_rs[tid] : tile_start[row * gx + tid]);
-            }
+            s_tot[tid] = total;
+        }
+        __syncthreads();
+        BIN_MARK(tl_slot, 2);
+        chain_prefix<256>(chain, (int)chunk, first, nb_used, s_tot, s_excl, s_part, &s_pstar);
+        BIN_MARK(tl_slot, 3);
+        if (tid < nb_used) {
+            const uint32_t basev = s_excl[tid] + ((PASS == 1) ? s_rs[tid] : tile_start[row * gx + tid]);
 #pragma unroll
             for (int w = 0; w < 8; w++) s_cnt[w * NB + tid] += (int)basev;
         }
@@ -535,25 +635,41 @@ __global__ void __launch_bounds__(256, (NB == 128) ? 4 : 2) range_partition_kern
             for (int j = 0; j < G; j++) cnt[lane * G + j] += __popc(msk[r * MS + lane * G + j]);
             __syncwarp();
         }
+        __syncthreads();
+        BIN_MARK(tl_slot, 4);
     }
 }
 
 }  // namespace
 
+#ifdef GS_TIMELINE
+extern "C" int gs_debug_bin_timeline(void* dev_buf) {
+    unsigned long long* p = (unsigned long long*)dev_buf;
+    return (int)cudaMemcpyToSymbol(g_bin_timeline, &p, sizeof(p));
+}
+#endif
+
 #define GS_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return e_; } while (0)
 
 cudaError_t gs_launch_depth_sort(const GsFrame& f, const GsGeom& g) {
     const uint32_t P = (uint32_t)f.s.P;
+    static bool attr_set = false;
+    if (!attr_set) {
+        GS_TRY(cudaFuncSetAttribute(depth_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_SMEM));
+        attr_set = true;
+    }
     const unsigned chunks = (unsigned)g.sort_chunks;
     depth_hist_kernel<<<(unsigned)min((size_t)64, gs_div_up(P, 8192)), 1024, 0, f.stream>>>(g.key[0], P, g.dhist);
     gs_note_launch();
     GS_TRY(cudaGetLastError());
     int side = 0;
     for (int pass = 0; pass < 4; pass++) {
-        depth_pass_kernel<<<chunks, SORT_THREADS, 0, f.stream>>>(g.key[side], g.idx[side], g.key[side ^ 1], g.idx[side ^ 1],
-                                                       g.dhist + pass * GS_RADIX,
-                                                       g.dstat + (size_t)pass * chunks * GS_RADIX,
-                                                       &g.hdr->tickets[pass], P, pass * GS_RADIX_BITS, pass == 0);
+        const GsChain ch = {g.dstate + (size_t)pass * chunks, g.dagg + (size_t)pass * chunks * GS_RADIX,
+                            g.dinc + (size_t)pass * chunks * GS_RADIX};
+        depth_pass_kernel<<<chunks, SORT_THREADS, SORT_SMEM, f.stream>>>(g.key[side], g.idx[side], g.key[side ^ 1],
+                                                                        g.idx[side ^ 1], g.dhist + pass * GS_RADIX, ch,
+                                                                        &g.hdr->tickets[pass], P, pass * GS_RADIX_BITS,
+                                                                        pass == 0);
         gs_note_launch();
         GS_TRY(cudaGetLastError());
         side ^= 1;
@@ -578,10 +694,11 @@ cudaError_t gs_launch_tile_lists(const GsFrame& f, const GsGeom& g, const GsBinn
     const unsigned grid1 = (unsigned)min((size_t)g_part_grid, g.row_chunks);
     const unsigned grid2 = (unsigned)min((size_t)g_part_grid, b.col_chunks);
     const unsigned long long rowcap = RowCap;
+    const GsChain ch_row = {g.rstate, g.ragg, g.rinc}, ch_col = {b.cstate, b.cagg, b.cinc};
 #define LAUNCH_PART(NB, PASS, GRID)                                                                               \
     range_partition_kernel<NB, PASS><<<GRID, 256, PART_SMEM(NB), f.stream>>>(                                     \
-        g.idx[0], g.rect, P, b.items, im.rdiff, f.gx, f.gy, im.tile_start, rowcap, (PASS == 1) ? g.rstat : b.cstat, \
-        GS_MAX_GRID, &g.hdr->tickets[3 + PASS], g.hdr, b.items, b.list)
+        g.idx[0], g.rect, P, b.items, im.rdiff, f.gx, f.gy, im.tile_start, rowcap, (PASS == 1) ? ch_row : ch_col, \
+        &g.hdr->tickets[3 + PASS], g.hdr, b.items, b.list)
     // row pass: Gaussians in depth order -> row items grouped by tile row
     if (f.gy <= 128) LAUNCH_PART(128, 1, grid1); else LAUNCH_PART(256, 1, grid1);
     gs_note_launch();

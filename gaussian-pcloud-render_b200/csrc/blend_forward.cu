@@ -417,7 +417,10 @@ __device__ __forceinline__ f2 mul2(f2 a, f2 b) { f2 r; asm("mul.rn.f32x2 %0, %1,
 __device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { f2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
 __device__ __forceinline__ void fma2_acc(f2& acc, f2 a, f2 b) { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b)); }
 
-__global__ void __launch_bounds__(BF_WARPS * 32, 4) blend_forward_px2_kernel(
+#ifndef BF_PX2_OCC
+#define BF_PX2_OCC 3
+#endif
+__global__ void __launch_bounds__(BF_WARPS * 32, BF_PX2_OCC) blend_forward_px2_kernel(
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ order, const uint32_t* __restrict__ list,
     const GsRec* __restrict__ rec, int W, int H, int gx, uint32_t num_tiles, GsHeader* __restrict__ hdr,
     const float* __restrict__ bg, float* __restrict__ final_T, uint32_t* __restrict__ n_contrib,

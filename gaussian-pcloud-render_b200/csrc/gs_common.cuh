@@ -4,8 +4,9 @@
 //   geometry buffer (per Gaussian, P entries)
 //     GsHeader            status block + counters (256 B)
 //     dhist [4][256] u32  digit histograms of the depth keys           } zeroed at the start of every frame
-//     dstat [4][C][256]   decoupled look-back state of the depth sort   } (C = ceil(P / 8192) chunks)
-//     rstat [C1][256]     look-back state of the row pass               } (C1 = ceil(P / 2048) chunks)
+//     dstate [4][C] u32   chunk states of the depth-sort chains          } (C = ceil(P / 8192) chunks)
+//     rstate [C1] u32     chunk states of the row-pass chain             } (C1 = ceil(P / 2048) chunks)
+//     dagg/dinc [4][C][256], ragg/rinc [C1][256] u32   per-chunk aggregates / inclusive prefixes (not zeroed)
 //     rec   [P] GsRec     48-B packed record read by the blend kernels (3 x float4)
 //     key   [2][P] u32    depth-sort keys (float bits of view-space z; 0xFFFFFFFF = culled), ping/pong
 //     idx   [2][P] u32    depth-sort values (Gaussian index), ping/pong
@@ -16,7 +17,8 @@
 //   binning buffer (per instance, R entries)
 //     list  [R] u32       final per-tile, depth-ordered Gaussian index list ("point_list"); FIRST, so that backward
 //                         finds it from num_rendered alone
-//     cstat [C2][NBX]     look-back state of the column pass (zeroed every frame)
+//     cstate [C2] u32     chunk states of the column-pass chains (zeroed every frame)
+//     cagg/cinc [C2][256] u32  per-chunk aggregates / inclusive prefixes (not zeroed)
 //     items [Rrow] uint2  row items after the row pass: (gaussian, x0 | x1 << 16), grouped by tile row, depth order
 //   image buffer
 //     rdiff [gy+1] i32    difference array of the row ranges -> row-item counts     } zeroed every
@@ -80,11 +82,21 @@ struct GsCarver {
 
 static inline __host__ __device__ size_t gs_div_up(size_t a, size_t b) { return (a + b - 1) / b; }
 
+// One chain of chunks with decoupled look-back (binning.cu: chain_prefix): state[c] = 0 / 1 (aggregate published) /
+// 2 (inclusive prefix published); agg / inc hold GS_MAX_GRID (= GS_RADIX) counters per chunk.
+struct GsChain {
+    unsigned* state;
+    uint32_t* agg;
+    uint32_t* inc;
+};
+
 struct GsGeom {
     GsHeader* hdr;
     uint32_t* dhist;   // [4][256]
-    uint32_t* dstat;   // [4][sort_chunks][256]
-    uint32_t* rstat;   // [row_chunks][256]
+    unsigned* dstate;  // [4][sort_chunks]
+    unsigned* rstate;  // [row_chunks]
+    uint32_t* dagg; uint32_t* dinc;  // [4][sort_chunks][256]
+    uint32_t* ragg; uint32_t* rinc;  // [row_chunks][256]
     GsRec* rec;
     uint32_t* key[2];
     uint32_t* idx[2];
@@ -99,9 +111,13 @@ struct GsGeom {
         sort_chunks = gs_div_up(P, GS_SORT_CHUNK);
         row_chunks = gs_div_up(P, GS_PART_CHUNK);
         dhist = c.take<uint32_t>(4 * GS_RADIX);
-        dstat = c.take<uint32_t>(4 * sort_chunks * GS_RADIX);
-        rstat = c.take<uint32_t>(row_chunks * GS_MAX_GRID);
-        zero_bytes = c.off;  // header + histograms + look-back state are zeroed at the start of every frame
+        dstate = c.take<unsigned>(4 * sort_chunks);
+        rstate = c.take<unsigned>(row_chunks);
+        zero_bytes = c.off;  // header + histograms + chunk states are zeroed at the start of every frame
+        dagg = c.take<uint32_t>(4 * sort_chunks * GS_RADIX);
+        dinc = c.take<uint32_t>(4 * sort_chunks * GS_RADIX);
+        ragg = c.take<uint32_t>(row_chunks * GS_MAX_GRID);
+        rinc = c.take<uint32_t>(row_chunks * GS_MAX_GRID);
         rec = c.take<GsRec>(P);
         key[0] = c.take<uint32_t>(P); key[1] = c.take<uint32_t>(P);
         idx[0] = c.take<uint32_t>(P); idx[1] = c.take<uint32_t>(P);
@@ -115,7 +131,8 @@ struct GsGeom {
 
 struct GsBinning {
     uint32_t* list;    // [Rcap]
-    uint32_t* cstat;   // [col_chunks][GS_MAX_GRID]
+    unsigned* cstate;  // [col_chunks]
+    uint32_t* cagg; uint32_t* cinc;  // [col_chunks][GS_MAX_GRID]
     uint2* items;      // [RowCap]
     size_t col_chunks, zero_off, zero_bytes, bytes;
     // Rcap = instance capacity, RowCap = row-item capacity (<= Rcap always holds for the true counts)
@@ -123,9 +140,11 @@ struct GsBinning {
         GsCarver c(base);
         list = c.take<uint32_t>(Rcap);
         col_chunks = gs_div_up(RowCap, GS_PART_CHUNK) + GS_MAX_GRID;
-        cstat = c.take<uint32_t>(col_chunks * GS_MAX_GRID);
-        zero_off = (size_t)(reinterpret_cast<char*>(cstat) - base);
+        cstate = c.take<unsigned>(col_chunks);
+        zero_off = (size_t)(reinterpret_cast<char*>(cstate) - base);
         zero_bytes = c.off - zero_off;
+        cagg = c.take<uint32_t>(col_chunks * GS_MAX_GRID);
+        cinc = c.take<uint32_t>(col_chunks * GS_MAX_GRID);
         items = c.take<uint2>(RowCap);
         bytes = c.off + GS_ALIGN;
     }
