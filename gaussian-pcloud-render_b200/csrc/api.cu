@@ -203,6 +203,23 @@ int32_t gs_forward_nosync(const GsScene* scene, char* geometry, char* binning, i
     return GS_OK;
 }
 
+int32_t gs_forward_recolor(const GsScene* scene, char* geometry, char* binning, char* image, float* out_color,
+                           void* stream) {
+    GsFrame f;
+    const int rc = make_frame(scene, stream, f);
+    if (rc != GS_OK) return rc;
+    if (!geometry || !binning || !image || !out_color) return GS_ERR_INVALID;
+    if (f.s.P == 0) return GS_OK;
+    GsGeom g(geometry, f.s.P);
+    GsImage im(image, (size_t)f.s.width * f.s.height, f.gx, f.gy);
+    GsBinning b(binning, 0, 0);  // only `list` (first array) is used
+    // restart the blend work queue (tickets 6..8); everything else in the header stays as the frame left it
+    GS_CU(cudaMemsetAsync(&g.hdr->tickets[6], 0, 3 * sizeof(unsigned int), f.stream));
+    GS_STAGE(gs_launch_recolor(f, g));
+    GS_STAGE(gs_launch_blend_forward(f, g, b, im, out_color));
+    return GS_OK;
+}
+
 void gs_profile_enable(int32_t on) { t_prof.on = on != 0; t_prof.armed = false; }
 
 int32_t gs_profile_read(float* ms4) {

@@ -192,6 +192,7 @@ struct GsFrame {  // host-side derived quantities handed to every launcher
 
 // stage launchers (each in its own translation unit)
 cudaError_t gs_launch_preprocess(const GsFrame& f, const GsGeom& g, const GsImage& im, int32_t* radii);
+cudaError_t gs_launch_recolor(const GsFrame& f, const GsGeom& g);  // colour-only pass (gs_forward_recolor)
 cudaError_t gs_launch_depth_sort(const GsFrame& f, const GsGeom& g);  // result in g.key[0] / g.idx[0]
 // row pass -> column histogram -> plan (ranges, tile_start, blend queue) -> column pass
 cudaError_t gs_launch_tile_lists(const GsFrame& f, const GsGeom& g, const GsBinning& b, size_t Rcap, size_t RowCap,

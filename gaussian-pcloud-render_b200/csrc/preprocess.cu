@@ -238,6 +238,27 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreArgs a) {
     }
 }
 
+// Colour-only pass over an already preprocessed frame (gs_forward_recolor): rewrites rec.c.xyz and the clamp bits.
+// A Gaussian culled by preprocess has no tile instance, so its record is never read and needs no update.
+__global__ void __launch_bounds__(256) recolor_kernel(int P, int D, int M, const float* __restrict__ means,
+                                                      const float* __restrict__ shs, const float* __restrict__ colors_pre,
+                                                      const float* __restrict__ campos, const uint32_t* __restrict__ ntile,
+                                                      GsRec* __restrict__ rec, uint8_t* __restrict__ clamp) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P || ntile[i] == 0u) return;
+    float3 rgb;
+    if (colors_pre != nullptr) {
+        rgb = make_float3(colors_pre[3 * i], colors_pre[3 * i + 1], colors_pre[3 * i + 2]);
+    } else {
+        unsigned clamp_bits = 0;
+        const float3 mean = make_float3(means[3 * i], means[3 * i + 1], means[3 * i + 2]);
+        rgb = sh_to_rgb(D, shs + (size_t)i * M * 3, mean, make_float3(campos[0], campos[1], campos[2]), clamp_bits);
+        clamp[i] = (uint8_t)clamp_bits;
+    }
+    float* c = reinterpret_cast<float*>(&rec[i].c);
+    c[0] = rgb.x; c[1] = rgb.y; c[2] = rgb.z;
+}
+
 __global__ void mark_visible_kernel(int P, const float* __restrict__ means, const float* __restrict__ view,
                                     uint8_t* __restrict__ present) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -280,6 +301,14 @@ cudaError_t gs_launch_preprocess(const GsFrame& f, const GsGeom& g, const GsImag
     }
     if (staged) preprocess_kernel<true><<<(unsigned)gs_div_up(s.P, 256), 256, stage_bytes, f.stream>>>(a);
     else preprocess_kernel<false><<<(unsigned)gs_div_up(s.P, 256), 256, 0, f.stream>>>(a);
+    gs_note_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t gs_launch_recolor(const GsFrame& f, const GsGeom& g) {
+    const GsScene& s = f.s;
+    recolor_kernel<<<(unsigned)gs_div_up(s.P, 256), 256, 0, f.stream>>>(s.P, s.sh_degree, s.sh_stride, s.means3D, s.shs,
+                                                                       s.colors_precomp, s.campos, g.ntile, g.rec, g.clamp);
     gs_note_launch();
     return cudaGetLastError();
 }

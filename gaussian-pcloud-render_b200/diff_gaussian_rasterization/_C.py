@@ -68,6 +68,8 @@ def lib() -> C.CDLL:
         L.gs_forward_nosync.restype = C.c_int32
         L.gs_forward_nosync.argtypes = [C.POINTER(GsScene), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p]
+        L.gs_forward_recolor.restype = C.c_int32
+        L.gs_forward_recolor.argtypes = [C.POINTER(GsScene), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.gs_read_status.restype = C.c_int32
         L.gs_read_status.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.gs_backward.restype = C.c_int32

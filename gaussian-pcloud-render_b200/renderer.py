@@ -80,6 +80,31 @@ class FrameRenderer:
                       "gs_read_status")
         return out
 
+    def enqueue_pass(self, view_dev, out_color: torch.Tensor, *, colors_precomp: Optional[torch.Tensor] = None,
+                     shs: Optional[torch.Tensor] = None, sh_degree: Optional[int] = None, tile_rows=None) -> torch.Tensor:
+        """Another colour pass over the frame this renderer enqueued last (same cloud geometry, same view): only
+        the per-Gaussian colours are recomputed and the blend re-run -- preprocess, depth sort and tile lists are
+        reused (the reference's caller renders position / RGB / hit-map / normal passes per view).
+        Exactly one of colors_precomp (P,3) / shs (P,M,3) is given; the result goes to `out_color` (3,H,W)."""
+        if (colors_precomp is None) == (shs is None):
+            raise ValueError("give exactly one of colors_precomp / shs")
+        viewmatrix, projmatrix, campos, tanx, tany = view_dev
+        f32 = lambda t: None if t is None else t.to(self.dev, torch.float32).contiguous()
+        cp, sh = f32(colors_precomp), f32(shs)
+        scene = _C.make_scene(P=self.P, sh_degree=int(self.sh_degree if sh_degree is None else sh_degree),
+                              sh_stride=0 if sh is None else int(sh.shape[1]), width=self.W, height=self.H,
+                              tan_fovx=float(tanx), tan_fovy=float(tany), scale_modifier=1.0, prefiltered=False,
+                              debug=False, background=self.bg, means3D=self.means3D, shs=sh, colors_precomp=cp,
+                              opacities=self.opacities, scales=self.scales, rotations=self.rotations,
+                              cov3D_precomp=None, viewmatrix=viewmatrix, projmatrix=projmatrix, campos=campos,
+                              tile_rows=tile_rows if tile_rows is not None else self.tile_rows)
+        with torch.cuda.device(self.dev):
+            st = torch.cuda.current_stream(self.dev).cuda_stream
+            _C._check(self.L.gs_forward_recolor(C.byref(scene), self.geom.data_ptr(), self.binning.data_ptr(),
+                                                self.img.data_ptr(), out_color.data_ptr(), st), "gs_forward_recolor")
+        self._keep = (cp, sh)  # keep the converted tensors alive until the stream has consumed them
+        return out_color
+
     def status(self, slot: int = 0) -> Tuple[int, int, int]:
         """(num_rendered, num_visible, code) of the frame enqueued with `slot`; call after synchronising the stream."""
         nr = int(self.status_host[slot % self.SLOTS, 0])

@@ -94,6 +94,15 @@ size_t gs_binning_bytes(int64_t num_rendered_capacity, int32_t P, int32_t width,
 int32_t gs_forward_nosync(const GsScene* scene, char* geometry, char* binning, int64_t num_rendered_capacity,
                           char* image, float* out_color, int32_t* radii, void* stream);
 
+/* Additional colour pass over the SAME geometry and camera (the reference's caller rasterizes every
+ * view four times -- position, RGB, hit-map and normal passes, simple_raw_render.py:411-522 -- and re-does the
+ * identical preprocess + sort each time).  geometry/binning/image must hold a frame rendered by gs_forward[_nosync]
+ * with the same means/covariances/opacities/camera/raster size; only scene->shs (+ sh_degree/sh_stride) or
+ * scene->colors_precomp are read anew.  Recomputes the per-Gaussian colours and re-runs the blend into out_color:
+ * bit-identical to a full forward with those colours.  Forward only (the buffers then describe THIS pass). */
+int32_t gs_forward_recolor(const GsScene* scene, char* geometry, char* binning, char* image, float* out_color,
+                           void* stream);
+
 typedef struct GsStatus {
     int64_t num_rendered;
     int32_t num_visible;

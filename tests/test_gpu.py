@@ -320,3 +320,31 @@ def test_odd_sizes_match_cpu_oracle(P, W, H, oracle32):
     for k, t in leaves.items():
         ref = gr[GRAD_KEYS[k]].reshape(t.grad.shape)
         assert np.abs(t.grad.cpu().numpy() - ref).max() <= GRAD_RTOL * (np.abs(ref).max() + 1e-12) + 1e-9, k
+
+
+def test_colour_passes_reuse_geometry_bitwise():
+    """gs_forward_recolor: extra colour passes over one preprocessed + binned frame equal full,
+    independent forwards with those colours -- the reference caller's position / RGB / hit-map / normal passes."""
+    dev = _dev()
+    from renderer import FrameRenderer
+    cl = scenes.human_cloud(50000, scale_factor=300.0, seed=11, opacity="uniform")
+    v = scenes.make_view(scenes.orbit_c2w(12)[2], 640, 400)
+    base = dict(means3D=cl["means3D"], opacities=cl["opacities"], W=640, H=400, viewmatrix=v.viewmatrix,
+                projmatrix=v.projmatrix, campos=v.campos, bg=np.ones(3, np.float32), tanfovx=v.tanfovx,
+                tanfovy=v.tanfovy, scales=cl["scales"], rotations=cl["rotations"])
+    rng = np.random.default_rng(5)
+    normals = torch.from_numpy(rng.standard_normal((50000, 3)).astype(np.float32))
+    passes = [dict(colors_precomp=cl["means3D"]), dict(shs=cl["shs"], sh_degree=1),
+              dict(colors_precomp=torch.ones(50000, 3)), dict(colors_precomp=normals)]
+    refs = []
+    for p in passes:
+        kw = dict(base, sh_degree=p.get("sh_degree", 0), **{k: x for k, x in p.items() if k != "sh_degree"})
+        refs.append(_render(kw, dev)[0].clone())
+    fr = FrameRenderer(cl, 640, 400, [1, 1, 1], dev, capacity=6_000_000)
+    vd = fr.upload_view(v)
+    fr.enqueue(vd)  # full frame once (the cloud's own SH colours)
+    outs = [fr.enqueue_pass(vd, torch.empty((3, 400, 640), device=dev), **p).clone() for p in passes]
+    torch.cuda.synchronize()
+    assert fr.status()[2] == 0
+    for a, b in zip(outs, refs):
+        assert torch.equal(a, b)
