@@ -166,8 +166,13 @@ def run_b200(args, rank, world):
             rng = _C.fetch("ranges", scene, fr.geom, fr.binning, fr.img, fr.capacity).view(-1, 2).to(torch.int64)
             inst = (rng[:, 1] - rng[:, 0]).view(gy, -1)
             parts.append(balanced_rows(sharding.row_cost(need.cpu().numpy(), inst.numpy()), world))
-    if world > 1:
-        import torch.distributed as dist
+    peer = None
+    if tiles_mode and args.exchange == "peer":
+        try:  # frame images in symmetric memory: the blend kernel stores its rows into every rank's image
+            peer = sharding.PeerFrame(H, W, dev)
+        except Exception as ex:  # noqa: BLE001
+            if rank == 0:
+                print(f"[bench] symmetric memory unavailable ({ex!r}); using the NCCL all-gather", file=sys.stderr)
 
     def frame(i, slot):
         if not tiles_mode:  # view-parallel: this rank's i-th frame is view rank + i*world of the orbit
@@ -176,9 +181,15 @@ def run_b200(args, rank, world):
             v = vdev[i % nv]
             rows = parts[i % nv]
             r0, r1 = rows[rank]
-            if r1 > r0:
-                fr.enqueue(v, tile_rows=(r0, r1), slot=slot)
-            sharding.exchange_image(fr.color, rows, rank)
+            if peer is not None:
+                _img, ptrs, peer_barrier = peer.next()
+                if r1 > r0:
+                    fr.enqueue(v, tile_rows=(r0, r1), slot=slot, peer_out=ptrs)
+                peer_barrier()
+            else:
+                if r1 > r0:
+                    fr.enqueue(v, tile_rows=(r0, r1), slot=slot)
+                sharding.exchange_image(fr.color, rows, rank)
 
     pipe.begin()
     for i in range(args.warmup):
@@ -347,7 +358,9 @@ def run_b200(args, rank, world):
                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if tiles_mode else "weak",
                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                "config": {"workload": f"{args.workload}: {w['desc']}", "parallelism": "single GPU" if world == 1 else
-                          (f"tile-row sharded x{world}, work-balanced rows, one image collective per frame" if tiles_mode
+                          (f"tile-row sharded x{world}, work-balanced rows, " +
+                           ("blend epilogue stores into all ranks' images over NVLink + one barrier per frame"
+                            if peer is not None else "one NCCL all-gather per frame") if tiles_mode
                            else f"view-parallel x{world}: rank r renders views r, r+{world}, ... (no collective)"),
                           "l2_policy": "inputs larger than L2 (160 MB of attributes per frame; consecutive steps render different views)",
                           "frames_in_flight": pipe.depth,
@@ -478,6 +491,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--streams", type=int, default=4, help="frames in flight (one CUDA stream + workspace each)")
     ap.add_argument("--parallel", default="views", choices=["views", "tiles"], help="multi-GPU sharding (N > 1)")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "allgather"],
+                    help="tiles mode: blend epilogue stores into peer images (symmetric memory) or NCCL all-gather")
     ap.add_argument("--stage-timing", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

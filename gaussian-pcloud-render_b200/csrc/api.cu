@@ -66,6 +66,9 @@ int make_frame(const GsScene* s, void* stream, GsFrame& f, bool forward = true) 
         if (s->shs && s->sh_stride < (s->sh_degree + 1) * (s->sh_degree + 1)) return GS_ERR_INVALID;
         if (s->sh_degree < 0 || s->sh_degree > 3) return GS_ERR_INVALID;
     }
+    if (s->num_peers < 0 || s->num_peers > 8) return GS_ERR_INVALID;
+    for (int k = 0; k < s->num_peers; k++)
+        if (!s->peer_out_color[k]) return GS_ERR_INVALID;
     f.s = *s;
     f.gx = (s->width + GS_TILE - 1) / GS_TILE;
     f.gy = (s->height + GS_TILE - 1) / GS_TILE;
@@ -213,8 +216,8 @@ int32_t gs_forward_recolor(const GsScene* scene, char* geometry, char* binning, 
     GsGeom g(geometry, f.s.P);
     GsImage im(image, (size_t)f.s.width * f.s.height, f.gx, f.gy);
     GsBinning b(binning, 0, 0);  // only `list` (first array) is used
-    // restart the blend work queue (tickets 6..8); everything else in the header stays as the frame left it
-    GS_CU(cudaMemsetAsync(&g.hdr->tickets[6], 0, 3 * sizeof(unsigned int), f.stream));
+    // restart the blend work queue; everything else in the header stays as the frame left it
+    GS_CU(cudaMemsetAsync(&g.hdr->tickets[6], 0, sizeof(unsigned int), f.stream));
     GS_STAGE(gs_launch_recolor(f, g));
     GS_STAGE(gs_launch_blend_forward(f, g, b, im, out_color));
     return GS_OK;

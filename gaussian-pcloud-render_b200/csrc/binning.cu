@@ -425,7 +425,6 @@ __global__ void __launch_bounds__(1024) plan_kernel(const uint32_t* __restrict__
         uint32_t acc = 0;
         for (int k = 0; k < 33; k++) { s_slot[k] = acc; acc += s_cnt[k]; }
         hdr->nonempty_tiles = acc - s_cnt[32];  // slot 32 = empty tiles, at the end of the order
-        hdr->tickets[9] = (acc - s_cnt[32]) * 8u + s_cnt[32];  // blend tasks of this frame (blend_forward.cu)
     }
     __syncthreads();
     for (int t = t_begin; t < t_end; t++) {

@@ -23,8 +23,6 @@
 //   image buffer
 //     rdiff [gy+1] i32    difference array of the row ranges -> row-item counts     } zeroed every
 //     tcount [Tn] u32     instances per tile (column histogram of the row items)   } frame
-//     bf_task [8192] uint4  split queue of the blend kernel                         }
-//     bf_state [8192][5][32] f32  pixel state handed over with a split-off task
 //     final_T [N] f32, n_contrib [N] u32, ranges [Tn] uint2, order [Tn] u32 (longest-list-first tile queue),
 //     tile_start [Tn+1] u32
 #pragma once
@@ -53,7 +51,7 @@ struct GsHeader {  // lives at offset 0 of the geometry buffer
     unsigned int skip;           // 1 = instance / row-item capacity exceeded (no-sync mode): the frame is skipped
     unsigned int pad0;
     unsigned int tickets[16];    // 0-3 depth-sort passes, 4 row pass, 5 column pass, 6 blend work queue,
-                                 // 7/8 head/tail of the blend split queue, 9 unfinished blend tasks
+                                 // 10 blend-backward work queue
     unsigned int pad[40];
 };
 static_assert(sizeof(GsHeader) == 256, "header is one aligned slot");
@@ -78,7 +76,6 @@ struct GsCarver {
 #define GS_SORT_CHUNK 8192   // depth keys per CTA and pass
 #define GS_PART_CHUNK 2048   // items per CTA of the row / column partition passes
 #define GS_MAX_GRID 256      // at most 256 x 256 tiles (4096 x 4096 pixels)
-#define GS_BF_QCAP 8192      // capacity of the blend kernel's split queue (tasks handed to idle warps)
 
 static inline __host__ __device__ size_t gs_div_up(size_t a, size_t b) { return (a + b - 1) / b; }
 
@@ -153,8 +150,6 @@ struct GsBinning {
 struct GsImage {
     int* rdiff;        // [gy+1]
     uint32_t* tcount;  // [Tn]
-    uint4* bf_task;    // [GS_BF_QCAP] split-off blend tasks (blend_forward.cu): unit, first instance, pixel rect, ready
-    float* bf_state;   // [GS_BF_QCAP][5][32] per-pixel T, C0..2, last contributor (sign bit of T = pixel finished)
     float* final_T;
     uint32_t* n_contrib;
     uint2* ranges;
@@ -166,9 +161,7 @@ struct GsImage {
         const size_t Tn = gx * gy;
         rdiff = c.take<int>(gy + 1);
         tcount = c.take<uint32_t>(Tn);
-        bf_task = c.take<uint4>(GS_BF_QCAP);
         zero_bytes = c.off;
-        bf_state = c.take<float>((size_t)GS_BF_QCAP * 5 * 32);
         final_T = c.take<float>(N);
         n_contrib = c.take<uint32_t>(N);
         ranges = c.take<uint2>(Tn);

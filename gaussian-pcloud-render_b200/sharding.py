@@ -73,3 +73,30 @@ def exchange_image(color: torch.Tensor, rows: Sequence[Tuple[int, int]], rank: i
         if r != rank and b > a:
             color[:, a:b, :] = slabs[r][:, : b - a, :]
     return color
+
+
+class PeerFrame:
+    """Frame images in symmetric memory (torch.distributed._symmetric_memory): every rank can address every rank's
+    (3,H,W) image through NVLink peer mappings, so the blend kernel writes its tile rows straight into all of them
+    (GsScene.peer_out_color) and one symmetric-memory barrier replaces the image collective.  Images are
+    double-buffered: a rank overwrites buffer k of its peers only two frames later, i.e. after a barrier that the
+    peers reach once they are done with frame k (stream order), so one barrier per frame suffices."""
+
+    def __init__(self, H: int, W: int, device, group=None, buffers: int = 2):
+        import torch.distributed._symmetric_memory as symm
+        group = dist.group.WORLD if group is None else group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.images, self.handles, self.peer_ptrs = [], [], []
+        for _ in range(buffers):
+            t = symm.empty((3, H, W), dtype=torch.float32, device=device)
+            h = symm.rendezvous(t, group)
+            self.images.append(t)
+            self.handles.append(h)
+            self.peer_ptrs.append([h.get_buffer(r, (3, H, W), torch.float32).data_ptr() for r in range(self.world)])
+        self.turn = 0
+
+    def next(self):
+        """(image of this rank, device pointers of all ranks' images, barrier callable) for the next frame."""
+        k = self.turn % len(self.images)
+        self.turn += 1
+        return self.images[k], self.peer_ptrs[k], self.handles[k].barrier

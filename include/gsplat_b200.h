@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define GS_ABI_VERSION 1
+#define GS_ABI_VERSION 2
 
 enum {
     GS_OK = 0,
@@ -65,6 +65,13 @@ typedef struct GsScene {
     const float* viewmatrix;     /* [16] */
     const float* projmatrix;     /* [16] */
     const float* campos;         /* [3] */
+    /* Multi-GPU tile-row sharding with peer stores: when num_peers > 0 the blend epilogue writes this
+     * shard's pixels into EVERY listed image (peer-mapped device pointers over NVLink, normally including this
+     * rank's own image) instead of into out_color, so the frame is assembled on all GPUs by the blend kernel itself
+     * and only a barrier follows.  0 = write out_color only. */
+    int32_t num_peers;
+    int32_t reserved;
+    float* peer_out_color[8];    /* each [3][H][W] */
 } GsScene;
 
 /* Growable scratch buffer: fn(user, bytes) must return a DEVICE pointer to at least `bytes` bytes that stays

@@ -348,3 +348,20 @@ def test_colour_passes_reuse_geometry_bitwise():
     assert fr.status()[2] == 0
     for a, b in zip(outs, refs):
         assert torch.equal(a, b)
+
+
+def test_peer_store_tile_sharding_two_gpus():
+    """Tile-row shards written by the blend epilogue into every rank's symmetric-memory image (NVLink peer stores +
+    one barrier) assemble the single-GPU frame bit for bit.  Needs two GPUs (skipped on the one-GPU test box;
+    run by hand with `gpurun --gpus 2`)."""
+    _dev()
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import os
+    import subprocess
+    import sys
+    from conftest import ROOT
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29577",
+                          os.path.join(ROOT, "tools", "peer_check.py")], capture_output=True, text=True, timeout=600)
+    assert "PEER CHECK OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
