@@ -69,6 +69,9 @@ int make_frame(const GsScene* s, void* stream, GsFrame& f, bool forward = true) 
     if (s->num_peers < 0 || s->num_peers > 8) return GS_ERR_INVALID;
     for (int k = 0; k < s->num_peers; k++)
         if (!s->peer_out_color[k]) return GS_ERR_INVALID;
+    if (s->num_extra < 0 || s->num_extra > 3) return GS_ERR_INVALID;
+    for (int k = 0; k < s->num_extra; k++)
+        if (!s->extra_colors[k] || !s->extra_out[k]) return GS_ERR_INVALID;
     f.s = *s;
     f.gx = (s->width + GS_TILE - 1) / GS_TILE;
     f.gy = (s->height + GS_TILE - 1) / GS_TILE;
@@ -174,6 +177,7 @@ int64_t gs_forward(const GsScene* scene, GsBuffer geometry, GsBuffer binning, Gs
     GS_CU(cudaMemsetAsync(bptr + b.zero_off, 0, b.zero_bytes, f.stream));
     GS_STAGE(gs_launch_tile_lists(f, g, b, (size_t)R, rows, im));
     t_prof.mark(3, f.stream);
+    GS_STAGE(gs_launch_pack_extra(f, g));
     GS_STAGE(gs_launch_blend_forward(f, g, b, im, out_color));
     t_prof.mark(4, f.stream);
     return (int64_t)R;
@@ -201,6 +205,7 @@ int32_t gs_forward_nosync(const GsScene* scene, char* geometry, char* binning, i
     t_prof.mark(2, f.stream);
     GS_STAGE(gs_launch_tile_lists(f, g, b, (size_t)cap, rowcap, im));
     t_prof.mark(3, f.stream);
+    GS_STAGE(gs_launch_pack_extra(f, g));
     GS_STAGE(gs_launch_blend_forward(f, g, b, im, out_color));
     t_prof.mark(4, f.stream);
     return GS_OK;
@@ -219,6 +224,7 @@ int32_t gs_forward_recolor(const GsScene* scene, char* geometry, char* binning, 
     // restart the blend work queue; everything else in the header stays as the frame left it
     GS_CU(cudaMemsetAsync(&g.hdr->tickets[6], 0, sizeof(unsigned int), f.stream));
     GS_STAGE(gs_launch_recolor(f, g));
+    GS_STAGE(gs_launch_pack_extra(f, g));
     GS_STAGE(gs_launch_blend_forward(f, g, b, im, out_color));
     return GS_OK;
 }

@@ -88,10 +88,18 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 #define BF_STAGES 3  // per-warp ring of 32-record batches: one being blended, two in flight
 
+template <int K>
 struct BfStage {
     float4 a[32];  // x, y, conic.x, conic.y
     float4 b[32];  // conic.z, opacity, thr, -B/C
     float4 c[32];  // r, g, b, -B/A
+    float4 e[K > 0 ? K : 1][32];  // colours of the extra passes (K > 0)
+};
+
+// Images of the extra colour passes blended in the same list walk (GsScene.extra_colors / extra_out).
+struct BfExtra {
+    const float4* xrec;  // [P][3]
+    float* out[3];
 };
 
 #define BF_CHECK 16  // batches between two looks at which pixels of the block are still live
@@ -115,17 +123,19 @@ __device__ __forceinline__ void fma2_acc(f2& acc, f2 a, f2 b) { asm("fma.rn.f32x
 #ifndef BF_PX2_OCC
 #define BF_PX2_OCC 3
 #endif
-__global__ void __launch_bounds__(BF_WARPS * 32, BF_PX2_OCC) blend_forward_px2_kernel(
+template <int K>
+__global__ void __launch_bounds__(BF_WARPS * 32, (K == 0) ? BF_PX2_OCC : 2) blend_forward_px2_kernel(
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ order, const uint32_t* __restrict__ list,
     const GsRec* __restrict__ rec, int W, int H, int gx, uint32_t num_tiles, GsHeader* __restrict__ hdr,
     const float* __restrict__ bg, float* __restrict__ final_T, uint32_t* __restrict__ n_contrib,
-    const BfTargets tg) {
-    __shared__ BfStage s_ring[BF_WARPS][BF_STAGES];
+    const BfTargets tg, const BfExtra ex) {
+    extern __shared__ __align__(16) unsigned char s_ring_raw[];
+    BfStage<K>(*s_ring)[BF_STAGES] = reinterpret_cast<BfStage<K>(*)[BF_STAGES]>(s_ring_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int lx = lane & 7, ly = lane >> 3;
     const float bg0 = bg[0], bg1 = bg[1], bg2 = bg[2];
     const size_t plane = (size_t)H * W;
-    BfStage* __restrict__ ring = s_ring[warp];
+    BfStage<K>* __restrict__ ring = s_ring[warp];
     unsigned* const q_fresh = &hdr->tickets[6];
     const uint32_t nonempty = hdr->nonempty_tiles;
     const uint32_t blend_units = nonempty * 4u;
@@ -152,6 +162,13 @@ __global__ void __launch_bounds__(BF_WARPS * 32, BF_PX2_OCC) blend_forward_px2_k
                             *reinterpret_cast<float4*>(oc + plane + pid) = make_float4(bg1, bg1, bg1, bg1);
                             *reinterpret_cast<float4*>(oc + 2 * plane + pid) = make_float4(bg2, bg2, bg2, bg2);
                         }
+#pragma unroll
+                        for (int k = 0; k < K; k++) {
+                            float* oc = ex.out[k];
+                            *reinterpret_cast<float4*>(oc + pid) = make_float4(bg0, bg0, bg0, bg0);
+                            *reinterpret_cast<float4*>(oc + plane + pid) = make_float4(bg1, bg1, bg1, bg1);
+                            *reinterpret_cast<float4*>(oc + 2 * plane + pid) = make_float4(bg2, bg2, bg2, bg2);
+                        }
                         *reinterpret_cast<float4*>(final_T + pid) = make_float4(1.f, 1.f, 1.f, 1.f);
                         *reinterpret_cast<uint4*>(n_contrib + pid) = make_uint4(0u, 0u, 0u, 0u);
                     }
@@ -163,6 +180,11 @@ __global__ void __launch_bounds__(BF_WARPS * 32, BF_PX2_OCC) blend_forward_px2_k
                         const size_t pid = (size_t)W * py + px;
                         _Pragma("unroll") for (int k = 0; k < 8; k++) if (k < tg.n) {
                             float* oc = tg.img[k];
+                            oc[pid] = bg0; oc[plane + pid] = bg1; oc[2 * plane + pid] = bg2;
+                        }
+#pragma unroll
+                        for (int k = 0; k < K; k++) {
+                            float* oc = ex.out[k];
                             oc[pid] = bg0; oc[plane + pid] = bg1; oc[2 * plane + pid] = bg2;
                         }
                         final_T[pid] = 1.f; n_contrib[pid] = 0u;
@@ -188,16 +210,22 @@ __global__ void __launch_bounds__(BF_WARPS * 32, BF_PX2_OCC) blend_forward_px2_k
 
         bool doneA = !insA, doneB = !insB;
         f2 T2 = bc(1.0f), C0 = bc(0.f), C1 = bc(0.f), C2 = bc(0.f);
+        f2 E[K > 0 ? K : 1][3];
+#pragma unroll
+        for (int k = 0; k < K; k++) { E[k][0] = bc(0.f); E[k][1] = bc(0.f); E[k][2] = bc(0.f); }
         uint32_t lastA = 0, lastB = 0;
 
         __syncwarp();
 #pragma unroll
         for (int p = 0; p < 2; p++) {
             if (p * 32 + lane < total) {
-                const GsRec* r = rec + lst[p * 32 + lane];
+                const uint32_t id = lst[p * 32 + lane];
+                const GsRec* r = rec + id;
                 cp_async16(&ring[p].a[lane], &r->a);
                 cp_async16(&ring[p].b[lane], &r->b);
                 cp_async16(&ring[p].c[lane], &r->c);
+#pragma unroll
+                for (int k = 0; k < K; k++) cp_async16(&ring[p].e[k][lane], ex.xrec + 3 * (size_t)id + k);
             }
             cp_async_commit();
         }
@@ -229,11 +257,13 @@ __global__ void __launch_bounds__(BF_WARPS * 32, BF_PX2_OCC) blend_forward_px2_k
                     cp_async16(&ring[nst].a[lane], &r->a);
                     cp_async16(&ring[nst].b[lane], &r->b);
                     cp_async16(&ring[nst].c[lane], &r->c);
+#pragma unroll
+                    for (int k = 0; k < K; k++) cp_async16(&ring[nst].e[k][lane], ex.xrec + 3 * (size_t)id_next + k);
                 }
                 cp_async_commit();
                 if (base + 96 + lane < total) id_next = lst[base + 96 + lane];
             }
-            const BfStage& st = ring[stage];
+            const BfStage<K>& st = ring[stage];
             stage = (stage + 1 == BF_STAGES) ? 0 : stage + 1;
 
             bool hit = false;
@@ -278,6 +308,13 @@ __global__ void __launch_bounds__(BF_WARPS * 32, BF_PX2_OCC) blend_forward_px2_k
                 fma2_acc(C0, mul2(bc(gc.x), a2), T2);
                 fma2_acc(C1, mul2(bc(gc.y), a2), T2);
                 fma2_acc(C2, mul2(bc(gc.z), a2), T2);
+#pragma unroll
+                for (int k = 0; k < K; k++) {  // the extra passes: same alpha, same T, other colours
+                    const float4 ge = st.e[k][j];
+                    fma2_acc(E[k][0], mul2(bc(ge.x), a2), T2);
+                    fma2_acc(E[k][1], mul2(bc(ge.y), a2), T2);
+                    fma2_acc(E[k][2], mul2(bc(ge.z), a2), T2);
+                }
                 T2 = pk(stopA ? lo(T2) : lo(tt2), stopB ? hi(T2) : hi(tt2));
                 if (okA && !stopA) lastA = base + (uint32_t)j + 1u;
                 if (okB && !stopB) lastB = base + (uint32_t)j + 1u;
@@ -297,6 +334,12 @@ __global__ void __launch_bounds__(BF_WARPS * 32, BF_PX2_OCC) blend_forward_px2_k
                 float* oc = tg.img[k];
                 oc[pid] = o0; oc[plane + pid] = o1; oc[2 * plane + pid] = o2;
             }
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                float* oc = ex.out[k];
+                oc[pid] = lo(E[k][0]) + T * bg0; oc[plane + pid] = lo(E[k][1]) + T * bg1;
+                oc[2 * plane + pid] = lo(E[k][2]) + T * bg2;
+            }
         }
         if (insB) {
             const size_t pid = (size_t)W * pyB + px;
@@ -308,13 +351,61 @@ __global__ void __launch_bounds__(BF_WARPS * 32, BF_PX2_OCC) blend_forward_px2_k
                 float* oc = tg.img[k];
                 oc[pid] = o0; oc[plane + pid] = o1; oc[2 * plane + pid] = o2;
             }
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                float* oc = ex.out[k];
+                oc[pid] = hi(E[k][0]) + T * bg0; oc[plane + pid] = hi(E[k][1]) + T * bg1;
+                oc[2 * plane + pid] = hi(E[k][2]) + T * bg2;
+            }
         }
     }
 }
 
-int g_blend_grid = 0;
+int g_blend_grid[4] = {0, 0, 0, 0};
+
+template <int K>
+cudaError_t launch_blend(const GsFrame& f, const GsGeom& g, const GsBinning& b, const GsImage& im, float* out_color,
+                         uint32_t num_tiles) {
+    const size_t smem = sizeof(BfStage<K>) * BF_STAGES * BF_WARPS;
+    if (g_blend_grid[K] == 0) {
+        int dev = 0, sms = 0, per_sm = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(blend_forward_px2_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, blend_forward_px2_kernel<K>, BF_WARPS * 32, smem);
+        if (e != cudaSuccess) return e;
+        g_blend_grid[K] = sms * (per_sm > 0 ? per_sm : 1);
+    }
+    BfTargets tg;
+    tg.n = f.s.num_peers > 0 ? f.s.num_peers : 1;
+    for (int k = 0; k < 8; k++) tg.img[k] = f.s.num_peers > 0 ? f.s.peer_out_color[k] : out_color;
+    BfExtra ex;
+    ex.xrec = g.xrec;
+    for (int k = 0; k < 3; k++) ex.out[k] = f.s.extra_out[k];
+    const unsigned grid = (unsigned)min((uint32_t)g_blend_grid[K], num_tiles);
+    blend_forward_px2_kernel<K><<<grid, BF_WARPS * 32, smem, f.stream>>>(im.ranges, im.order, b.list, g.rec, f.s.width,
+                                                                        f.s.height, f.gx, num_tiles, g.hdr,
+                                                                        f.s.background, im.final_T, im.n_contrib, tg, ex);
+    gs_note_launch();
+    return cudaGetLastError();
+}
 
 }  // namespace
+
+cudaError_t gs_launch_blend_forward(const GsFrame& f, const GsGeom& g, const GsBinning& b, const GsImage& im,
+                                    float* out_color) {
+    const uint32_t num_tiles = (uint32_t)f.gx * (uint32_t)(f.row1 - f.row0);
+    if (num_tiles == 0) return cudaSuccess;
+    switch (f.s.num_extra) {
+        case 1: return launch_blend<1>(f, g, b, im, out_color, num_tiles);
+        case 2: return launch_blend<2>(f, g, b, im, out_color, num_tiles);
+        case 3: return launch_blend<3>(f, g, b, im, out_color, num_tiles);
+        default: return launch_blend<0>(f, g, b, im, out_color, num_tiles);
+    }
+}
 
 #ifdef GS_TIMELINE
 extern "C" int gs_debug_timeline(void* dev_buf) {
@@ -322,28 +413,3 @@ extern "C" int gs_debug_timeline(void* dev_buf) {
     return (int)cudaMemcpyToSymbol(g_timeline, &p, sizeof(p));
 }
 #endif
-
-cudaError_t gs_launch_blend_forward(const GsFrame& f, const GsGeom& g, const GsBinning& b, const GsImage& im,
-                                    float* out_color) {
-    const uint32_t num_tiles = (uint32_t)f.gx * (uint32_t)(f.row1 - f.row0);
-    if (num_tiles == 0) return cudaSuccess;
-    if (g_blend_grid == 0) {
-        int dev = 0, sms = 0, per_sm = 0;
-        cudaError_t e = cudaGetDevice(&dev);
-        if (e != cudaSuccess) return e;
-        e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (e != cudaSuccess) return e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, blend_forward_px2_kernel, BF_WARPS * 32, 0);
-        if (e != cudaSuccess) return e;
-        g_blend_grid = sms * (per_sm > 0 ? per_sm : 1);
-    }
-    const unsigned grid = (unsigned)min((uint32_t)g_blend_grid, num_tiles);
-    BfTargets tg;
-    tg.n = f.s.num_peers > 0 ? f.s.num_peers : 1;
-    for (int k = 0; k < 8; k++) tg.img[k] = f.s.num_peers > 0 ? f.s.peer_out_color[k] : out_color;
-    blend_forward_px2_kernel<<<grid, BF_WARPS * 32, 0, f.stream>>>(im.ranges, im.order, b.list, g.rec, f.s.width,
-                                                                  f.s.height, f.gx, num_tiles, g.hdr, f.s.background,
-                                                                  im.final_T, im.n_contrib, tg);
-    gs_note_launch();
-    return cudaGetLastError();
-}

@@ -14,6 +14,7 @@
 //     ntile [P] u32       tiles touched
 //     cov3D [P][6] f32    world covariance (only when computed from scale/rotation)
 //     clamp [P] u8        bit c set = SH colour channel c was clamped at 0
+//     xrec  [P][3] float4 colours of up to three extra passes blended in the same list walk (GsScene.extra_colors)
 //   binning buffer (per instance, R entries)
 //     list  [R] u32       final per-tile, depth-ordered Gaussian index list ("point_list"); FIRST, so that backward
 //                         finds it from num_rendered alone
@@ -101,6 +102,7 @@ struct GsGeom {
     uint32_t* ntile;
     float* cov3D;
     uint8_t* clamp;
+    float4* xrec;      // [P][3] colours of up to three extra passes (rgb + pad), gathered like rec by the blend
     size_t sort_chunks, row_chunks, zero_bytes, bytes;
     __host__ __device__ GsGeom(char* base, size_t P) {
         GsCarver c(base);
@@ -122,6 +124,7 @@ struct GsGeom {
         ntile = c.take<uint32_t>(P);
         cov3D = c.take<float>(6 * P);
         clamp = c.take<uint8_t>(P);
+        xrec = c.take<float4>(3 * P);
         bytes = c.off + GS_ALIGN;
     }
 };
@@ -186,6 +189,7 @@ struct GsFrame {  // host-side derived quantities handed to every launcher
 // stage launchers (each in its own translation unit)
 cudaError_t gs_launch_preprocess(const GsFrame& f, const GsGeom& g, const GsImage& im, int32_t* radii);
 cudaError_t gs_launch_recolor(const GsFrame& f, const GsGeom& g);  // colour-only pass (gs_forward_recolor)
+cudaError_t gs_launch_pack_extra(const GsFrame& f, const GsGeom& g);  // GsScene.extra_colors -> g.xrec
 cudaError_t gs_launch_depth_sort(const GsFrame& f, const GsGeom& g);  // result in g.key[0] / g.idx[0]
 // row pass -> column histogram -> plan (ranges, tile_start, blend queue) -> column pass
 cudaError_t gs_launch_tile_lists(const GsFrame& f, const GsGeom& g, const GsBinning& b, size_t Rcap, size_t RowCap,

@@ -259,6 +259,19 @@ __global__ void __launch_bounds__(256) recolor_kernel(int P, int D, int M, const
     c[0] = rgb.x; c[1] = rgb.y; c[2] = rgb.z;
 }
 
+// Extra colour passes (GsScene.extra_colors): pack up to three [P][3] arrays into 16-B aligned entries that the
+// blend kernel can gather with cp.async next to the 48-B record.
+__global__ void __launch_bounds__(256) pack_extra_kernel(int P, int K, const float* __restrict__ c0,
+                                                         const float* __restrict__ c1, const float* __restrict__ c2,
+                                                         float4* __restrict__ xrec) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    const float* src[3] = {c0, c1, c2};
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+        if (k < K) xrec[3 * (size_t)i + k] = make_float4(src[k][3 * i], src[k][3 * i + 1], src[k][3 * i + 2], 0.f);
+}
+
 __global__ void mark_visible_kernel(int P, const float* __restrict__ means, const float* __restrict__ view,
                                     uint8_t* __restrict__ present) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -301,6 +314,15 @@ cudaError_t gs_launch_preprocess(const GsFrame& f, const GsGeom& g, const GsImag
     }
     if (staged) preprocess_kernel<true><<<(unsigned)gs_div_up(s.P, 256), 256, stage_bytes, f.stream>>>(a);
     else preprocess_kernel<false><<<(unsigned)gs_div_up(s.P, 256), 256, 0, f.stream>>>(a);
+    gs_note_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t gs_launch_pack_extra(const GsFrame& f, const GsGeom& g) {
+    const GsScene& s = f.s;
+    if (s.num_extra <= 0) return cudaSuccess;
+    pack_extra_kernel<<<(unsigned)gs_div_up(s.P, 256), 256, 0, f.stream>>>(s.P, s.num_extra, s.extra_colors[0],
+                                                                          s.extra_colors[1], s.extra_colors[2], g.xrec);
     gs_note_launch();
     return cudaGetLastError();
 }

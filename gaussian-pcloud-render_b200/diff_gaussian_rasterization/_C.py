@@ -39,7 +39,9 @@ class GsScene(C.Structure):
                 ("colors_precomp", C.c_void_p), ("opacities", C.c_void_p), ("scales", C.c_void_p),
                 ("rotations", C.c_void_p), ("cov3D_precomp", C.c_void_p), ("viewmatrix", C.c_void_p),
                 ("projmatrix", C.c_void_p), ("campos", C.c_void_p),
-                ("num_peers", C.c_int32), ("reserved", C.c_int32), ("peer_out_color", C.c_void_p * 8)]
+                ("num_peers", C.c_int32), ("reserved", C.c_int32), ("peer_out_color", C.c_void_p * 8),
+                ("num_extra", C.c_int32), ("reserved2", C.c_int32), ("extra_colors", C.c_void_p * 3),
+                ("extra_out", C.c_void_p * 3)]
 
 
 RESIZE_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t)
@@ -155,17 +157,25 @@ def _pooled_workspaces(dev):
 
 def make_scene(*, P, sh_degree, sh_stride, width, height, tan_fovx, tan_fovy, scale_modifier, prefiltered, debug,
                background, means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, viewmatrix,
-               projmatrix, campos, tile_rows: Optional[Tuple[int, int]] = None, peer_out=None) -> GsScene:
-    """peer_out: optional list of (peer-mapped) device pointers of (3,H,W) images the blend epilogue writes to."""
+               projmatrix, campos, tile_rows: Optional[Tuple[int, int]] = None, peer_out=None,
+               extra_passes=None) -> GsScene:
+    """peer_out: optional list of (peer-mapped) device pointers of (3,H,W) images the blend epilogue writes to.
+    extra_passes: optional list of up to three (colors (P,3) CUDA tensor, out (3,H,W) CUDA tensor) pairs blended in
+    the same list walk (the caller keeps the tensors alive)."""
     r0, r1 = tile_rows if tile_rows is not None else (0, 0)
     peers = list(peer_out) if peer_out else []
     if len(peers) > 8:
         raise ValueError("at most 8 peer images")
     arr = (C.c_void_p * 8)(*([int(p) for p in peers] + [None] * (8 - len(peers))))
+    extras = list(extra_passes) if extra_passes else []
+    if len(extras) > 3:
+        raise ValueError("at most 3 extra colour passes")
     return GsScene(P, sh_degree, sh_stride, width, height, tan_fovx, tan_fovy, scale_modifier, int(bool(prefiltered)),
                    int(bool(debug)), int(r0), int(r1), _ptr(background), _ptr(means3D), _ptr(shs),
                    _ptr(colors_precomp), _ptr(opacities), _ptr(scales), _ptr(rotations), _ptr(cov3D_precomp),
-                   _ptr(viewmatrix), _ptr(projmatrix), _ptr(campos), len(peers), 0, arr)
+                   _ptr(viewmatrix), _ptr(projmatrix), _ptr(campos), len(peers), 0, arr, len(extras), 0,
+                   (C.c_void_p * 3)(*([_ptr(c) for c, _ in extras] + [None] * (3 - len(extras)))),
+                   (C.c_void_p * 3)(*([_ptr(o) for _, o in extras] + [None] * (3 - len(extras)))))
 
 
 def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp,

@@ -53,14 +53,15 @@ class FrameRenderer:
             self.binning = torch.empty(self.L.gs_binning_bytes(self.capacity, self.P, self.W, self.H),
                                        dtype=torch.uint8, device=self.dev)
 
-    def _scene(self, view_dev, tile_rows, peer_out=None):
+    def _scene(self, view_dev, tile_rows, peer_out=None, extra_passes=None):
         viewmatrix, projmatrix, campos, tanx, tany = view_dev
         return _C.make_scene(P=self.P, sh_degree=self.sh_degree, sh_stride=int(self.shs.shape[1]), width=self.W,
                              height=self.H, tan_fovx=float(tanx), tan_fovy=float(tany), scale_modifier=1.0,
                              prefiltered=False, debug=False, background=self.bg, means3D=self.means3D, shs=self.shs,
                              colors_precomp=None, opacities=self.opacities, scales=self.scales,
                              rotations=self.rotations, cov3D_precomp=None, viewmatrix=viewmatrix,
-                             projmatrix=projmatrix, campos=campos, tile_rows=tile_rows, peer_out=peer_out)
+                             projmatrix=projmatrix, campos=campos, tile_rows=tile_rows, peer_out=peer_out,
+                             extra_passes=extra_passes)
 
     def upload_view(self, view):
         """host View (scenes.make_view) -> device tensors; done once per camera, outside the frame loop."""
@@ -68,12 +69,14 @@ class FrameRenderer:
         return (t(view.viewmatrix), t(view.projmatrix), t(view.campos), view.tanfovx, view.tanfovy)
 
     def enqueue(self, view_dev, out_color: Optional[torch.Tensor] = None, tile_rows=None, slot: int = 0,
-                peer_out=None) -> torch.Tensor:
+                peer_out=None, extra_passes=None) -> torch.Tensor:
         """Queues one frame on the current stream; no host synchronisation.  Returns the (3,H,W) colour tensor.
         peer_out: device pointers of the (3,H,W) images of all ranks (sharding.PeerFrame): the blend epilogue then
-        writes this rank's tile rows into every one of them instead of into out_color."""
+        writes this rank's tile rows into every one of them instead of into out_color.
+        extra_passes: up to three (colors (P,3), out (3,H,W)) pairs of contiguous fp32 CUDA tensors blended in the same
+        list walk as the frame; each `out` equals a separate forward with colors_precomp = colors."""
         out = self.color if out_color is None else out_color
-        scene = self._scene(view_dev, tile_rows if tile_rows is not None else self.tile_rows, peer_out)
+        scene = self._scene(view_dev, tile_rows if tile_rows is not None else self.tile_rows, peer_out, extra_passes)
         with torch.cuda.device(self.dev):
             st = torch.cuda.current_stream(self.dev).cuda_stream
             _C._check(self.L.gs_forward_nosync(C.byref(scene), self.geom.data_ptr(), self.binning.data_ptr(),

@@ -72,6 +72,14 @@ typedef struct GsScene {
     int32_t num_peers;
     int32_t reserved;
     float* peer_out_color[8];    /* each [3][H][W] */
+    /* Extra colour passes blended in the SAME list walk as the frame (forward only): up to three more
+     * per-Gaussian colour sets, e.g. the position / hit-map / normal passes of the reference's caller
+     * (simple_raw_render.py:411-522).  extra_out[k] receives exactly the image a separate forward with
+     * colors_precomp = extra_colors[k] would produce. */
+    int32_t num_extra;
+    int32_t reserved2;
+    const float* extra_colors[3];  /* each [P][3] */
+    float* extra_out[3];           /* each [3][H][W] */
 } GsScene;
 
 /* Growable scratch buffer: fn(user, bytes) must return a DEVICE pointer to at least `bytes` bytes that stays

@@ -348,6 +348,14 @@ def test_colour_passes_reuse_geometry_bitwise():
     assert fr.status()[2] == 0
     for a, b in zip(outs, refs):
         assert torch.equal(a, b)
+    # the same four passes in ONE list walk: the frame (RGB from SH) + three extra colour sets
+    extra = [(passes[k]["colors_precomp"].to(dev).contiguous(), torch.empty((3, 400, 640), device=dev)) for k in (0, 2, 3)]
+    rgb = fr.enqueue(vd, out_color=torch.empty((3, 400, 640), device=dev), extra_passes=extra)
+    torch.cuda.synchronize()
+    assert fr.status()[2] == 0
+    assert torch.equal(rgb, refs[1])
+    for (_, o), k in zip(extra, (0, 2, 3)):
+        assert torch.equal(o, refs[k])
 
 
 def test_peer_store_tile_sharding_two_gpus():
