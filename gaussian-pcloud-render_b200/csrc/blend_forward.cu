@@ -209,7 +209,8 @@ __global__ void __launch_bounds__(BF_WARPS * 32, (K == 0) ? BF_PX2_OCC : 2) blen
         const uint32_t* __restrict__ lst = list + range.x;
 
         bool doneA = !insA, doneB = !insB;
-        f2 T2 = bc(1.0f), C0 = bc(0.f), C1 = bc(0.f), C2 = bc(0.f);
+        f2 T2 = bc(1.0f);
+        float c0A = 0.f, c0B = 0.f, c1A = 0.f, c1B = 0.f, c2A = 0.f, c2B = 0.f;
         f2 E[K > 0 ? K : 1][3];
 #pragma unroll
         for (int k = 0; k < K; k++) { E[k][0] = bc(0.f); E[k][1] = bc(0.f); E[k][2] = bc(0.f); }
@@ -305,9 +306,13 @@ __global__ void __launch_bounds__(BF_WARPS * 32, (K == 0) ? BF_PX2_OCC : 2) blen
                 alphaB = stopB ? 0.0f : alphaB;
                 const f2 a2 = pk(alphaA, alphaB);
                 const float4 gc = st.c[j];
-                fma2_acc(C0, mul2(bc(gc.x), a2), T2);
-                fma2_acc(C1, mul2(bc(gc.y), a2), T2);
-                fma2_acc(C2, mul2(bc(gc.z), a2), T2);
+                {   // scalar FFMAs: a loop-carried FFMA2 accumulator costs two extra register moves per iteration
+                    const float TA = lo(T2), TB = hi(T2);
+                    const f2 w0 = mul2(bc(gc.x), a2), w1 = mul2(bc(gc.y), a2), w2 = mul2(bc(gc.z), a2);
+                    c0A = __fmaf_rn(lo(w0), TA, c0A); c0B = __fmaf_rn(hi(w0), TB, c0B);
+                    c1A = __fmaf_rn(lo(w1), TA, c1A); c1B = __fmaf_rn(hi(w1), TB, c1B);
+                    c2A = __fmaf_rn(lo(w2), TA, c2A); c2B = __fmaf_rn(hi(w2), TB, c2B);
+                }
 #pragma unroll
                 for (int k = 0; k < K; k++) {  // the extra passes: same alpha, same T, other colours
                     const float4 ge = st.e[k][j];
@@ -323,6 +328,7 @@ __global__ void __launch_bounds__(BF_WARPS * 32, (K == 0) ? BF_PX2_OCC : 2) blen
             if (__all_sync(GS_FULL, doneA && doneB)) break;
         }
         cp_async_wait<0>();
+        const f2 C0 = pk(c0A, c0B), C1 = pk(c1A, c1B), C2 = pk(c2A, c2B);
 
         if (insA) {
             const size_t pid = (size_t)W * pyA + px;

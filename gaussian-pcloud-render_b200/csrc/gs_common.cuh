@@ -74,7 +74,9 @@ struct GsCarver {
 // chunk sizes of the binning kernels (one CTA of 256 threads per chunk)
 #define GS_RADIX_BITS 8
 #define GS_RADIX 256
+#ifndef GS_SORT_CHUNK
 #define GS_SORT_CHUNK 8192   // depth keys per CTA and pass
+#endif
 #define GS_PART_CHUNK 2048   // items per CTA of the row / column partition passes
 #define GS_MAX_GRID 256      // at most 256 x 256 tiles (4096 x 4096 pixels)
 
