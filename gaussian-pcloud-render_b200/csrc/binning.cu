@@ -677,6 +677,9 @@ cudaError_t gs_launch_depth_sort(const GsFrame& f, const GsGeom& g) {
 }
 
 #define PART_SMEM(NB) ((8 * PART_ROUNDS * ((NB) + 4) + 8 * (NB)) * 4)
+#ifndef PART_GRID_MULT
+#define PART_GRID_MULT 4
+#endif
 static int g_part_grid = 0;
 
 cudaError_t gs_launch_tile_lists(const GsFrame& f, const GsGeom& g, const GsBinning& b, size_t Rcap, size_t RowCap,
@@ -688,7 +691,7 @@ cudaError_t gs_launch_tile_lists(const GsFrame& f, const GsGeom& g, const GsBinn
         GS_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         GS_TRY(cudaFuncSetAttribute(range_partition_kernel<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PART_SMEM(256)));
         GS_TRY(cudaFuncSetAttribute(range_partition_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, PART_SMEM(256)));
-        g_part_grid = sms * 4;
+        g_part_grid = sms * PART_GRID_MULT;
     }
     const unsigned grid1 = (unsigned)min((size_t)g_part_grid, g.row_chunks);
     const unsigned grid2 = (unsigned)min((size_t)g_part_grid, b.col_chunks);
