@@ -174,7 +174,6 @@ int64_t gs_forward(const GsScene* scene, GsBuffer geometry, GsBuffer binning, Gs
     char* bptr = binning.fn(binning.user, GsBinning(nullptr, (size_t)R, rows).bytes);
     if (!bptr) return GS_ERR_ALLOC;
     GsBinning b(bptr, (size_t)R, rows);
-    GS_CU(cudaMemsetAsync(bptr + b.zero_off, 0, b.zero_bytes, f.stream));
     GS_STAGE(gs_launch_tile_lists(f, g, b, (size_t)R, rows, im));
     t_prof.mark(3, f.stream);
     GS_STAGE(gs_launch_pack_extra(f, g));
@@ -197,7 +196,6 @@ int32_t gs_forward_nosync(const GsScene* scene, char* geometry, char* binning, i
     GsBinning b(binning, (size_t)cap, rowcap);
     GS_CU(cudaMemsetAsync(geometry, 0, g.zero_bytes, f.stream));
     GS_CU(cudaMemsetAsync(image, 0, im.zero_bytes, f.stream));
-    GS_CU(cudaMemsetAsync(binning + b.zero_off, 0, b.zero_bytes, f.stream));
     t_prof.mark(0, f.stream);
     GS_STAGE(gs_launch_preprocess(f, g, im, radii));
     t_prof.mark(1, f.stream);

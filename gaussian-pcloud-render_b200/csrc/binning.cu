@@ -14,9 +14,10 @@
 //   4. column pass: walk each row's items (still in depth order) and stably partition one entry per
 //      (item, tile column) by column, writing the final u32 Gaussian index straight into the tile's list.
 // Passes 3 and 4 exploit that a Gaussian covers a contiguous RANGE of rows / columns and contributes at most one
-// element per bin: a warp builds, for 32 items at once, the bitmask of covering items for every bin with two
-// shared-memory atomicXor per item and a prefix-xor over the bins; an element's stable rank is a popcount.
-// Both passes are single kernels with chained look-back (row pass: one chain; column pass: one chain per tile row).
+// element per bin: a warp builds, for 32 items at once, the bitmask of covering items for every bin (two matches,
+// group leaders store range starts / ends, prefix-xor over the bins); an element's stable rank is a popcount.
+// Each pass is count -> scan -> scatter: a counting kernel writes per-chunk bin counts, the block that finishes
+// last (rows) / extra blocks of the plan kernel (columns) turn them into output positions.
 // HBM traffic: ~8 B per row item written + read, 4 B per instance written: ~8 B per instance instead of ~172 B.
 #include "gs_common.cuh"
 
@@ -83,10 +84,12 @@ __device__ __forceinline__ void chain_prefix(const GsChain ch, int chunk, int fi
         __stcg(ch.agg + row + b, s_tot[b]);
         if (head) __stcg(ch.inc + row + b, s_tot[b]);
     }
-    __threadfence();
     if (tid == 0) *s_pstar = first - 1;
     __syncthreads();
-    if (tid == 0) st_volatile_u32(ch.state + chunk, head ? 2u : 1u);
+    if (tid == 0) {  // one fence after the barrier orders every thread's counters before the state word
+        __threadfence();
+        st_volatile_u32(ch.state + chunk, head ? 2u : 1u);
+    }
     if (head) {
         for (int b = tid; b < nb; b += NT) s_excl[b] = 0;
         __syncthreads();
@@ -127,9 +130,11 @@ __device__ __forceinline__ void chain_prefix(const GsChain ch, int chunk, int fi
         s_excl[b] = e;
         __stcg(ch.inc + row + b, e + s_tot[b]);
     }
-    __threadfence();
     __syncthreads();
-    if (tid == 0) st_volatile_u32(ch.state + chunk, 2u);
+    if (tid == 0) {
+        __threadfence();
+        st_volatile_u32(ch.state + chunk, 2u);
+    }
 }
 
 // Row tables, recomputed by warp 0 of every CTA that needs them (<= 257 entries): prefix sum of the row difference
@@ -337,13 +342,70 @@ __global__ void __launch_bounds__(SORT_THREADS) depth_pass_kernel(const uint32_t
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Row counts: per chunk of GS_PART_CHUNK depth-sorted Gaussians, the number of row items it emits into each tile row
+// (difference array in shared memory, +1 at y0, -1 at y1); row_scan_kernel then turns the table into the output
+// positions of the row pass: exclusive prefix over the chunks, per row, on top of the row's first position.
+// (Replaces a chained look-back inside the row pass: with a few hundred chunks that are all resident at once every
+// chunk had to add up all its predecessors' counters -- O(chunks^2) reads of the same hot rows, 18 us per chunk.)
+template <int NB>
+__global__ void __launch_bounds__(256) row_count_kernel(const uint32_t* __restrict__ sorted_idx,
+                                                        const ushort4* __restrict__ rect, uint32_t P, int gy,
+                                                        uint32_t* __restrict__ chunk_cnt /*[gy][nchunks]*/) {
+    constexpr int G = NB / 32;
+    __shared__ int s_d[NB + 1];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t chunk = blockIdx.x, nchunks = gridDim.x;
+    for (int i = tid; i <= NB; i += 256) s_d[i] = 0;
+    __syncthreads();
+    const uint32_t ibeg = chunk * GS_PART_CHUNK, iend = min(P, ibeg + (uint32_t)GS_PART_CHUNK);
+    for (uint32_t i = ibeg + tid; i < iend; i += 256) {
+        const ushort4 rc = rect[sorted_idx[i]];
+        if (rc.w > rc.y) {
+            atomicAdd(&s_d[rc.y], 1);
+            atomicAdd(&s_d[rc.w], -1);
+        }
+    }
+    __syncthreads();
+    if (warp == 0) {
+        int v[G], sum = 0;
+#pragma unroll
+        for (int j = 0; j < G; j++) { sum += s_d[lane * G + j]; v[j] = sum; }
+        const int pre = (int)warp_incl_scan((uint32_t)sum, lane) - sum;
+#pragma unroll
+        for (int j = 0; j < G; j++) {
+            const int y = lane * G + j;
+            if (y < gy) chunk_cnt[(size_t)y * nchunks + chunk] = (uint32_t)(v[j] + pre);
+        }
+    }
+}
+
+// One warp per tile row: exclusive prefix of the row's chunk counts on top of the row's first output position.
+__global__ void __launch_bounds__(32) row_scan_kernel(const int* __restrict__ rdiff, int gy, uint32_t nchunks,
+                                                      uint32_t* __restrict__ chunk_cnt /*[gy][nchunks]*/) {
+    __shared__ uint32_t s_rs[GS_MAX_GRID + 1], s_cf[GS_MAX_GRID + 1];
+    const int lane = threadIdx.x, y = blockIdx.x;
+    row_tables(rdiff, gy, s_rs, s_cf, lane);
+    __syncwarp();
+    uint32_t run = s_rs[y];
+    uint32_t* row = chunk_cnt + (size_t)y * nchunks;
+    for (uint32_t c0 = 0; c0 < nchunks; c0 += 32) {
+        const uint32_t c = c0 + lane;
+        const uint32_t v = (c < nchunks) ? row[c] : 0u;
+        const uint32_t incl = warp_incl_scan(v, lane);
+        if (c < nchunks) row[c] = run + incl - v;
+        run += __shfl_sync(GS_FULL, incl, 31);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Column histogram: instances per tile = number of row items of the tile's row that cover its column.  A CTA owns
 // one column-pass chunk (items of ONE row), builds the column difference array in shared memory (+1 at x0, -1 at
 // x1 per item), integrates it and adds the non-zero counts to tcount.
 template <int NB>
 __global__ void __launch_bounds__(256) column_hist_kernel(const uint2* __restrict__ items, const int* __restrict__ rdiff,
                                                           int gx, int gy, unsigned long long RowCap,
-                                                          uint32_t* __restrict__ tcount) {
+                                                          uint32_t* __restrict__ tcount,
+                                                          uint32_t* __restrict__ chunk_cnt /*[chunks][GS_MAX_GRID]*/) {
     constexpr int G = NB / 32;
     __shared__ uint32_t s_rs[GS_MAX_GRID + 1], s_cf[GS_MAX_GRID + 1];
     __shared__ int s_d[NB + 1];
@@ -372,7 +434,10 @@ __global__ void __launch_bounds__(256) column_hist_kernel(const uint2* __restric
 #pragma unroll
             for (int j = 0; j < G; j++) {
                 const int x = lane * G + j, c = v[j] + pre;
-                if (x < gx && c) atomicAdd(&tcount[row * gx + x], (uint32_t)c);
+                if (x < gx) {
+                    chunk_cnt[(size_t)chunk * GS_MAX_GRID + x] = (uint32_t)c;  // -> exclusive prefix by plan_kernel
+                    if (c) atomicAdd(&tcount[row * gx + x], (uint32_t)c);
+                }
             }
         }
         __syncthreads();
@@ -384,10 +449,31 @@ __global__ void __launch_bounds__(256) column_hist_kernel(const uint2* __restric
 __global__ void __launch_bounds__(1024) plan_kernel(const uint32_t* __restrict__ tcount, int gx, int gy, int row0,
                                                     int row1, uint32_t* __restrict__ tile_start,
                                                     uint2* __restrict__ ranges, uint32_t* __restrict__ order,
-                                                    GsHeader* __restrict__ hdr, unsigned long long Rcap) {
+                                                    GsHeader* __restrict__ hdr, unsigned long long Rcap,
+                                                    const int* __restrict__ rdiff, unsigned long long RowCap,
+                                                    uint32_t* __restrict__ chunk_cnt /*[chunks][GS_MAX_GRID]*/) {
     __shared__ uint32_t s_wsum[32];
     __shared__ uint32_t s_cnt[33], s_slot[33];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (blockIdx.x > 0) {
+        // blocks 1..gy: exclusive prefix of the column counts over the chunks of tile row blockIdx.x - 1 (the column
+        // pass adds the tile's first position); block 0 below does the plan proper
+        __shared__ uint32_t s_rs[GS_MAX_GRID + 1], s_cf[GS_MAX_GRID + 1];
+        if (warp == 0) row_tables(rdiff, gy, s_rs, s_cf, lane);
+        __syncthreads();
+        if ((unsigned long long)s_rs[gy] > RowCap) return;
+        const int y = (int)blockIdx.x - 1;
+        const uint32_t c0 = s_cf[y], c1 = s_cf[y + 1];
+        if (tid < gx) {
+            uint32_t run = 0;
+            for (uint32_t c = c0; c < c1; c++) {
+                const uint32_t v = chunk_cnt[(size_t)c * GS_MAX_GRID + tid];
+                chunk_cnt[(size_t)c * GS_MAX_GRID + tid] = run;
+                run += v;
+            }
+        }
+        return;
+    }
     const int Tn = gx * gy;
     const int per = (Tn + 1023) / 1024;  // each thread owns a contiguous run of tiles
     const int t_begin = min(Tn, tid * per), t_end = min(Tn, t_begin + per);
@@ -468,18 +554,16 @@ __global__ void __launch_bounds__(256, (NB == 128) ? 4 : 2) range_partition_kern
     const uint32_t* __restrict__ sorted_idx, const ushort4* __restrict__ rect, uint32_t P,  // PASS 1 input
     const uint2* __restrict__ items_in,                                                      // PASS 2 input
     const int* __restrict__ rdiff, int gx, int gy, const uint32_t* __restrict__ tile_start,
-    unsigned long long RowCap, const GsChain chain, unsigned* __restrict__ ticket,
-    GsHeader* __restrict__ hdr, uint2* __restrict__ items_out, uint32_t* __restrict__ list_out) {
+    unsigned long long RowCap, const uint32_t* __restrict__ chunk_base /*[chunks][GS_MAX_GRID]*/,
+    unsigned* __restrict__ ticket, GsHeader* __restrict__ hdr, uint2* __restrict__ items_out,
+    uint32_t* __restrict__ list_out) {
     constexpr int G = NB / 32;    // bins per lane in the warp-wide scans
     constexpr int MS = NB + 4;    // mask row stride (words), multiple of 4 for the vectorised clear
     extern __shared__ __align__(16) uint32_t s_dyn[];
     uint32_t* s_mask = s_dyn;                                         // [8 warps][PART_ROUNDS][MS]
     int* s_cnt = reinterpret_cast<int*>(s_dyn + 8 * PART_ROUNDS * MS);  // [8 warps][NB]: counts -> output positions
     __shared__ uint32_t s_rs[GS_MAX_GRID + 1], s_cf[GS_MAX_GRID + 1];
-    __shared__ uint32_t s_tot[NB], s_excl[NB];
-    __shared__ __align__(16) uint32_t s_part[4 * 256];
     __shared__ uint32_t s_chunk;
-    __shared__ int s_pstar;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (PASS == 2 && hdr->skip) return;
     if (warp == 0) row_tables(rdiff, gy, s_rs, s_cf, lane);
@@ -598,26 +682,22 @@ __global__ void __launch_bounds__(256, (NB == 128) ? 4 : 2) range_partition_kern
         }
         __syncthreads();
         BIN_MARK(tl_slot, 1);
-        // ---- phase B: thread b = bin b: scan over warps, chunk aggregate; chunk chain; output base
+        BIN_MARK(tl_slot, 2);
+        // ---- phase B: thread b = bin b: exclusive scan over the warps on top of the chunk's first output position
+        // (row pass: row_count_kernel's table; column pass: the tile's first position + plan_kernel's table)
         const int nb_used = (PASS == 1) ? gy : gx;
         if (tid < NB) {
-            uint32_t total = 0;
+            uint32_t run = 0;
+            if (tid < nb_used) {
+                if (PASS == 1) run = chunk_base[(size_t)tid * nchunks + chunk];  // [row][chunk] (row_scan_kernel)
+                else run = chunk_base[(size_t)chunk * GS_MAX_GRID + tid] + tile_start[row * gx + tid];
+            }
 #pragma unroll
             for (int w = 0; w < 8; w++) {
                 const uint32_t t = (uint32_t)s_cnt[w * NB + tid];
-                s_cnt[w * NB + tid] = (int)total;
-                total += t;
+                s_cnt[w * NB + tid] = (int)run;
+                run += t;
             }
-            s_tot[tid] = total;
-        }
-        __syncthreads();
-        BIN_MARK(tl_slot, 2);
-        chain_prefix<256>(chain, (int)chunk, first, nb_used, s_tot, s_excl, s_part, &s_pstar);
-        BIN_MARK(tl_slot, 3);
-        if (tid < nb_used) {
-            const uint32_t basev = s_excl[tid] + ((PASS == 1) ? s_rs[tid] : tile_start[row * gx + tid]);
-#pragma unroll
-            for (int w = 0; w < 8; w++) s_cnt[w * NB + tid] += (int)basev;
         }
         __syncthreads();
         // ---- phase C: scatter, round by round (positions of a bin advance by the round's population)
@@ -696,22 +776,32 @@ cudaError_t gs_launch_tile_lists(const GsFrame& f, const GsGeom& g, const GsBinn
     const unsigned grid1 = (unsigned)min((size_t)g_part_grid, g.row_chunks);
     const unsigned grid2 = (unsigned)min((size_t)g_part_grid, b.col_chunks);
     const unsigned long long rowcap = RowCap;
-    const GsChain ch_row = {g.rstate, g.ragg, g.rinc}, ch_col = {b.cstate, b.cagg, b.cinc};
 #define LAUNCH_PART(NB, PASS, GRID)                                                                               \
     range_partition_kernel<NB, PASS><<<GRID, 256, PART_SMEM(NB), f.stream>>>(                                     \
-        g.idx[0], g.rect, P, b.items, im.rdiff, f.gx, f.gy, im.tile_start, rowcap, (PASS == 1) ? ch_row : ch_col, \
+        g.idx[0], g.rect, P, b.items, im.rdiff, f.gx, f.gy, im.tile_start, rowcap, (PASS == 1) ? g.ragg : b.cagg, \
         &g.hdr->tickets[3 + PASS], g.hdr, b.items, b.list)
-    // row pass: Gaussians in depth order -> row items grouped by tile row
+    // row counts per chunk -> output positions; row pass: Gaussians in depth order -> row items grouped by tile row
+    if (f.gy <= 128)
+        row_count_kernel<128><<<(unsigned)g.row_chunks, 256, 0, f.stream>>>(g.idx[0], g.rect, P, f.gy, g.ragg);
+    else
+        row_count_kernel<256><<<(unsigned)g.row_chunks, 256, 0, f.stream>>>(g.idx[0], g.rect, P, f.gy, g.ragg);
+    gs_note_launch();
+    GS_TRY(cudaGetLastError());
+    row_scan_kernel<<<(unsigned)f.gy, 32, 0, f.stream>>>(im.rdiff, f.gy, (uint32_t)g.row_chunks, g.ragg);
+    gs_note_launch();
+    GS_TRY(cudaGetLastError());
     if (f.gy <= 128) LAUNCH_PART(128, 1, grid1); else LAUNCH_PART(256, 1, grid1);
     gs_note_launch();
     GS_TRY(cudaGetLastError());
     // column histogram -> per-tile counts, then the plan (ranges, tile_start, blend queue)
-    if (f.gx <= 128) column_hist_kernel<128><<<grid2, 256, 0, f.stream>>>(b.items, im.rdiff, f.gx, f.gy, rowcap, im.tcount);
-    else column_hist_kernel<256><<<grid2, 256, 0, f.stream>>>(b.items, im.rdiff, f.gx, f.gy, rowcap, im.tcount);
+    if (f.gx <= 128)
+        column_hist_kernel<128><<<grid2, 256, 0, f.stream>>>(b.items, im.rdiff, f.gx, f.gy, rowcap, im.tcount, b.cagg);
+    else
+        column_hist_kernel<256><<<grid2, 256, 0, f.stream>>>(b.items, im.rdiff, f.gx, f.gy, rowcap, im.tcount, b.cagg);
     gs_note_launch();
     GS_TRY(cudaGetLastError());
-    plan_kernel<<<1, 1024, 0, f.stream>>>(im.tcount, f.gx, f.gy, f.row0, f.row1, im.tile_start, im.ranges, im.order,
-                                         g.hdr, (unsigned long long)Rcap);
+    plan_kernel<<<1 + f.gy, 1024, 0, f.stream>>>(im.tcount, f.gx, f.gy, f.row0, f.row1, im.tile_start, im.ranges,
+                                                im.order, g.hdr, (unsigned long long)Rcap, im.rdiff, rowcap, b.cagg);
     gs_note_launch();
     GS_TRY(cudaGetLastError());
     // column pass: row items -> final per-tile lists

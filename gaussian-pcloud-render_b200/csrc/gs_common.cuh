@@ -5,8 +5,8 @@
 //     GsHeader            status block + counters (256 B)
 //     dhist [4][256] u32  digit histograms of the depth keys           } zeroed at the start of every frame
 //     dstate [4][C] u32   chunk states of the depth-sort chains          } (C = ceil(P / 8192) chunks)
-//     rstate [C1] u32     chunk states of the row-pass chain             } (C1 = ceil(P / 2048) chunks)
-//     dagg/dinc [4][C][256], ragg/rinc [C1][256] u32   per-chunk aggregates / inclusive prefixes (not zeroed)
+//     dagg/dinc [4][C][256] u32   per-chunk aggregates / inclusive prefixes of the sort chains (not zeroed)
+//     ragg [256][C1] u32  row-pass counts per chunk -> output positions (C1 = ceil(P / 2048) chunks)
 //     rec   [P] GsRec     48-B packed record read by the blend kernels (3 x float4)
 //     key   [2][P] u32    depth-sort keys (float bits of view-space z; 0xFFFFFFFF = culled), ping/pong
 //     idx   [2][P] u32    depth-sort values (Gaussian index), ping/pong
@@ -18,8 +18,7 @@
 //   binning buffer (per instance, R entries)
 //     list  [R] u32       final per-tile, depth-ordered Gaussian index list ("point_list"); FIRST, so that backward
 //                         finds it from num_rendered alone
-//     cstate [C2] u32     chunk states of the column-pass chains (zeroed every frame)
-//     cagg/cinc [C2][256] u32  per-chunk aggregates / inclusive prefixes (not zeroed)
+//     cagg [C2][256] u32  column-pass counts per chunk -> output positions
 //     items [Rrow] uint2  row items after the row pass: (gaussian, x0 | x1 << 16), grouped by tile row, depth order
 //   image buffer
 //     rdiff [gy+1] i32    difference array of the row ranges -> row-item counts     } zeroed every
@@ -94,9 +93,8 @@ struct GsGeom {
     GsHeader* hdr;
     uint32_t* dhist;   // [4][256]
     unsigned* dstate;  // [4][sort_chunks]
-    unsigned* rstate;  // [row_chunks]
     uint32_t* dagg; uint32_t* dinc;  // [4][sort_chunks][256]
-    uint32_t* ragg; uint32_t* rinc;  // [row_chunks][256]
+    uint32_t* ragg;    // [256][row_chunks] row-pass counts per chunk -> output positions (row_count / row_scan)
     GsRec* rec;
     uint32_t* key[2];
     uint32_t* idx[2];
@@ -113,12 +111,10 @@ struct GsGeom {
         row_chunks = gs_div_up(P, GS_PART_CHUNK);
         dhist = c.take<uint32_t>(4 * GS_RADIX);
         dstate = c.take<unsigned>(4 * sort_chunks);
-        rstate = c.take<unsigned>(row_chunks);
         zero_bytes = c.off;  // header + histograms + chunk states are zeroed at the start of every frame
         dagg = c.take<uint32_t>(4 * sort_chunks * GS_RADIX);
         dinc = c.take<uint32_t>(4 * sort_chunks * GS_RADIX);
         ragg = c.take<uint32_t>(row_chunks * GS_MAX_GRID);
-        rinc = c.take<uint32_t>(row_chunks * GS_MAX_GRID);
         rec = c.take<GsRec>(P);
         key[0] = c.take<uint32_t>(P); key[1] = c.take<uint32_t>(P);
         idx[0] = c.take<uint32_t>(P); idx[1] = c.take<uint32_t>(P);
@@ -133,8 +129,7 @@ struct GsGeom {
 
 struct GsBinning {
     uint32_t* list;    // [Rcap]
-    unsigned* cstate;  // [col_chunks]
-    uint32_t* cagg; uint32_t* cinc;  // [col_chunks][GS_MAX_GRID]
+    uint32_t* cagg;    // [col_chunks][GS_MAX_GRID] column-pass counts per chunk -> output positions (plan_kernel)
     uint2* items;      // [RowCap]
     size_t col_chunks, zero_off, zero_bytes, bytes;
     // Rcap = instance capacity, RowCap = row-item capacity (<= Rcap always holds for the true counts)
@@ -142,11 +137,9 @@ struct GsBinning {
         GsCarver c(base);
         list = c.take<uint32_t>(Rcap);
         col_chunks = gs_div_up(RowCap, GS_PART_CHUNK) + GS_MAX_GRID;
-        cstate = c.take<unsigned>(col_chunks);
-        zero_off = (size_t)(reinterpret_cast<char*>(cstate) - base);
-        zero_bytes = c.off - zero_off;
+        zero_off = c.off;
+        zero_bytes = 0;  // nothing in this buffer needs clearing
         cagg = c.take<uint32_t>(col_chunks * GS_MAX_GRID);
-        cinc = c.take<uint32_t>(col_chunks * GS_MAX_GRID);
         items = c.take<uint2>(RowCap);
         bytes = c.off + GS_ALIGN;
     }
