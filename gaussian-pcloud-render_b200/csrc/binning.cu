@@ -466,8 +466,19 @@ __global__ void __launch_bounds__(1024) plan_kernel(const uint32_t* __restrict__
         const uint32_t c0 = s_cf[y], c1 = s_cf[y + 1];
         if (tid < gx) {
             uint32_t run = 0;
-            for (uint32_t c = c0; c < c1; c++) {
-                const uint32_t v = chunk_cnt[(size_t)c * GS_MAX_GRID + tid];
+            uint32_t c = c0;
+            for (; c + 8 <= c1; c += 8) {  // eight independent loads in flight, then the dependent running sum
+                uint32_t v[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) v[k] = __ldcg(chunk_cnt + (size_t)(c + k) * GS_MAX_GRID + tid);
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    chunk_cnt[(size_t)(c + k) * GS_MAX_GRID + tid] = run;
+                    run += v[k];
+                }
+            }
+            for (; c < c1; c++) {
+                const uint32_t v = __ldcg(chunk_cnt + (size_t)c * GS_MAX_GRID + tid);
                 chunk_cnt[(size_t)c * GS_MAX_GRID + tid] = run;
                 run += v;
             }
@@ -478,6 +489,7 @@ __global__ void __launch_bounds__(1024) plan_kernel(const uint32_t* __restrict__
     const int per = (Tn + 1023) / 1024;  // each thread owns a contiguous run of tiles
     const int t_begin = min(Tn, tid * per), t_end = min(Tn, t_begin + per);
     uint32_t local = 0;
+#pragma unroll 8
     for (int t = t_begin; t < t_end; t++) local += tcount[t];
     const uint32_t incl = warp_incl_scan(local, lane);
     if (lane == 31) s_wsum[warp] = incl;
