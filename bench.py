@@ -72,33 +72,53 @@ class ClockSampler(threading.Thread):
     def __init__(self, gpu_index=0):
         super().__init__(daemon=True)
         self.gpu_index = gpu_index
-        self.rows = []
+        self.rows = []   # (wall-clock time of the sample, fields)
         self.proc = None
+        self.t0 = self.t1 = None
 
     def run(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu_index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "50", "-i", str(self.gpu_index)], stdout=subprocess.PIPE, text=True)
             for line in self.proc.stdout:
-                self.rows.append([c.strip() for c in line.split(",")])
+                self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
         except Exception:  # noqa: BLE001
             pass
+
+    def wait_first(self, timeout=3.0):
+        """Blocks until nvidia-smi has produced its first sample (its start-up takes a few hundred ms)."""
+        t = time.time()
+        while not self.rows and time.time() - t < timeout:
+            time.sleep(0.01)
+
+    def mark(self, begin):
+        if begin:
+            self.t0 = time.time()
+        else:
+            self.t1 = time.time()
 
     def stop(self):
         if self.proc is not None:
             self.proc.terminate()
         self.join(timeout=2)
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        # samples taken inside the timed region; the sampler runs from the warm-up on, so if the region is shorter
+        # than the sampling period the samples of the (identically loaded) warm-up stand in
+        rows = [r for ts, r in self.rows if self.t0 is not None and self.t0 - 0.02 <= ts <= (self.t1 or ts) + 0.02]
+        window = "timed region"
+        if len(rows) < 2:
+            rows, window = [r for _, r in self.rows[1:]] or [r for _, r in self.rows], "warm-up + timed region"
+        self.rows_used, self.window = rows, window
+        sm = [float(r[1]) for r in rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
         reasons = set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in rows:
             if len(r) >= 9:
                 for n, v in zip(names, r[5:9]):
                     if v.lower().startswith("active"):
                         reasons.add(n)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def dist_setup(n):
@@ -191,19 +211,20 @@ def run_b200(args, rank, world):
                     fr.enqueue(v, tile_rows=(r0, r1), slot=slot)
                 sharding.exchange_image(fr.color, rows, rank)
 
-    pipe.begin()
-    for i in range(args.warmup):
-        frame(i, i)
-    pipe.end()
-    barrier(world)
     clocks = ClockSampler(torch.cuda.current_device())
     if rank == 0:
         clocks.start()
-        time.sleep(0.15)
+        clocks.wait_first()
+    pipe.begin()
+    for i in range(max(args.warmup, 3)):
+        frame(i, i)
+    pipe.end()
+    barrier(world)
     launches0 = L.gs_launch_count()
     stage_ms = np.zeros(4)
     barrier(world)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    clocks.mark(True)
     e0.record()
     pipe.begin()
     for i in range(args.steps):
@@ -211,6 +232,7 @@ def run_b200(args, rank, world):
     pipe.end()
     e1.record()
     barrier(world)
+    clocks.mark(False)
     ms = e0.elapsed_time(e1)
     launches = L.gs_launch_count() - launches0
     clk = clocks.stop() if rank == 0 else None
@@ -252,7 +274,7 @@ def run_b200(args, rank, world):
             ncu = json.load(open(os.path.join(ROOT, "profiles", "blend_forward_traffic.json")))
         except Exception:  # noqa: BLE001
             pass
-        roof = {"bound": "hbm", "kernel": "blend_forward_kernel", "achieved": ach, "peak": peak, "unit": "GB/s",
+        roof = {"bound": "hbm", "kernel": "blend_forward_px2_kernel<0>", "achieved": ach, "peak": peak, "unit": "GB/s",
                 "frac": ach / peak, "traffic": ncu.get("traffic") if args.workload == "C2" else None,
                 "peak_source": "measured" if peaks else "fallback",
                 "ncu": {k: ncu.get(k) for k in ("issue_active_pct", "l2_hit_pct", "warp_instructions", "source")} if ncu else None,
@@ -415,18 +437,20 @@ def run_reference(args, rank, world):
                            campos=cp, bg=bg, tanfovx=views[k].tanfovx, tanfovy=views[k].tanfovy,
                            sh_degree=cloud["sh_degree"], shs=dd["shs"], scales=dd["scales"], rotations=dd["rotations"])[0]
 
+    clocks = ClockSampler(torch.cuda.current_device())
+    clocks.start()
+    clocks.wait_first()
     for i in range(args.warmup):
         frame(i)
     torch.cuda.synchronize()
-    clocks = ClockSampler(torch.cuda.current_device())
-    clocks.start()
-    time.sleep(0.15)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    clocks.mark(True)
     e0.record()
     for i in range(args.steps):
         frame(args.warmup + i)
     e1.record()
     torch.cuda.synchronize()
+    clocks.mark(False)
     ms = e0.elapsed_time(e1)
     clk = clocks.stop()
     host = {k: cloud[k].contiguous().pin_memory() for k in d}
@@ -484,8 +508,8 @@ def run_cpu_port(args, cloud=None, views=None, w=None, impl="cpu-port", note=Non
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=240)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=1200)
+    ap.add_argument("--warmup", type=int, default=60)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference", "cpu-port"])
     ap.add_argument("--workload", default="C2", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
