@@ -16,8 +16,13 @@
 // Passes 3 and 4 exploit that a Gaussian covers a contiguous RANGE of rows / columns and contributes at most one
 // element per bin: a warp builds, for 32 items at once, the bitmask of covering items for every bin (two matches,
 // group leaders store range starts / ends, prefix-xor over the bins); an element's stable rank is a popcount.
-// Each pass is count -> scan -> scatter: a counting kernel writes per-chunk bin counts, the block that finishes
-// last (rows) / extra blocks of the plan kernel (columns) turn them into output positions.
+// Each pass is count -> scan -> scatter: a counting kernel writes per-chunk bin counts, a one-warp-per-row scan (rows)
+// / extra blocks of the plan kernel (columns) turn them into output positions.
+// Measured on B200 and rejected: hardware MATCH.ANY in the sort (no faster than 8 ballots), shared-memory atomicXor
+// for the masks (ATOMS serialises), in-kernel decoupled look-back for the row / column passes (all chunks resident at
+// once -> O(chunks^2) reads of hot rows, 8-18 us per chunk), 4096-key sort chunks (longer chains), 1024-item column
+// chunks with the output staged in shared memory and written as coalesced runs (68 vs 56 us: the extra barriers and
+// per-chunk overheads cost more than the scattered 4-byte stores).
 // HBM traffic: ~8 B per row item written + read, 4 B per instance written: ~8 B per instance instead of ~172 B.
 #include "gs_common.cuh"
 

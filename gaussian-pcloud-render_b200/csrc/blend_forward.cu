@@ -120,6 +120,10 @@ __device__ __forceinline__ f2 mul2(f2 a, f2 b) { f2 r; asm("mul.rn.f32x2 %0, %1,
 __device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { f2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
 __device__ __forceinline__ void fma2_acc(f2& acc, f2 a, f2 b) { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b)); }
 
+#ifndef BF_SLOT_NUM  // fraction of the CTA slots the blend grid may occupy
+#define BF_SLOT_NUM 3
+#define BF_SLOT_DEN 5
+#endif
 #ifndef BF_PX2_OCC
 #define BF_PX2_OCC 3
 #endif
@@ -396,7 +400,7 @@ cudaError_t launch_blend(const GsFrame& f, const GsGeom& g, const GsBinning& b, 
     for (int k = 0; k < 3; k++) ex.out[k] = f.s.extra_out[k];
     // grid x 8 warps x quota covers the upper bound of units (4 per tile); quota >= 16, grid <= 60 % of the slots
     const uint32_t units_max = num_tiles * 4u;
-    const uint32_t slots = (uint32_t)((g_blend_grid[K] * 3 + 4) / 5);
+    const uint32_t slots = (uint32_t)((g_blend_grid[K] * BF_SLOT_NUM + BF_SLOT_DEN - 1) / BF_SLOT_DEN);
     uint32_t quota = (units_max + BF_WARPS * slots - 1) / (BF_WARPS * slots);
     if (quota < 16u) quota = 16u;
     const unsigned grid = (units_max + BF_WARPS * quota - 1) / (BF_WARPS * quota);
