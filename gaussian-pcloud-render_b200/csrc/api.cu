@@ -84,7 +84,7 @@ int make_frame(const GsScene* s, void* stream, GsFrame& f, bool forward = true) 
         if (f.row1 < f.row0) f.row1 = f.row0;
     }
     if (f.gx > GS_MAX_GRID || f.gy > GS_MAX_GRID) return GS_ERR_UNSUPPORTED;  // at most 4096 x 4096 pixels
-    if ((unsigned long long)s->P >= (1ull << 30)) return GS_ERR_UNSUPPORTED;  // look-back counters are 30 bits
+    if ((unsigned long long)s->P >= (1ull << 30)) return GS_ERR_UNSUPPORTED;  // instance counters stay well inside 32 bits
     f.focal_y = s->height / (2.0f * s->tan_fovy);  // rasterizer_impl.cu:222-223
     f.focal_x = s->width / (2.0f * s->tan_fovx);
     f.stream = (cudaStream_t)stream;

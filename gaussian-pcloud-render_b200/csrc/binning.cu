@@ -6,7 +6,7 @@
 // (SURVEY 8a row a10).  Here the same final order -- per tile, ascending depth, ties by ascending Gaussian index
 //  -- is produced without ever materialising a key per instance:
 //   1. depth sort: stable LSD radix sort of the P Gaussians by their 32-bit depth key, 8 bits per pass, each pass a
-//      single "onesweep" kernel (rank in shared memory, chained decoupled look-back across CTAs, direct scatter);
+//      single "onesweep" kernel (rank in shared memory, chunk chain across CTAs, reorder in shared memory);
 //   2. plan: preprocess accumulated a 2-D difference array of the tile rectangles; one CTA integrates it into the
 //      exact per-tile instance counts, their exclusive scan (= the tile ranges), the per-row item counts and the
 //      longest-list-first tile queue of the blend kernel.  No instance is touched;
@@ -607,7 +607,7 @@ __global__ void __launch_bounds__(256, (NB == 128) ? 4 : 2) range_partition_kern
         const uint32_t tl_slot = 4096u + (uint32_t)(PASS - 1) * 16384u + chunk;
         BIN_MARK(tl_slot, 0);
 
-        // chunk -> item range and head of its look-back chain
+        // chunk -> item range (column pass: the tile row it belongs to)
         uint32_t ibeg, iend;
         int first = 0, row = 0;
         if (PASS == 1) {
