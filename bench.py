@@ -513,7 +513,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference", "cpu-port"])
     ap.add_argument("--workload", default="C2", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--streams", type=int, default=4, help="frames in flight (one CUDA stream + workspace each)")
+    ap.add_argument("--streams", type=int, default=6, help="frames in flight (one CUDA stream + workspace each)")
     ap.add_argument("--parallel", default="views", choices=["views", "tiles"], help="multi-GPU sharding (N > 1)")
     ap.add_argument("--exchange", default="peer", choices=["peer", "allgather"],
                     help="tiles mode: blend epilogue stores into peer images (symmetric memory) or NCCL all-gather")

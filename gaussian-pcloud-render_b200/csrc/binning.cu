@@ -238,7 +238,10 @@ __global__ void __launch_bounds__(1024) depth_hist_kernel(const uint32_t* __rest
 #define SORT_WARPS (SORT_THREADS / 32)
 #define SORT_ROUNDS (GS_SORT_CHUNK / SORT_THREADS)
 #define SORT_SMEM ((2 * GS_SORT_CHUNK + SORT_WARPS * GS_RADIX + 4 * GS_RADIX + 4 * SORT_THREADS) * 4 + 64)
-__global__ void __launch_bounds__(SORT_THREADS) depth_pass_kernel(const uint32_t* __restrict__ key_in,
+#ifndef SORT_MIN_BLOCKS
+#define SORT_MIN_BLOCKS 2  // <= 64 registers: leaves room for blend CTAs of other frames next to a sort CTA (+6 % frames/s)
+#endif
+__global__ void __launch_bounds__(SORT_THREADS, SORT_MIN_BLOCKS) depth_pass_kernel(const uint32_t* __restrict__ key_in,
                                                                   const uint32_t* __restrict__ idx_in,
                                                                   uint32_t* __restrict__ key_out,
                                                                   uint32_t* __restrict__ idx_out,
@@ -566,8 +569,11 @@ __global__ void __launch_bounds__(1024) plan_kernel(const uint32_t* __restrict__
 #define PART_MATCH(act, v) match_bits<(NB == 128) ? 8 : 9>(act, v)
 #endif
 
+#ifndef PART_MIN_BLOCKS
+#define PART_MIN_BLOCKS 4
+#endif
 template <int NB, int PASS>
-__global__ void __launch_bounds__(256, (NB == 128) ? 4 : 2) range_partition_kernel(
+__global__ void __launch_bounds__(256, (NB == 128) ? PART_MIN_BLOCKS : 2) range_partition_kernel(
     const uint32_t* __restrict__ sorted_idx, const ushort4* __restrict__ rect, uint32_t P,  // PASS 1 input
     const uint2* __restrict__ items_in,                                                      // PASS 2 input
     const int* __restrict__ rdiff, int gx, int gy, const uint32_t* __restrict__ tile_start,
