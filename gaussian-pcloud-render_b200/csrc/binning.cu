@@ -723,6 +723,7 @@ __global__ void __launch_bounds__(256, (NB == 128) ? PART_MIN_BLOCKS : 2) range_
             }
         }
         __syncthreads();
+        BIN_MARK(tl_slot, 3);
         // ---- phase C: scatter, round by round (positions of a bin advance by the round's population)
 #pragma unroll
         for (int r = 0; r < PART_ROUNDS; r++) {
