@@ -14,6 +14,9 @@
 //     reduction before they reach memory, so a Gaussian receives 9 atomics per WARP that touches it instead of
 //     9 per PIXEL (backward.cu:523-554): 10-32x fewer L2 atomics.  Summation order differs from the reference's
 //     (which is itself non-deterministic); gradients agree to fp32 round-off (measured 1e-6 relative at C3).
+// Measured and rejected: two pixels per lane (8x8 blocks, partials pre-added in the lane, one reduction per 64
+// pixels).  106 registers (2 CTAs/SM instead of 3) and two divergent per-pixel regions per hit: backward 2.19 ms
+// against 1.77 ms for this kernel at C3 (tools/bench_backward.py, median of 40 views).
 #include "gs_common.cuh"
 
 namespace {

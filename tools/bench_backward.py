@@ -29,6 +29,9 @@ vd = [(t(v.viewmatrix), t(v.projmatrix), t(v.campos)) for v in views]
 L = _C.lib()
 
 
+bwd_events = None
+
+
 def ours(i, backward=True):
     v = views[i % 120]
     vm, pm, cp = vd[i % 120]
@@ -39,7 +42,11 @@ def ours(i, backward=True):
     if backward:
         for x in d.values():
             x.grad = None
+        if bwd_events is not None:
+            bwd_events[0].record()
         color.backward(wgt)
+        if bwd_events is not None:
+            bwd_events[1].record()
 
 
 ref = ReferenceCUDA() if ReferenceCUDA.available() else None
@@ -55,22 +62,38 @@ def theirs(i, backward=True):
         ref.backward(wgt)
 
 
-def timeit(fn, n=30, **kw):
-    for i in range(5):
-        fn(i, **kw)
+def timeit(fn, n=40, **kw):
+    """Median over n views of the per-call device time (the mean is dominated by caching-allocator growth spikes)."""
+    for i in range(10):
+        fn(i * 7, **kw)
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
+    ts = []
     for i in range(n):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
         fn(5 + i * 7, **kw)
-    e1.record()
-    torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / n
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return float(np.median(ts))
+
+
+def time_backward_only(n=40):
+    global bwd_events
+    ts = []
+    for i in range(n):
+        bwd_events = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ours(5 + i * 7)
+        torch.cuda.synchronize()
+        ts.append(bwd_events[0].elapsed_time(bwd_events[1]))
+    bwd_events = None
+    return float(np.median(ts))
 
 
 out = {"workload": f"C3: 800K pts, 1920x1080, forward+backward, opacity={opacity}"}
 out["b200_fwd_ms"] = timeit(ours, backward=False)
 out["b200_fwd_bwd_ms"] = timeit(ours)
+out["b200_bwd_only_ms"] = time_backward_only()
 if ref is not None:
     out["reference_fwd_ms"] = timeit(theirs, backward=False)
     out["reference_fwd_bwd_ms"] = timeit(theirs)
