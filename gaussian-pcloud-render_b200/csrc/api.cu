@@ -66,6 +66,8 @@ int make_frame(const GsScene* s, void* stream, GsFrame& f, bool forward = true) 
         if (s->shs && s->sh_stride < (s->sh_degree + 1) * (s->sh_degree + 1)) return GS_ERR_INVALID;
         if (s->sh_degree < 0 || s->sh_degree > 3) return GS_ERR_INVALID;
     }
+    if (s->downsample < 0 || s->downsample > 2) return GS_ERR_INVALID;
+    if (s->downsample == 2 && ((s->width | s->height) & 1)) return GS_ERR_INVALID;
     if (s->num_peers < 0 || s->num_peers > 8) return GS_ERR_INVALID;
     for (int k = 0; k < s->num_peers; k++)
         if (!s->peer_out_color[k]) return GS_ERR_INVALID;

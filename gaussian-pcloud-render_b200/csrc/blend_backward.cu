@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(BB_WARPS * 32, 3) blend_backward_kernel(
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ order, const uint32_t* __restrict__ list,
     const GsRec* __restrict__ rec, int W, int H, int gx, const GsHeader* __restrict__ hdr,
     unsigned int* __restrict__ queue, const float* __restrict__ bg, const float* __restrict__ final_T,
-    const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dpix, float* __restrict__ dL_dmean2D,
+    const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dpix, int ds, float* __restrict__ dL_dmean2D,
     float* __restrict__ dL_dconic, float* __restrict__ dL_dopacity, float* __restrict__ dL_dcolor) {
     __shared__ BbStage s_ring[BB_WARPS][BB_STAGES];
 
@@ -113,9 +113,17 @@ __global__ void __launch_bounds__(BB_WARPS * 32, 3) blend_backward_kernel(
         float T = T_final;
         float dpx = 0.f, dpy = 0.f, dpz = 0.f;
         if (inside) {
-            dpx = dL_dpix[pid];
-            dpy = dL_dpix[plane + pid];
-            dpz = dL_dpix[2 * plane + pid];
+            if (ds) {  // gradient of the 2x2 box mean (GsScene.downsample): a quarter of the half-resolution pixel's
+                const size_t plane2 = (size_t)(H >> 1) * (W >> 1);
+                const size_t q = (size_t)(W >> 1) * (py >> 1) + (px >> 1);
+                dpx = 0.25f * dL_dpix[q];
+                dpy = 0.25f * dL_dpix[plane2 + q];
+                dpz = 0.25f * dL_dpix[2 * plane2 + q];
+            } else {
+                dpx = dL_dpix[pid];
+                dpy = dL_dpix[plane + pid];
+                dpz = dL_dpix[2 * plane + pid];
+            }
         }
         float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
         float last_alpha = 0.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f;
@@ -286,7 +294,8 @@ cudaError_t gs_launch_blend_backward(const GsFrame& f, const GsGeom& g, const Gs
     const unsigned grid = (unsigned)min((uint32_t)g_bwd_grid, num_tiles);
     blend_backward_kernel<<<grid, BB_WARPS * 32, 0, f.stream>>>(im.ranges, im.order, b.list, g.rec, f.s.width, f.s.height,
                                                                f.gx, g.hdr, queue, f.s.background, im.final_T,
-                                                               im.n_contrib, dL_dpix, dL_dmean2D, dL_dconic, dL_dopacity,
+                                                               im.n_contrib, dL_dpix, f.s.downsample == 2 ? 1 : 0, dL_dmean2D,
+                                                               dL_dconic, dL_dopacity,
                                                                dL_dcolor);
     gs_note_launch();
     return cudaGetLastError();

@@ -108,6 +108,7 @@ struct BfExtra {
 // ranks, addressed through NVLink peer mappings -- the blend kernel assembles the frame on every GPU itself.
 struct BfTargets {
     int n;
+    int ds;  // 1: the epilogue stores the 2x2 box mean of the frame, images are [3][H/2][W/2] (GsScene.downsample)
     float* img[8];
 };
 typedef unsigned long long f2;
@@ -119,6 +120,14 @@ __device__ __forceinline__ f2 sub2(f2 a, f2 b) { f2 r; asm("sub.rn.f32x2 %0, %1,
 __device__ __forceinline__ f2 mul2(f2 a, f2 b) { f2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { f2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
 __device__ __forceinline__ void fma2_acc(f2& acc, f2 a, f2 b) { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b)); }
+
+// 2x2 box mean of a value held by the four lanes (lx, lx^1) x (ly, ly^1) of a block: bit for bit what
+// F.interpolate(mode="bilinear", align_corners=False) computes when halving an image (all four weights are 0.5 * 0.5;
+// simple_raw_render.py:281-284).
+__device__ __forceinline__ float box4(float v) {
+    const float h = v + __shfl_xor_sync(GS_FULL, v, 1);
+    return 0.25f * (h + __shfl_xor_sync(GS_FULL, h, 8));
+}
 
 #ifndef BF_SLOT_NUM  // fraction of the CTA slots the blend grid may occupy
 #define BF_SLOT_NUM 3
@@ -156,6 +165,34 @@ __global__ void __launch_bounds__(BF_WARPS * 32, (K == 0) ? BF_PX2_OCC : 2) blen
         if (unit >= blend_units) {  // ---- empty tile: colour = background, T = 1, no contributor
             const uint32_t tile = order[nonempty + (unit - blend_units)];
             const int x0 = (int)(tile % gx) * GS_TILE, y0 = (int)(tile / gx) * GS_TILE;
+            if (tg.ds) {  // half-resolution colour (8x8 per tile), full-resolution T / contributor count
+                const int W2 = W >> 1, H2 = H >> 1;
+                const size_t plane2 = (size_t)W2 * H2;
+                const int qx = (x0 >> 1) + (lane & 7);
+#pragma unroll
+                for (int r = 0; r < 2; r++) {
+                    const int qy = (y0 >> 1) + r * 4 + (lane >> 3);
+                    if (qx < W2 && qy < H2) {
+                        const size_t pid = (size_t)W2 * qy + qx;
+                        _Pragma("unroll") for (int k = 0; k < 8; k++) if (k < tg.n) {
+                            float* oc = tg.img[k];
+                            oc[pid] = bg0; oc[plane2 + pid] = bg1; oc[2 * plane2 + pid] = bg2;
+                        }
+#pragma unroll
+                        for (int k = 0; k < K; k++) {
+                            float* oc = ex.out[k];
+                            oc[pid] = bg0; oc[plane2 + pid] = bg1; oc[2 * plane2 + pid] = bg2;
+                        }
+                    }
+                }
+                for (int r = 0; r < 8; r++) {
+                    const int px = x0 + (lane & 15), py = y0 + r * 2 + (lane >> 4);
+                    if (px < W && py < H) {
+                        const size_t pid = (size_t)W * py + px;
+                        final_T[pid] = 1.f; n_contrib[pid] = 0u;
+                    }
+                }
+            } else
             if ((W & 3) == 0 && x0 + GS_TILE <= W) {
                 const int px = x0 + (lane & 3) * 4;
 #pragma unroll
@@ -337,38 +374,52 @@ __global__ void __launch_bounds__(BF_WARPS * 32, (K == 0) ? BF_PX2_OCC : 2) blen
         cp_async_wait<0>();
         const f2 C0 = pk(c0A, c0B), C1 = pk(c1A, c1B), C2 = pk(c2A, c2B);
 
-        if (insA) {
-            const size_t pid = (size_t)W * pyA + px;
-            const float T = lo(T2);
-            final_T[pid] = T;
-            n_contrib[pid] = lastA;
-            const float o0 = lo(C0) + T * bg0, o1 = lo(C1) + T * bg1, o2 = lo(C2) + T * bg2;
+        const float TA = lo(T2), TB = hi(T2);
+        const size_t pidA = (size_t)W * pyA + px, pidB = (size_t)W * pyB + px;
+        if (insA) { final_T[pidA] = TA; n_contrib[pidA] = lastA; }
+        if (insB) { final_T[pidB] = TB; n_contrib[pidB] = lastB; }
+        float oA[3 * (K + 1)], oB[3 * (K + 1)];
+        oA[0] = lo(C0) + TA * bg0; oA[1] = lo(C1) + TA * bg1; oA[2] = lo(C2) + TA * bg2;
+        oB[0] = hi(C0) + TB * bg0; oB[1] = hi(C1) + TB * bg1; oB[2] = hi(C2) + TB * bg2;
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            oA[3 * k + 3] = lo(E[k][0]) + TA * bg0; oA[3 * k + 4] = lo(E[k][1]) + TA * bg1;
+            oA[3 * k + 5] = lo(E[k][2]) + TA * bg2;
+            oB[3 * k + 3] = hi(E[k][0]) + TB * bg0; oB[3 * k + 4] = hi(E[k][1]) + TB * bg1;
+            oB[3 * k + 5] = hi(E[k][2]) + TB * bg2;
+        }
+        size_t oplane = plane, opA = pidA, opB = pidB;
+        bool wA = insA, wB = insB;
+        if (tg.ds) {  // W, H even and blocks start on even pixels: a 2x2 group is inside or outside as a whole
+#pragma unroll
+            for (int c = 0; c < 3 * (K + 1); c++) { oA[c] = box4(oA[c]); oB[c] = box4(oB[c]); }
+            const int W2 = W >> 1;
+            oplane = (size_t)W2 * (H >> 1);
+            opA = (size_t)W2 * (pyA >> 1) + (px >> 1);
+            opB = (size_t)W2 * (pyB >> 1) + (px >> 1);
+            const bool writer = (lane & 9) == 0;  // even lx, even ly
+            wA = insA && writer; wB = insB && writer;
+        }
+        if (wA) {
             _Pragma("unroll") for (int k = 0; k < 8; k++) if (k < tg.n) {
                 float* oc = tg.img[k];
-                oc[pid] = o0; oc[plane + pid] = o1; oc[2 * plane + pid] = o2;
+                oc[opA] = oA[0]; oc[oplane + opA] = oA[1]; oc[2 * oplane + opA] = oA[2];
             }
 #pragma unroll
             for (int k = 0; k < K; k++) {
                 float* oc = ex.out[k];
-                oc[pid] = lo(E[k][0]) + T * bg0; oc[plane + pid] = lo(E[k][1]) + T * bg1;
-                oc[2 * plane + pid] = lo(E[k][2]) + T * bg2;
+                oc[opA] = oA[3 * k + 3]; oc[oplane + opA] = oA[3 * k + 4]; oc[2 * oplane + opA] = oA[3 * k + 5];
             }
         }
-        if (insB) {
-            const size_t pid = (size_t)W * pyB + px;
-            const float T = hi(T2);
-            final_T[pid] = T;
-            n_contrib[pid] = lastB;
-            const float o0 = hi(C0) + T * bg0, o1 = hi(C1) + T * bg1, o2 = hi(C2) + T * bg2;
+        if (wB) {
             _Pragma("unroll") for (int k = 0; k < 8; k++) if (k < tg.n) {
                 float* oc = tg.img[k];
-                oc[pid] = o0; oc[plane + pid] = o1; oc[2 * plane + pid] = o2;
+                oc[opB] = oB[0]; oc[oplane + opB] = oB[1]; oc[2 * oplane + opB] = oB[2];
             }
 #pragma unroll
             for (int k = 0; k < K; k++) {
                 float* oc = ex.out[k];
-                oc[pid] = hi(E[k][0]) + T * bg0; oc[plane + pid] = hi(E[k][1]) + T * bg1;
-                oc[2 * plane + pid] = hi(E[k][2]) + T * bg2;
+                oc[opB] = oB[3 * k + 3]; oc[oplane + opB] = oB[3 * k + 4]; oc[2 * oplane + opB] = oB[3 * k + 5];
             }
         }
     }
@@ -394,6 +445,7 @@ cudaError_t launch_blend(const GsFrame& f, const GsGeom& g, const GsBinning& b, 
     }
     BfTargets tg;
     tg.n = f.s.num_peers > 0 ? f.s.num_peers : 1;
+    tg.ds = f.s.downsample == 2 ? 1 : 0;
     for (int k = 0; k < 8; k++) tg.img[k] = f.s.num_peers > 0 ? f.s.peer_out_color[k] : out_color;
     BfExtra ex;
     ex.xrec = g.xrec;

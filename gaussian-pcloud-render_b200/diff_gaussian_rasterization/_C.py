@@ -39,7 +39,7 @@ class GsScene(C.Structure):
                 ("colors_precomp", C.c_void_p), ("opacities", C.c_void_p), ("scales", C.c_void_p),
                 ("rotations", C.c_void_p), ("cov3D_precomp", C.c_void_p), ("viewmatrix", C.c_void_p),
                 ("projmatrix", C.c_void_p), ("campos", C.c_void_p),
-                ("num_peers", C.c_int32), ("reserved", C.c_int32), ("peer_out_color", C.c_void_p * 8),
+                ("num_peers", C.c_int32), ("downsample", C.c_int32), ("peer_out_color", C.c_void_p * 8),
                 ("num_extra", C.c_int32), ("reserved2", C.c_int32), ("extra_colors", C.c_void_p * 3),
                 ("extra_out", C.c_void_p * 3)]
 
@@ -158,8 +158,9 @@ def _pooled_workspaces(dev):
 def make_scene(*, P, sh_degree, sh_stride, width, height, tan_fovx, tan_fovy, scale_modifier, prefiltered, debug,
                background, means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, viewmatrix,
                projmatrix, campos, tile_rows: Optional[Tuple[int, int]] = None, peer_out=None,
-               extra_passes=None) -> GsScene:
-    """peer_out: optional list of (peer-mapped) device pointers of (3,H,W) images the blend epilogue writes to.
+               extra_passes=None, downsample: int = 1) -> GsScene:
+    """downsample: 2 = the blend epilogue stores the 2x2 box mean (all output images are (3,H/2,W/2)).
+    peer_out: optional list of (peer-mapped) device pointers of (3,H,W) images the blend epilogue writes to.
     extra_passes: optional list of up to three (colors (P,3) CUDA tensor, out (3,H,W) CUDA tensor) pairs blended in
     the same list walk (the caller keeps the tensors alive)."""
     r0, r1 = tile_rows if tile_rows is not None else (0, 0)
@@ -173,7 +174,7 @@ def make_scene(*, P, sh_degree, sh_stride, width, height, tan_fovx, tan_fovy, sc
     return GsScene(P, sh_degree, sh_stride, width, height, tan_fovx, tan_fovy, scale_modifier, int(bool(prefiltered)),
                    int(bool(debug)), int(r0), int(r1), _ptr(background), _ptr(means3D), _ptr(shs),
                    _ptr(colors_precomp), _ptr(opacities), _ptr(scales), _ptr(rotations), _ptr(cov3D_precomp),
-                   _ptr(viewmatrix), _ptr(projmatrix), _ptr(campos), len(peers), 0, arr, len(extras), 0,
+                   _ptr(viewmatrix), _ptr(projmatrix), _ptr(campos), len(peers), int(downsample), arr, len(extras), 0,
                    (C.c_void_p * 3)(*([_ptr(c) for c, _ in extras] + [None] * (3 - len(extras)))),
                    (C.c_void_p * 3)(*([_ptr(o) for _, o in extras] + [None] * (3 - len(extras)))))
 
@@ -181,7 +182,7 @@ def make_scene(*, P, sh_degree, sh_stride, width, height, tan_fovx, tan_fovy, sc
 def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp,
                         viewmatrix, projmatrix, tan_fovx, tan_fovy, image_height, image_width, sh, degree, campos,
                         prefiltered, debug, tile_rows: Optional[Tuple[int, int]] = None, out_color=None,
-                        reuse_workspace: bool = False):
+                        reuse_workspace: bool = False, downsample: int = 1):
     if means3D.dim() != 2 or means3D.size(1) != 3:
         raise RuntimeError("means3D must have dimensions (num_points, 3)")
     if not means3D.is_cuda:
@@ -194,8 +195,10 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
                                    viewmatrix, projmatrix, campos)]
         bg_, m3_, sh_, col_, op_, sc_, rot_, cov_, view_, proj_, cam_ = keep
         M = int(sh.size(1)) if (sh is not None and sh.numel() != 0) else 0
+        if downsample not in (1, 2) or (downsample == 2 and (H % 2 or W % 2)):
+            raise ValueError("downsample must be 1 or 2 (2 needs an even raster size)")
         if out_color is None:
-            out_color = torch.zeros((3, H, W), dtype=torch.float32, device=dev)
+            out_color = torch.zeros((3, H // downsample, W // downsample), dtype=torch.float32, device=dev)
         radii = torch.zeros((P,), dtype=torch.int32, device=dev)
         # reuse_workspace: the three scratch buffers come from a grow-only per-device pool instead of being
         # allocated per call; valid only if nothing (no backward) reads them after the next forward on this device
@@ -206,7 +209,7 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
                                tan_fovy=float(tan_fovy), scale_modifier=float(scale_modifier), prefiltered=prefiltered,
                                debug=debug, background=bg_, means3D=m3_, shs=sh_, colors_precomp=col_, opacities=op_,
                                scales=sc_, rotations=rot_, cov3D_precomp=cov_, viewmatrix=view_, projmatrix=proj_,
-                               campos=cam_, tile_rows=tile_rows)
+                               campos=cam_, tile_rows=tile_rows, downsample=downsample)
             stream = torch.cuda.current_stream(dev).cuda_stream
             rendered = _check(L.gs_forward(C.byref(scene), geom.buf, binning.buf, img.buf, out_color.data_ptr(),
                                            radii.data_ptr(), stream), "rasterize_gaussians")
@@ -216,11 +219,11 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
 def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rotations, scale_modifier, cov3D_precomp,
                                  viewmatrix, projmatrix, tan_fovx, tan_fovy, dL_dout_color, sh, degree, campos,
                                  geomBuffer, R, binningBuffer, imageBuffer, debug,
-                                 tile_rows: Optional[Tuple[int, int]] = None):
+                                 tile_rows: Optional[Tuple[int, int]] = None, downsample: int = 1):
     L = lib()
     dev = means3D.device
     P = int(means3D.size(0))
-    H, W = int(dL_dout_color.size(1)), int(dL_dout_color.size(2))
+    H, W = int(dL_dout_color.size(1)) * downsample, int(dL_dout_color.size(2)) * downsample  # raster size
     M = int(sh.size(1)) if (sh is not None and sh.numel() != 0) else 0
     with torch.cuda.device(dev):
         z = lambda *s: torch.zeros(s, dtype=torch.float32, device=dev)
@@ -237,7 +240,7 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
                                tan_fovy=float(tan_fovy), scale_modifier=float(scale_modifier), prefiltered=False,
                                debug=debug, background=bg_, means3D=m3_, shs=sh_, colors_precomp=col_,
                                opacities=None, scales=sc_, rotations=rot_, cov3D_precomp=cov_, viewmatrix=view_,
-                               projmatrix=proj_, campos=cam_, tile_rows=tile_rows)
+                               projmatrix=proj_, campos=cam_, tile_rows=tile_rows, downsample=downsample)
             stream = torch.cuda.current_stream(dev).cuda_stream
             _check(L.gs_backward(C.byref(scene), int(R), _ptr(radii_), _ptr(geomBuffer), _ptr(binningBuffer),
                                  _ptr(imageBuffer), _ptr(dpix_), _ptr(dL_dmeans2D), _ptr(dL_dconic), _ptr(dL_dopacity),

@@ -11,8 +11,10 @@ so `from diff_gaussian_rasterization import GaussianRasterizationSettings, Gauss
 (simple_raw_render.py:12) keeps working unchanged.  Same exceptions for the exactly-one-of rules, same
 `debug=True` behaviour (inputs dumped to snapshot_fw.dump / snapshot_bw.dump when the library raises).
 
-Extension used by the multi-GPU path only: `GaussianRasterizer(settings, tile_rows=(r0, r1))` restricts binning
-and blending to tile rows [r0, r1); the default renders the whole frame.
+Extensions (defaults = reference behaviour): `GaussianRasterizer(settings, tile_rows=(r0, r1))` restricts binning
+and blending to tile rows [r0, r1) (multi-GPU path); `GaussianRasterizer(settings, downsample=2)` returns
+the (3, H/2, W/2) image the reference's caller computes with `F.interpolate(..., mode="bilinear")` after a
+super-sampled render (simple_raw_render.py:281-284), folded into the blend epilogue, differentiable.
 """
 from typing import NamedTuple, Optional, Tuple
 
@@ -28,15 +30,15 @@ def cpu_deep_copy_tuple(input_tuple):
 
 
 def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
-                        raster_settings, tile_rows: Optional[Tuple[int, int]] = None):
+                        raster_settings, tile_rows: Optional[Tuple[int, int]] = None, downsample: int = 1):
     return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
-                                     cov3Ds_precomp, raster_settings, tile_rows)
+                                     cov3Ds_precomp, raster_settings, tile_rows, downsample)
 
 
 class _RasterizeGaussians(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
-                raster_settings, tile_rows=None):
+                raster_settings, tile_rows=None, downsample=1):
         rs = raster_settings
         args = (rs.bg, means3D, colors_precomp, opacities, scales, rotations, rs.scale_modifier, cov3Ds_precomp,
                 rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, rs.image_height, rs.image_width, sh,
@@ -47,17 +49,18 @@ class _RasterizeGaussians(torch.autograd.Function):
         if rs.debug:
             cpu_args = cpu_deep_copy_tuple(args)  # copy before anything can corrupt them
             try:
-                out = _C.rasterize_gaussians(*args, tile_rows=tile_rows, reuse_workspace=reuse)
+                out = _C.rasterize_gaussians(*args, tile_rows=tile_rows, reuse_workspace=reuse, downsample=downsample)
             except Exception as ex:
                 torch.save(cpu_args, "snapshot_fw.dump")
                 print("\nAn error occured in forward. Please forward snapshot_fw.dump for debugging.")
                 raise ex
         else:
-            out = _C.rasterize_gaussians(*args, tile_rows=tile_rows, reuse_workspace=reuse)
+            out = _C.rasterize_gaussians(*args, tile_rows=tile_rows, reuse_workspace=reuse, downsample=downsample)
         num_rendered, color, radii, geomBuffer, binningBuffer, imgBuffer = out
         ctx.raster_settings = rs
         ctx.num_rendered = num_rendered
         ctx.tile_rows = tile_rows
+        ctx.downsample = downsample
         ctx.save_for_backward(colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, geomBuffer,
                               binningBuffer, imgBuffer)
         ctx.mark_non_differentiable(radii)
@@ -74,13 +77,13 @@ class _RasterizeGaussians(torch.autograd.Function):
         if rs.debug:
             cpu_args = cpu_deep_copy_tuple(args)
             try:
-                grads_c = _C.rasterize_gaussians_backward(*args, tile_rows=ctx.tile_rows)
+                grads_c = _C.rasterize_gaussians_backward(*args, tile_rows=ctx.tile_rows, downsample=ctx.downsample)
             except Exception as ex:
                 torch.save(cpu_args, "snapshot_bw.dump")
                 print("\nAn error occured in backward. Writing snapshot_bw.dump for debugging.\n")
                 raise ex
         else:
-            grads_c = _C.rasterize_gaussians_backward(*args, tile_rows=ctx.tile_rows)
+            grads_c = _C.rasterize_gaussians_backward(*args, tile_rows=ctx.tile_rows, downsample=ctx.downsample)
         (grad_means2D, grad_colors_precomp, grad_opacities, grad_means3D, grad_cov3Ds_precomp, grad_sh, grad_scales,
          grad_rotations) = grads_c
 
@@ -89,7 +92,7 @@ class _RasterizeGaussians(torch.autograd.Function):
 
         return (grad_means3D, grad_means2D, _like(grad_sh, sh), _like(grad_colors_precomp, colors_precomp),
                 grad_opacities, _like(grad_scales, scales),
-                _like(grad_rotations, rotations), _like(grad_cov3Ds_precomp, cov3Ds_precomp), None, None)
+                _like(grad_rotations, rotations), _like(grad_cov3Ds_precomp, cov3Ds_precomp), None, None, None)
 
 
 class GaussianRasterizationSettings(NamedTuple):
@@ -108,10 +111,11 @@ class GaussianRasterizationSettings(NamedTuple):
 
 
 class GaussianRasterizer(nn.Module):
-    def __init__(self, raster_settings, tile_rows: Optional[Tuple[int, int]] = None):
+    def __init__(self, raster_settings, tile_rows: Optional[Tuple[int, int]] = None, downsample: int = 1):
         super().__init__()
         self.raster_settings = raster_settings
         self.tile_rows = tile_rows
+        self.downsample = downsample
 
     def markVisible(self, positions):
         # Mark visible points (based on frustum culling for camera) with a boolean
@@ -143,4 +147,4 @@ class GaussianRasterizer(nn.Module):
             cov3D_precomp = torch.Tensor([])
 
         return rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp,
-                                   raster_settings, self.tile_rows)
+                                   raster_settings, self.tile_rows, self.downsample)

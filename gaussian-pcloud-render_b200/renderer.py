@@ -21,8 +21,14 @@ class FrameRenderer:
     SLOTS = 1024  # pinned status slots: one per in-flight frame
 
     def __init__(self, cloud: dict, width: int, height: int, bg, device, capacity: int = 0, headroom: float = 1.3,
-                 tile_rows: Optional[Tuple[int, int]] = None, share: Optional["FrameRenderer"] = None):
+                 tile_rows: Optional[Tuple[int, int]] = None, share: Optional["FrameRenderer"] = None,
+                 downsample: int = 1):
+        """downsample=2: width x height is the (super-sampled) raster size, every output image is the 2x2 box mean
+        (3, height/2, width/2) -- the reference caller's bilinear x0.5, done in the blend epilogue."""
         self.L = _C.lib()
+        if downsample not in (1, 2) or (downsample == 2 and (int(width) % 2 or int(height) % 2)):
+            raise ValueError("downsample must be 1 or 2 (2 needs an even raster size)")
+        self.downsample = int(downsample)
         self.dev = torch.device(device)
         self.W, self.H = int(width), int(height)
         if share is not None:  # same cloud already resident on the device: share the attribute tensors
@@ -41,7 +47,8 @@ class FrameRenderer:
             self.geom = torch.empty(self.L.gs_geometry_bytes(self.P), dtype=torch.uint8, device=self.dev)
             self.img = torch.empty(self.L.gs_image_bytes(self.W, self.H), dtype=torch.uint8, device=self.dev)
             self.radii = torch.zeros(self.P, dtype=torch.int32, device=self.dev)
-            self.color = torch.zeros((3, self.H, self.W), dtype=torch.float32, device=self.dev)
+            self.color = torch.zeros((3, self.H // self.downsample, self.W // self.downsample), dtype=torch.float32,
+                                     device=self.dev)
             self.status_host = torch.zeros((self.SLOTS, 2), dtype=torch.int64).pin_memory()
         self.capacity = 0
         self.binning = None
@@ -61,7 +68,7 @@ class FrameRenderer:
                              colors_precomp=None, opacities=self.opacities, scales=self.scales,
                              rotations=self.rotations, cov3D_precomp=None, viewmatrix=viewmatrix,
                              projmatrix=projmatrix, campos=campos, tile_rows=tile_rows, peer_out=peer_out,
-                             extra_passes=extra_passes)
+                             extra_passes=extra_passes, downsample=self.downsample)
 
     def upload_view(self, view):
         """host View (scenes.make_view) -> device tensors; done once per camera, outside the frame loop."""
@@ -103,7 +110,8 @@ class FrameRenderer:
                               debug=False, background=self.bg, means3D=self.means3D, shs=sh, colors_precomp=cp,
                               opacities=self.opacities, scales=self.scales, rotations=self.rotations,
                               cov3D_precomp=None, viewmatrix=viewmatrix, projmatrix=projmatrix, campos=campos,
-                              tile_rows=tile_rows if tile_rows is not None else self.tile_rows)
+                              tile_rows=tile_rows if tile_rows is not None else self.tile_rows,
+                              downsample=self.downsample)
         with torch.cuda.device(self.dev):
             st = torch.cuda.current_stream(self.dev).cuda_stream
             _C._check(self.L.gs_forward_recolor(C.byref(scene), self.geom.data_ptr(), self.binning.data_ptr(),
@@ -153,11 +161,11 @@ class FramePipeline:
     """
 
     def __init__(self, cloud: dict, width: int, height: int, bg, device, depth: int = 3, capacity: int = 0,
-                 headroom: float = 1.3):
+                 headroom: float = 1.3, downsample: int = 1):
         self.lanes = []
         for k in range(max(1, int(depth))):
             self.lanes.append(FrameRenderer(cloud, width, height, bg, device, capacity=capacity, headroom=headroom,
-                                            share=self.lanes[0] if self.lanes else None))
+                                            share=self.lanes[0] if self.lanes else None, downsample=downsample))
         self.dev = self.lanes[0].dev
         with torch.cuda.device(self.dev):
             self.streams = [torch.cuda.Stream(self.dev) for _ in self.lanes]

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define GS_ABI_VERSION 2
+#define GS_ABI_VERSION 3
 
 enum {
     GS_OK = 0,
@@ -70,7 +70,12 @@ typedef struct GsScene {
      * rank's own image) instead of into out_color, so the frame is assembled on all GPUs by the blend kernel itself
      * and only a barrier follows.  0 = write out_color only. */
     int32_t num_peers;
-    int32_t reserved;
+    /* Super-sample epilogue: 0 or 1 = full-resolution output (reference behaviour).  2 = the blend
+     * epilogue stores the 2x2 box mean of the frame, i.e. exactly the image the reference's caller obtains with
+     * F.interpolate(size=(H/2, W/2), mode="bilinear", align_corners=False) (simple_raw_render.py:281-284): out_color,
+     * peer_out_color[], extra_out[] and gs_backward's dL_dpix are then [3][H/2][W/2]; width and height (the raster
+     * size) must be even. */
+    int32_t downsample;
     float* peer_out_color[8];    /* each [3][H][W] */
     /* Extra colour passes blended in the SAME list walk as the frame (forward only): up to three more
      * per-Gaussian colour sets, e.g. the position / hit-map / normal passes of the reference's caller

@@ -358,6 +358,94 @@ def test_colour_passes_reuse_geometry_bitwise():
         assert torch.equal(o, refs[k])
 
 
+def _halve(img):
+    """What the reference's caller does after a super-sampled render (simple_raw_render.py:281-284)."""
+    import torch.nn.functional as F
+    return F.interpolate(img[None], size=(img.shape[1] // 2, img.shape[2] // 2), mode="bilinear",
+                         align_corners=False)[0]
+
+
+@pytest.mark.parametrize("P,W,H,sf", [(30000, 512, 512, 256.0), (8000, 330, 190, 200.0), (300, 34, 18, 60.0),
+                                      (60000, 1024, 1024, 256.0)])
+def test_supersample_epilogue_equals_bilinear_halving(P, W, H, sf, oracle32):
+    """GsScene.downsample = 2: the half-resolution image written by the blend epilogue is bit for bit
+    torch's bilinear x0.5 of the full-resolution frame (drop-in module, resident renderer, extra colour passes,
+    empty tiles, partial tiles), and within the pixel tolerance of the CPU oracle's frame halved on the CPU."""
+    dev = _dev()
+    from diff_gaussian_rasterization import GaussianRasterizer
+    from renderer import FrameRenderer
+    cl = scenes.human_cloud(P, scale_factor=sf, seed=21, opacity="uniform")
+    v = scenes.make_view(scenes.orbit_c2w(12)[5], W, H)
+    kw = dict(means3D=cl["means3D"], opacities=cl["opacities"], W=W, H=H, viewmatrix=v.viewmatrix,
+              projmatrix=v.projmatrix, campos=v.campos, bg=np.array([1.0, 0.5, 0.25], np.float32), tanfovx=v.tanfovx,
+              tanfovy=v.tanfovy, sh_degree=1, shs=cl["shs"], scales=cl["scales"], rotations=cl["rotations"])
+    full, radii, leaves, _ = _render(kw, dev)
+    want = _halve(full)
+    rs = _settings(kw, dev)
+    half, radii2 = GaussianRasterizer(rs, downsample=2)(leaves["means3D"], None, leaves["opacities"], shs=leaves["shs"],
+                                                         scales=leaves["scales"], rotations=leaves["rotations"])
+    assert half.shape == (3, H // 2, W // 2) and torch.equal(radii, radii2)
+    assert torch.equal(half, want)
+    if P <= 30000:
+        f = oracle32.forward(**kw)
+        assert (half.cpu() - _halve(torch.from_numpy(f["color"]))).abs().max() <= PIX_TOL
+    # resident renderer + three extra colour passes in the same list walk
+    fr = FrameRenderer(cl, W, H, [1.0, 0.5, 0.25], dev, capacity=8_000_000, downsample=2)
+    vd = fr.upload_view(v)
+    rng = np.random.default_rng(3)
+    cols = [torch.from_numpy(rng.random((P, 3)).astype(np.float32)).to(dev) for _ in range(3)]
+    extra = [(c, torch.empty((3, H // 2, W // 2), device=dev)) for c in cols]
+    out = fr.enqueue(vd, extra_passes=extra)
+    torch.cuda.synchronize()
+    assert fr.status()[2] == 0 and torch.equal(out, want)
+    for c, o in extra:
+        ref_full = _render(dict({k: x for k, x in kw.items() if k != "shs"}, colors_precomp=c.cpu(), sh_degree=0), dev)[0]
+        assert torch.equal(o, _halve(ref_full))
+    again = fr.enqueue_pass(vd, torch.empty((3, H // 2, W // 2), device=dev), colors_precomp=cols[1])
+    torch.cuda.synchronize()
+    assert torch.equal(again, extra[1][1])
+
+
+def test_supersample_epilogue_backward_matches_autograd_through_interpolate():
+    """Gradients through the fused 2x2 mean equal autograd through the full-resolution frame + F.interpolate."""
+    dev = _dev()
+    from diff_gaussian_rasterization import GaussianRasterizer
+    W, H, P = 384, 256, 20000
+    cl = scenes.human_cloud(P, scale_factor=200.0, seed=22, opacity="uniform")
+    v = scenes.make_view(scenes.orbit_c2w(12)[4], W, H)
+    kw = dict(means3D=cl["means3D"], opacities=cl["opacities"], W=W, H=H, viewmatrix=v.viewmatrix,
+              projmatrix=v.projmatrix, campos=v.campos, bg=np.ones(3, np.float32), tanfovx=v.tanfovx,
+              tanfovy=v.tanfovy, sh_degree=1, shs=cl["shs"], scales=cl["scales"], rotations=cl["rotations"])
+    wgt = torch.from_numpy(loss_weights((3, H // 2, W // 2))).to(dev)
+    full, _, la, m2a = _render(kw, dev, requires_grad=True)
+    (_halve(full) * wgt).sum().backward()
+    rs = _settings(kw, dev)
+    lb = {k: t.detach().clone().requires_grad_(True) for k, t in la.items()}
+    m2b = torch.zeros_like(lb["means3D"], requires_grad=True)
+    half, _ = GaussianRasterizer(rs, downsample=2)(lb["means3D"], m2b, lb["opacities"], shs=lb["shs"],
+                                                   scales=lb["scales"], rotations=lb["rotations"])
+    (half * wgt).sum().backward()
+    for k in la:
+        ga, gb = la[k].grad, lb[k].grad
+        assert float((ga - gb).abs().max()) <= 2e-5 * float(ga.abs().max()) + 1e-12, k
+    assert float((m2a.grad - m2b.grad).abs().max()) <= 2e-5 * float(m2a.grad.abs().max()) + 1e-12
+
+
+def test_supersample_epilogue_rejects_odd_raster():
+    dev = _dev()
+    from diff_gaussian_rasterization import GaussianRasterizer
+    cl = scenes.tiny_cloud(10, seed=1, sh_degree=1)
+    v = scenes.make_view(scenes.orbit_c2w(12)[1], 33, 32)
+    kw = dict(means3D=cl["means3D"], opacities=cl["opacities"], W=33, H=32, viewmatrix=v.viewmatrix,
+              projmatrix=v.projmatrix, campos=v.campos, bg=np.ones(3, np.float32), tanfovx=v.tanfovx,
+              tanfovy=v.tanfovy, sh_degree=1, shs=cl["shs"], scales=cl["scales"], rotations=cl["rotations"])
+    rs = _settings(kw, dev)
+    t = lambda k: torch.as_tensor(kw[k]).to(dev).float()
+    with pytest.raises((ValueError, RuntimeError)):
+        GaussianRasterizer(rs, downsample=2)(t("means3D"), None, t("opacities"), shs=t("shs"), scales=t("scales"),
+                                             rotations=t("rotations"))
+
+
 def test_peer_store_tile_sharding_two_gpus():
     """Tile-row shards written by the blend epilogue into every rank's symmetric-memory image (NVLink peer stores +
     one barrier) assemble the single-GPU frame bit for bit.  Needs two GPUs (skipped on the one-GPU test box;
