@@ -279,6 +279,12 @@ int32_t gs_mark_visible(int32_t P, const float* means3D, const float* viewmatrix
     return GS_OK;
 }
 
+int32_t gs_make_views(const float* c2w, int32_t N, const float* proj4_host, float* views, void* stream) {
+    if (N < 0 || !proj4_host || (N > 0 && (!c2w || !views))) return GS_ERR_INVALID;
+    GS_CU(gs_launch_make_views(c2w, N, proj4_host, views, (cudaStream_t)stream));
+    return GS_OK;
+}
+
 int64_t gs_fetch(const GsScene* scene, const char* geometry, const char* binning, const char* image,
                  int64_t num_rendered, const char* name, void* host_dst, int64_t max_bytes, void* stream) {
     GsFrame f;

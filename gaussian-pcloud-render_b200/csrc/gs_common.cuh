@@ -200,3 +200,4 @@ cudaError_t gs_launch_preprocess_backward(const GsFrame& f, const GsGeom& g, con
                                           float* dL_drot);
 cudaError_t gs_launch_mark_visible(int P, const float* means3D, const float* view, uint8_t* present,
                                    cudaStream_t stream);
+cudaError_t gs_launch_make_views(const float* c2w, int N, const float* p4, float* views, cudaStream_t stream);

@@ -280,6 +280,34 @@ __global__ void mark_visible_kernel(int P, const float* __restrict__ means, cons
     present[i] = p.z > 0.2f;
 }
 
+// One thread per view: rigid inverse (R^T, -R^T t), transposes, and the product with the sparse projection matrix.
+__global__ void make_views_kernel(const float* __restrict__ c2w, int N, float p00, float p11, float p22, float p23,
+                                  float* __restrict__ views) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const float* h = c2w + 16 * (size_t)n;
+    float* o = views + GS_VIEW_STRIDE * (size_t)n;
+    // w2c = [R^T | -(R^T t)]; viewmatrix = w2c^T, i.e. vt[i][k] = w2c[k][i]
+    float w2c[4][4];
+    for (int i = 0; i < 3; i++) {
+        for (int j = 0; j < 3; j++) w2c[i][j] = h[4 * j + i];
+        w2c[i][3] = -1.0f * (h[4 * 0 + i] * h[3] + h[4 * 1 + i] * h[7] + h[4 * 2 + i] * h[11]);
+    }
+    w2c[3][0] = w2c[3][1] = w2c[3][2] = 0.f;
+    w2c[3][3] = 1.f;
+    for (int i = 0; i < 4; i++) {
+        const float v0 = w2c[0][i], v1 = w2c[1][i], v2 = w2c[2][i], v3 = w2c[3][i];  // row i of viewmatrix
+        o[4 * i + 0] = v0; o[4 * i + 1] = v1; o[4 * i + 2] = v2; o[4 * i + 3] = v3;
+        // row i of viewmatrix * P^T; P^T has (0,0)=p00 (1,1)=p11 (2,2)=p22 (3,2)=p23 (2,3)=1
+        o[16 + 4 * i + 0] = v0 * p00;
+        o[16 + 4 * i + 1] = v1 * p11;
+        o[16 + 4 * i + 2] = v2 * p22 + v3 * p23;
+        o[16 + 4 * i + 3] = v2;
+    }
+    o[32] = h[3]; o[33] = h[7]; o[34] = h[11];
+    for (int k = 35; k < GS_VIEW_STRIDE; k++) o[k] = 0.f;
+}
+
 }  // namespace
 
 cudaError_t gs_launch_preprocess(const GsFrame& f, const GsGeom& g, const GsImage& im, int32_t* radii) {
@@ -338,6 +366,13 @@ cudaError_t gs_launch_recolor(const GsFrame& f, const GsGeom& g) {
 cudaError_t gs_launch_mark_visible(int P, const float* means3D, const float* view, uint8_t* present,
                                    cudaStream_t stream) {
     mark_visible_kernel<<<(unsigned)gs_div_up(P, 256), 256, 0, stream>>>(P, means3D, view, present);
+    gs_note_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t gs_launch_make_views(const float* c2w, int N, const float* p4, float* views, cudaStream_t stream) {
+    if (N <= 0) return cudaSuccess;
+    make_views_kernel<<<(unsigned)gs_div_up(N, 64), 64, 0, stream>>>(c2w, N, p4[0], p4[1], p4[2], p4[3], views);
     gs_note_launch();
     return cudaGetLastError();
 }

@@ -79,6 +79,8 @@ def lib() -> C.CDLL:
         L.gs_backward.argtypes = [C.POINTER(GsScene), C.c_int64] + [C.c_void_p] * 15
         L.gs_mark_visible.restype = C.c_int32
         L.gs_mark_visible.argtypes = [C.c_int32] + [C.c_void_p] * 5
+        L.gs_make_views.restype = C.c_int32
+        L.gs_make_views.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_float), C.c_void_p, C.c_void_p]
         L.gs_fetch.restype = C.c_int64
         L.gs_fetch.argtypes = [C.POINTER(GsScene), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_char_p,
                                C.c_void_p, C.c_int64, C.c_void_p]
@@ -260,6 +262,36 @@ def mark_visible(means3D, viewmatrix, projmatrix):
             _check(lib().gs_mark_visible(P, _ptr(m), _ptr(v), _ptr(p), present.data_ptr(),
                                          torch.cuda.current_stream(means3D.device).cuda_stream), "mark_visible")
     return present
+
+
+GS_VIEW_STRIDE = 48
+
+
+def projection_entries(fovx_deg: float, fovy_deg: float, znear: float = 0.01, zfar: float = 100.0):
+    """The four non-trivial entries P[0][0], P[1][1], P[2][2], P[2][3] of getProjectionMatrix
+    (simple_raw_render.py:50-69), in Python doubles as the reference computes them before storing fp32."""
+    import math
+    fovx, fovy = math.pi * fovx_deg / 180, math.pi * fovy_deg / 180  # np.pi * fov / 180, simple_raw_render.py:87
+    top, right = math.tan(fovy / 2) * znear, math.tan(fovx / 2) * znear
+    bottom, left = -top, -right
+    return (2.0 * znear / (right - left), 2.0 * znear / (top - bottom), 1.0 * zfar / (zfar - znear),
+            -(zfar * znear) / (zfar - znear))
+
+
+def make_views(c2w: torch.Tensor, fovx_deg: float, fovy_deg: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """gs_make_views: (N,4,4) camera-to-world matrices on the device -> (N, 48) fp32 rows holding viewmatrix [0:16],
+    projmatrix [16:32] and campos [32:35] of every view, built by one kernel on the current stream."""
+    if not c2w.is_cuda or c2w.dtype != torch.float32 or c2w.shape[-2:] != (4, 4):
+        raise ValueError("make_views expects a float32 CUDA tensor of shape (N, 4, 4)")
+    c2w = c2w.reshape(-1, 4, 4).contiguous()
+    N = int(c2w.size(0))
+    if out is None:
+        out = torch.empty((N, GS_VIEW_STRIDE), dtype=torch.float32, device=c2w.device)
+    p4 = (C.c_float * 4)(*projection_entries(fovx_deg, fovy_deg))
+    with torch.cuda.device(c2w.device):
+        _check(lib().gs_make_views(c2w.data_ptr(), N, p4, out.data_ptr(),
+                                   torch.cuda.current_stream(c2w.device).cuda_stream), "make_views")
+    return out
 
 
 _FETCH_DT = {"records": torch.float32, "sorted_idx": torch.int32, "sorted_key": torch.int32, "cov3D": torch.float32,

@@ -150,6 +150,27 @@ class FrameRenderer:
         return worst
 
 
+class ViewBatch:
+    """All cameras of a render call set up on the device by ONE kernel: what the reference's caller does
+    per view on the host in get_rasterize_param_from_camera (rigid inverse, transposes, a bmm, four small H2D copies;
+    simple_raw_render.py:79-112).  `batch[k]` is the view tuple FrameRenderer.enqueue takes."""
+
+    def __init__(self, c2w, fov_deg: float, device):
+        import math
+        self.dev = torch.device(device)
+        c2w = torch.as_tensor(c2w, dtype=torch.float32).reshape(-1, 4, 4)
+        self.c2w = c2w.to(self.dev, non_blocking=True)  # one upload for all views
+        self.buf = _C.make_views(self.c2w, fov_deg, fov_deg)
+        self.tanfov = math.tan(fov_deg / 180.0 * math.pi)  # the reference passes the FULL angle (simple_raw_render.py:102)
+
+    def __len__(self) -> int:
+        return int(self.buf.shape[0])
+
+    def __getitem__(self, k: int):
+        row = self.buf[k]
+        return (row[0:16], row[16:32], row[32:35], self.tanfov, self.tanfov)
+
+
 class FramePipeline:
     """Several frames in flight on separate CUDA streams, each with its own workspaces (the cloud is shared).
 

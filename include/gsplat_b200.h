@@ -144,6 +144,16 @@ int32_t gs_backward(const GsScene* scene, int64_t num_rendered, const int32_t* r
 int32_t gs_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, const float* projmatrix,
                         uint8_t* present, void* stream);
 
+/* Camera set-up for a batch of views on the device (replaces the per-view host work of
+ * get_rasterize_param_from_camera, simple_raw_render.py:79-112, and Camera.get_H_w2c = inv_homogeneous_tensors,
+ * plib/rigid_motion.py:687-703).  c2w: DEVICE array [N][4][4] of row-major camera-to-world matrices (rigid motions).
+ * proj4 = {P[0][0], P[1][1], P[2][2], P[2][3]} of getProjectionMatrix (simple_raw_render.py:50-69), computed by the
+ * caller.  views: DEVICE array [N][GS_VIEW_STRIDE] floats; per view: [0,16) viewmatrix = transpose(inverse(c2w)),
+ * [16,32) projmatrix = viewmatrix * transpose(P), [32,35) campos = translation of c2w -- the three pointers
+ * GsScene wants for view k are views + k*GS_VIEW_STRIDE + {0, 16, 32}. */
+#define GS_VIEW_STRIDE 48
+int32_t gs_make_views(const float* c2w, int32_t N, const float* proj4_host, float* views, void* stream);
+
 /* Introspection for tests / profiling: copies a named internal array of the last forward into HOST memory.
  * names: "records" (P x 12 f32: x y cx cy | cz opacity thr -cy/cz | r g b -cy/cx), "point_list" (R x u32),
  * "ranges" (Tn x 2 u32), "n_contrib" (H*W u32), "final_T" (H*W f32), "sorted_idx" (P u32), "cov3D" (P x 6 f32),

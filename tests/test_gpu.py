@@ -1,6 +1,8 @@
 """GPU parity tests (run on the B200 box: pytest -m gpu).  Everything goes through the drop-in Python API, i.e.
 through the C ABI of libgsplat_b200.so.  Checkers: the golden vectors produced by the unmodified reference CUDA
 library, the CPU oracle, and -- when oracle/_ref/libgs_ref.so travelled with the snapshot -- the live reference."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -444,6 +446,43 @@ def test_supersample_epilogue_rejects_odd_raster():
     with pytest.raises((ValueError, RuntimeError)):
         GaussianRasterizer(rs, downsample=2)(t("means3D"), None, t("opacities"), shs=t("shs"), scales=t("scales"),
                                              rotations=t("rotations"))
+
+
+@pytest.mark.parametrize("fov", [45, 40])
+def test_views_built_on_device_match_reference_camera_setup(fov, oracle32):
+    """gs_make_views against the golden outputs of the reference's get_rasterize_param_from_camera
+    and the numpy oracle; a frame rendered through a ViewBatch entry matches the CPU oracle's frame."""
+    dev = _dev()
+    from diff_gaussian_rasterization import _C
+    from oracle import camera
+    from renderer import FrameRenderer, ViewBatch
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "camera_params.npz"))
+    buf = _C.make_views(torch.from_numpy(g["c2w"]).to(dev), float(fov), float(fov)).cpu().numpy()
+    view, proj, campos = buf[:, 0:16].reshape(-1, 4, 4), buf[:, 16:32].reshape(-1, 4, 4), buf[:, 32:35]
+    r = camera.raster_params(g["c2w"], float(fov), float(fov))
+    for want in (g[f"view_{fov}"], r["viewmatrix"]):
+        np.testing.assert_allclose(view, want, rtol=0, atol=2e-6)
+    for want in (g[f"proj_{fov}"], r["projmatrix"]):
+        np.testing.assert_allclose(proj, want, rtol=2e-6, atol=2e-6)
+    assert np.array_equal(campos, g[f"campos_{fov}"]) and not buf[:, 35:].any()
+    assert _C.make_views(torch.empty((0, 4, 4), device=dev), 45.0, 45.0).shape == (0, 48)
+    # a frame through the batch
+    W, H, P = 320, 208, 20000
+    cl = scenes.human_cloud(P, scale_factor=200.0, seed=31, opacity="uniform")
+    c2w = scenes.orbit_c2w(12)
+    vb = ViewBatch(c2w, float(fov), dev)
+    assert len(vb) == 12
+    fr = FrameRenderer(cl, W, H, [1, 1, 1], dev, capacity=4_000_000)
+    img = fr.enqueue(vb[5]).clone()
+    torch.cuda.synchronize()
+    assert fr.status()[2] == 0
+    row = vb.buf[5].cpu().numpy()  # the oracle renders with the very matrices the kernel produced
+    f = oracle32.forward(means3D=cl["means3D"], opacities=cl["opacities"], W=W, H=H, viewmatrix=row[0:16].reshape(4, 4),
+                         projmatrix=row[16:32].reshape(4, 4), campos=row[32:35], bg=np.ones(3, np.float32),
+                         tanfovx=vb.tanfov, tanfovy=vb.tanfov, sh_degree=1, shs=cl["shs"], scales=cl["scales"],
+                         rotations=cl["rotations"])
+    assert np.abs(img.cpu().numpy() - f["color"]).max() <= PIX_TOL
+    assert np.array_equal(fr.radii.cpu().numpy(), f["radii"])
 
 
 def test_peer_store_tile_sharding_two_gpus():

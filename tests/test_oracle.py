@@ -176,3 +176,22 @@ def test_backward_against_finite_differences(oracle64):
             num = (loss(xp)[0] - loss(xm)[0]) / (float(xp[k][idx]) - float(xm[k][idx]))
             ana = g[gk].reshape(x.shape)[idx]
             assert ana == pytest.approx(num, rel=2e-2, abs=2e-3 * (np.abs(g[gk]).max() + 1e-9)), (k, idx, ana, num)
+
+
+@pytest.mark.parametrize("fov", [45, 40])
+def test_camera_oracle_matches_reference_camera_setup(fov):
+    """oracle/camera.py against the outputs of the reference's own get_rasterize_param_from_camera /
+    inv_homogeneous_tensors (tests/golden/camera_params.npz, generated by tests/golden/make_camera_golden.py)."""
+    from oracle import camera
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "camera_params.npz"))
+    r = camera.raster_params(g["c2w"], float(fov), float(fov), 512, 512, 2)
+    assert np.array_equal(r["viewmatrix"][:, :, :3][:, :3], g[f"view_{fov}"][:, :3, :3])      # transposed rotation: exact
+    np.testing.assert_allclose(r["viewmatrix"], g[f"view_{fov}"], rtol=0, atol=2e-6)          # -R^T t: summation order
+    np.testing.assert_allclose(r["projmatrix"], g[f"proj_{fov}"], rtol=2e-6, atol=2e-6)
+    assert np.array_equal(r["campos"], g[f"campos_{fov}"])
+    assert [r["tanfovx"], r["tanfovy"], r["image_height"], r["image_width"]] == list(g[f"scalars_{fov}"])
+    # the bench's own cameras (scenes.make_view) are the same construction
+    v = scenes.make_view(g["c2w"][3], 512, 512, fov_deg=float(fov), super_sample=2)
+    np.testing.assert_allclose(v.viewmatrix, g[f"view_{fov}"][3], atol=2e-6)
+    np.testing.assert_allclose(v.projmatrix, g[f"proj_{fov}"][3], rtol=2e-6, atol=2e-6)
+    assert (v.image_height, v.image_width, v.tanfovx) == (1024, 1024, g[f"scalars_{fov}"][0])
