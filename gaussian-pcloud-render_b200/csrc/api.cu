@@ -285,6 +285,21 @@ int32_t gs_make_views(const float* c2w, int32_t N, const float* proj4_host, floa
     return GS_OK;
 }
 
+int32_t gs_decode_head(const float* features, const float* dc_rgb, const float* primitives, int32_t P,
+                       const GsHeadLayout* L, float* means3D, float* rotations, float* scales, float* opacities,
+                       float* shs, float* normals, void* stream) {
+    if (P < 0 || !L || L->C < 0 || L->C > 96 || L->sh_ac_coeffs < 0) return GS_ERR_INVALID;
+    const int need = 4 * !!L->use_rotation + 3 * !!L->use_scale + !!L->use_opacity + 3 * !!L->use_offset +
+                     3 * !!L->use_dc_offset + 3 * !!L->est_normal + 3 * L->sh_ac_coeffs;
+    if (need > L->C || L->xyz_factor == 0.f) return GS_ERR_INVALID;
+    if (P > 0 && ((L->C > 0 && !features) || !dc_rgb || !primitives || !means3D || !rotations || !scales || !opacities ||
+                  !shs))
+        return GS_ERR_INVALID;
+    GS_CU(gs_launch_decode_head(features, dc_rgb, primitives, P, *L, means3D, rotations, scales, opacities, shs, normals,
+                                (cudaStream_t)stream));
+    return GS_OK;
+}
+
 int64_t gs_fetch(const GsScene* scene, const char* geometry, const char* binning, const char* image,
                  int64_t num_rendered, const char* name, void* host_dst, int64_t max_bytes, void* stream) {
     GsFrame f;

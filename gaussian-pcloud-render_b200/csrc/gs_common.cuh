@@ -201,3 +201,6 @@ cudaError_t gs_launch_preprocess_backward(const GsFrame& f, const GsGeom& g, con
 cudaError_t gs_launch_mark_visible(int P, const float* means3D, const float* view, uint8_t* present,
                                    cudaStream_t stream);
 cudaError_t gs_launch_make_views(const float* c2w, int N, const float* p4, float* views, cudaStream_t stream);
+cudaError_t gs_launch_decode_head(const float* feat, const float* rgb, const float* prim, int P, const GsHeadLayout& L,
+                                  float* means3D, float* rot, float* scales, float* opac, float* shs, float* normals,
+                                  cudaStream_t stream);

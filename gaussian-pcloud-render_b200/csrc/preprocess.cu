@@ -35,7 +35,9 @@ __device__ __forceinline__ float3 sh_to_rgb(int deg, const float* __restrict__ s
 #pragma unroll
     for (int ch = 0; ch < 3; ch++) {
 #define SHC(i) sh[(i) * 3 + ch]
-        float r = GS_SH_C0 * SHC(0);
+        // rounded product: on the degree-0 path the compiler would otherwise fuse it with the `+ 0.5f` below, which
+        // the reference's build does not do (measured against the live reference library: 1 ulp in the colours)
+        float r = __fmul_rn(GS_SH_C0, SHC(0));
         if (deg > 0) {
             r = r - GS_SH_C1 * y * SHC(1) + GS_SH_C1 * z * SHC(2) - GS_SH_C1 * x * SHC(3);
             if (deg > 1) {
@@ -308,6 +310,72 @@ __global__ void make_views_kernel(const float* __restrict__ c2w, int N, float p0
     for (int k = 35; k < GS_VIEW_STRIDE; k++) o[k] = 0.f;
 }
 
+// Head decode: 128 points per CTA; the feature rows are staged in shared memory with coalesced loads, then one thread
+// decodes one point.  Every operation is a single IEEE fp32 op in the reference's order, so results are bit-identical
+// to the torch expressions of model_v2.py:287-375 (clamps written as compares so that NaNs propagate like torch.clamp).
+#define HEAD_PTS 128
+__global__ void __launch_bounds__(HEAD_PTS) decode_head_kernel(const float* __restrict__ feat,
+                                                               const float* __restrict__ rgb,
+                                                               const float* __restrict__ prim, int P, GsHeadLayout L,
+                                                               float* __restrict__ means3D, float* __restrict__ rot,
+                                                               float* __restrict__ scales, float* __restrict__ opac,
+                                                               float* __restrict__ shs, float* __restrict__ normals) {
+    extern __shared__ float s_feat[];
+    const int C = L.C;
+    const size_t p0 = (size_t)blockIdx.x * HEAD_PTS;
+    const int np = (int)min((size_t)HEAD_PTS, (size_t)P - p0);
+    for (int i = threadIdx.x; i < np * C; i += HEAD_PTS) s_feat[i] = feat[p0 * C + i];
+    __syncthreads();
+    if ((int)threadIdx.x >= np) return;
+    const float* f = s_feat + threadIdx.x * C;
+    const size_t p = p0 + threadIdx.x;
+    // torch divides a CUDA tensor by a Python scalar as a multiplication with the reciprocal (ATen
+    // BinaryDivTrueKernel.cu); measured on torch 2.11 the reciprocal is taken in double and then narrowed
+    // (tools/div_probe.py).  The reference runs these expressions on the GPU, so that is what is reproduced.
+    const float inv_factor = (float)(1.0 / (double)L.xyz_factor), inv_c0 = (float)(1.0 / 0.28209479177387814);
+    int used = 0;
+    float q0 = 1.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+    if (L.use_rotation) { q0 = f[0] + 1.f; q1 = f[1] + 0.f; q2 = f[2] + 0.f; q3 = f[3] + 0.f; used += 4; }
+    rot[4 * p + 0] = q0; rot[4 * p + 1] = q1; rot[4 * p + 2] = q2; rot[4 * p + 3] = q3;
+    for (int c = 0; c < 3; c++) {
+        float sc = 1.f;
+        if (L.use_scale) { sc = f[used + c] + 1.f; sc = sc < 0.f ? 0.f : sc; }
+        scales[3 * p + c] = sc * L.radius;
+    }
+    if (L.use_scale) used += 3;
+    float o = 1.f;
+    if (L.use_opacity) {
+        const float v = f[used];
+        if (L.enable_opacity) o = v < 0.f ? 0.f : (v > 1.f ? 1.f : v);
+        used += 1;
+    }
+    opac[p] = o;
+    for (int c = 0; c < 3; c++) {
+        float x = prim[3 * p + c];
+        if (L.use_offset) x = x + f[used + c];
+        means3D[3 * p + c] = __fmul_rn(x - L.xyz_offset, inv_factor);
+    }
+    if (L.use_offset) used += 3;
+    const int M = 1 + L.sh_ac_coeffs;
+    for (int c = 0; c < 3; c++) {
+        const float dc = __fmul_rn(rgb[3 * p + c] - 0.5f, inv_c0);  // RGB2SH, models/sh_utils.py:114-115
+        shs[(size_t)3 * M * p + c] = L.use_dc_offset ? __fadd_rn(f[used + c], dc) : dc;
+    }
+    if (L.use_dc_offset) used += 3;
+    if (L.est_normal) {
+        if (normals) {
+            float n0 = f[used], n1 = f[used + 1], n2 = f[used + 2];
+            if (L.normalize_normal) {
+                const float d = fmaxf(sqrtf(n0 * n0 + n1 * n1 + n2 * n2), 1e-12f);
+                n0 /= d; n1 /= d; n2 /= d;
+            }
+            normals[3 * p] = n0; normals[3 * p + 1] = n1; normals[3 * p + 2] = n2;
+        }
+        used += 3;
+    }
+    for (int k = 0; k < 3 * L.sh_ac_coeffs; k++) shs[(size_t)3 * M * p + 3 + k] = f[used + k];
+}
+
 }  // namespace
 
 cudaError_t gs_launch_preprocess(const GsFrame& f, const GsGeom& g, const GsImage& im, int32_t* radii) {
@@ -373,6 +441,16 @@ cudaError_t gs_launch_mark_visible(int P, const float* means3D, const float* vie
 cudaError_t gs_launch_make_views(const float* c2w, int N, const float* p4, float* views, cudaStream_t stream) {
     if (N <= 0) return cudaSuccess;
     make_views_kernel<<<(unsigned)gs_div_up(N, 64), 64, 0, stream>>>(c2w, N, p4[0], p4[1], p4[2], p4[3], views);
+    gs_note_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t gs_launch_decode_head(const float* feat, const float* rgb, const float* prim, int P, const GsHeadLayout& L,
+                                  float* means3D, float* rot, float* scales, float* opac, float* shs, float* normals,
+                                  cudaStream_t stream) {
+    if (P <= 0) return cudaSuccess;
+    decode_head_kernel<<<(unsigned)gs_div_up(P, HEAD_PTS), HEAD_PTS, (size_t)HEAD_PTS * L.C * sizeof(float), stream>>>(
+        feat, rgb, prim, P, L, means3D, rot, scales, opac, shs, normals);
     gs_note_launch();
     return cudaGetLastError();
 }

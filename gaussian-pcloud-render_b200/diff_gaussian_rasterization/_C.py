@@ -44,6 +44,13 @@ class GsScene(C.Structure):
                 ("extra_out", C.c_void_p * 3)]
 
 
+class GsHeadLayout(C.Structure):
+    _fields_ = [("C", C.c_int32), ("use_rotation", C.c_int32), ("use_scale", C.c_int32), ("use_opacity", C.c_int32),
+                ("use_offset", C.c_int32), ("use_dc_offset", C.c_int32), ("est_normal", C.c_int32),
+                ("normalize_normal", C.c_int32), ("sh_ac_coeffs", C.c_int32), ("enable_opacity", C.c_int32),
+                ("radius", C.c_float), ("xyz_offset", C.c_float), ("xyz_factor", C.c_float)]
+
+
 RESIZE_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t)
 
 
@@ -81,6 +88,9 @@ def lib() -> C.CDLL:
         L.gs_mark_visible.argtypes = [C.c_int32] + [C.c_void_p] * 5
         L.gs_make_views.restype = C.c_int32
         L.gs_make_views.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_float), C.c_void_p, C.c_void_p]
+        L.gs_decode_head.restype = C.c_int32
+        L.gs_decode_head.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(GsHeadLayout)] + \
+                                    [C.c_void_p] * 7
         L.gs_fetch.restype = C.c_int64
         L.gs_fetch.argtypes = [C.POINTER(GsScene), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_char_p,
                                C.c_void_p, C.c_int64, C.c_void_p]
@@ -291,6 +301,38 @@ def make_views(c2w: torch.Tensor, fovx_deg: float, fovy_deg: float, out: Optiona
     with torch.cuda.device(c2w.device):
         _check(lib().gs_make_views(c2w.data_ptr(), N, p4, out.data_ptr(),
                                    torch.cuda.current_stream(c2w.device).cuda_stream), "make_views")
+    return out
+
+
+def decode_head(features: torch.Tensor, dc_rgb: torch.Tensor, primitives: torch.Tensor, *, scale_factor: float,
+                xyz_offset: float, use_rotation=True, use_scale=True, use_opacity=True, use_offset=False,
+                use_dc_offset=False, est_normal=False, normalize_normal=True, sh_ac_coeffs: int = 0,
+                enable_opacity=True) -> dict:
+    """gs_decode_head: the network head's feature rows -> rasterizer inputs in one kernel (models/model_v2.py:287-375,
+    simple_raw_render.py:243-250,390-394).  Returns dict(means3D, rotations, scales, opacities, shs (P,1+K,3),
+    sh_degree, normals or None); `shs` carries no zero padding -- render it with the returned sh_degree."""
+    import math
+    if not (features.is_cuda and dc_rgb.is_cuda and primitives.is_cuda):
+        raise RuntimeError("decode_head: all tensors must be CUDA tensors; no CPU path exists")
+    f32 = lambda t: t.to(torch.float32).contiguous()
+    features, dc_rgb, primitives = f32(features), f32(dc_rgb), f32(primitives)
+    P, Cc = int(features.shape[0]), int(features.shape[1])
+    dev = features.device
+    radius = math.sqrt(3) / scale_factor * 6  # np.sqrt(3) / self.scale_factor * 6, simple_raw_render.py:248
+    lay = GsHeadLayout(Cc, int(use_rotation), int(use_scale), int(use_opacity), int(use_offset), int(use_dc_offset),
+                       int(est_normal), int(normalize_normal), int(sh_ac_coeffs), int(enable_opacity), radius,
+                       float(xyz_offset), float(scale_factor))
+    e = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
+    out = dict(means3D=e(P, 3), rotations=e(P, 4), scales=e(P, 3), opacities=e(P, 1), shs=e(P, 1 + sh_ac_coeffs, 3),
+               normals=e(P, 3) if est_normal else None)
+    with torch.cuda.device(dev):
+        _check(lib().gs_decode_head(features.data_ptr(), dc_rgb.data_ptr(), primitives.data_ptr(), P, C.byref(lay),
+                                    out["means3D"].data_ptr(), out["rotations"].data_ptr(), out["scales"].data_ptr(),
+                                    out["opacities"].data_ptr(), out["shs"].data_ptr(),
+                                    out["normals"].data_ptr() if est_normal else None,
+                                    torch.cuda.current_stream(dev).cuda_stream), "decode_head")
+    k = 1 + sh_ac_coeffs
+    out["sh_degree"] = 0 if k < 4 else 1 if k < 9 else 2 if k < 16 else 3
     return out
 
 

@@ -154,6 +154,34 @@ int32_t gs_mark_visible(int32_t P, const float* means3D, const float* viewmatrix
 #define GS_VIEW_STRIDE 48
 int32_t gs_make_views(const float* c2w, int32_t N, const float* proj4_host, float* views, void* stream);
 
+/* Network head -> rasterizer inputs in one kernel (replaces the Python list comprehensions of
+ * models/model_v2.py:287-375 and the glue of simple_raw_render.py:243-250,390-394).  The flags are the reference's
+ * `args` of the same names; feature columns are consumed in the reference's order: rotation (4), scale (3),
+ * opacity (1), offset (3), dc offset (3), normal (3), then sh_ac_coeffs x 3 SH AC coefficients.
+ *   rotations = use_rotation ? f[0:4] + (1,0,0,0) : (1,0,0,0)
+ *   scales    = (use_scale ? clamp(f + 1, min 0) : 1) * radius              radius = sqrt(3)/scale_factor*6
+ *   opacities = (use_opacity && enable_opacity) ? clamp(f, 0, 1) : 1
+ *   means3D   = ((primitives + (use_offset ? f : 0)) - xyz_offset) / xyz_factor            (pcgc_rescale)
+ *   shs       = [(use_dc_offset ? f : 0) + (dc_rgb - 0.5)/C0 , AC...]   [P][1 + sh_ac_coeffs][3]
+ *   normals   = est_normal ? (normalize_normal ? f/max(|f|,1e-12) : f) : untouched        (may be NULL)
+ * The reference pads shs with 12 zero coefficients and renders with sh_degree 1 (model_v2.py:358-365); zero
+ * coefficients contribute exactly nothing (forward.cu:30-62), so the packed [P][1][3] array with sh_degree 0 gives
+ * the same frame bit for bit while preprocess reads 12 instead of 48 SH bytes per Gaussian.
+ * Divisions by a scalar are evaluated as torch evaluates them on a CUDA tensor (multiplication by the reciprocal),
+ * so every output except the normalised normals equals the reference's GPU result bit for bit.
+ * All arrays are DEVICE arrays; features is [P][C] row-major, dc_rgb and primitives are [P][3]. */
+typedef struct GsHeadLayout {
+    int32_t C;                 /* feature columns */
+    int32_t use_rotation, use_scale, use_opacity, use_offset, use_dc_offset, est_normal, normalize_normal;
+    int32_t sh_ac_coeffs;      /* AC coefficients taken from the remaining columns (0 = DC only) */
+    int32_t enable_opacity;    /* the render() argument (simple_raw_render.py:243-247) */
+    float radius;              /* multiplies the decoded scales */
+    float xyz_offset, xyz_factor;
+} GsHeadLayout;
+int32_t gs_decode_head(const float* features, const float* dc_rgb, const float* primitives, int32_t P,
+                       const GsHeadLayout* layout, float* means3D, float* rotations, float* scales, float* opacities,
+                       float* shs, float* normals, void* stream);
+
 /* Introspection for tests / profiling: copies a named internal array of the last forward into HOST memory.
  * names: "records" (P x 12 f32: x y cx cy | cz opacity thr -cy/cz | r g b -cy/cx), "point_list" (R x u32),
  * "ranges" (Tn x 2 u32), "n_contrib" (H*W u32), "final_T" (H*W f32), "sorted_idx" (P u32), "cov3D" (P x 6 f32),

@@ -39,4 +39,4 @@ def golden():
     return out
 
 
-GOLDEN_NAMES = ["tiny_sh3", "tiny_ties", "human_m13", "precomp", "cull_edges"]
+GOLDEN_NAMES = ["tiny_sh3", "tiny_ties", "human_m13", "precomp", "cull_edges", "sh0_packed"]

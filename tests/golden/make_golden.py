@@ -48,6 +48,10 @@ def golden_cases():
     c = scenes.tiny_cloud(4000, seed=9, sh_degree=1, spread=2.5, scale=0.08)
     c["scales"][::7] = 0.0
     cases["cull_edges"] = dict(cloud=c, view=scenes.make_view(orbit[2], 176, 144), bg=[0.5, 0.5, 0.5])
+    # SH degree 0 read from a packed (P,1,3) array: the form gs_decode_head emits (forward.cu:30 + `+ 0.5f` only)
+    c = scenes.human_cloud(5000, scale_factor=200.0, seed=6, opacity="uniform")
+    c = dict(c, shs=c["shs"][:, :1].contiguous(), sh_degree=0)
+    cases["sh0_packed"] = dict(cloud=c, view=scenes.make_view(orbit[9], 192, 128), bg=[0.1, 0.9, 0.3])
     return cases
 
 

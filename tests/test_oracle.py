@@ -2,6 +2,7 @@
 The golden vectors were produced by the UNMODIFIED reference CUDA library on a B200 (tests/golden/make_golden.py)."""
 import math
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -195,3 +196,29 @@ def test_camera_oracle_matches_reference_camera_setup(fov):
     np.testing.assert_allclose(v.viewmatrix, g[f"view_{fov}"][3], atol=2e-6)
     np.testing.assert_allclose(v.projmatrix, g[f"proj_{fov}"][3], rtol=2e-6, atol=2e-6)
     assert (v.image_height, v.image_width, v.tanfovx) == (1024, 1024, g[f"scalars_{fov}"][0])
+
+
+def _head_case(name):
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    import make_head_golden as mh
+    cfg = dict(mh.CONFIGS[name])
+    cfg.pop("C")
+    return mh.inputs(name), cfg
+
+
+@pytest.mark.parametrize("name", ["shipped", "all_heads", "bare", "raw_normal"])
+def test_head_oracle_matches_reference_head_decode(name):
+    """oracle/head.py against the outputs of the reference's own head-decode statements (models/model_v2.py:286-375 +
+    the caller's glue), tests/golden/head_decode.npz generated by tests/golden/make_head_golden.py."""
+    from oracle import head
+    (feat, rgb, prim), cfg = _head_case(name)
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "head_decode.npz"))
+    r = head.decode_head(feat, rgb, prim, scale_factor=448, xyz_offset=512, **cfg)
+    for k in ("means3D", "rotations", "scales", "opacities", "shs"):
+        assert np.array_equal(r[k].numpy(), g[f"{name}.{k}"]), k
+    if cfg["est_normal"]:
+        assert np.array_equal(r["normals"].numpy(), g[f"{name}.normals"])
+    # the GPU flavour of the two scalar divisions stays within one ulp of the true division
+    r2 = head.decode_head(feat, rgb, prim, scale_factor=448, xyz_offset=512, cuda_scalar_division=True, **cfg)
+    for k in ("means3D", "shs"):
+        np.testing.assert_allclose(r2[k].numpy(), r[k].numpy(), rtol=2.4e-7, atol=3e-7)
