@@ -142,6 +142,23 @@ def test_live_reference_library_bit_parity():
         assert float((t.grad - b).abs().max()) <= GRAD_RTOL * (float(b.abs().max()) + 1e-12), k
 
 
+def test_differential_fuzz_against_live_reference():
+    """Random sizes, SH degrees / strides, colour and covariance sources, scale modifiers, anisotropic fields of view:
+    images and radii bit-identical to the unmodified reference kernels, gradients equal up to the order of the
+    atomic additions (tools/fuzz_vs_reference.py; skipped if oracle/_ref did not travel)."""
+    _dev()
+    from oracle.oracle import ReferenceCUDA
+    if not ReferenceCUDA.available():
+        pytest.skip("oracle/_ref/libgs_ref.so not present")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(
+        "fuzz_vs_reference", os.path.join(os.path.dirname(os.path.dirname(__file__)), "tools", "fuzz_vs_reference.py"))
+    fuzz = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(fuzz)
+    lines, bad = fuzz.run(20, seed=7)
+    assert bad == 0, "\n".join(l for l in lines if "CHECK" in l)
+
+
 def test_edge_cases_empty_and_api_quirks(golden):
     dev = _dev()
     from diff_gaussian_rasterization import GaussianRasterizer

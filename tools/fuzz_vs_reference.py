@@ -1,0 +1,86 @@
+"""Developer tool (GPU box): differential fuzzing of the drop-in module against the live reference library
+(oracle/_ref/libgs_ref.so) over random sizes, SH degrees / strides, colour and covariance sources, scale modifiers,
+anisotropic fields of view and backgrounds.  Reports, per case, whether image and radii are bit-identical and the
+relative gradient error.  Writes gpurun_out/fuzz_vs_reference.txt."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "gaussian-pcloud-render_b200"))
+import scenes  # noqa: E402
+from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer  # noqa: E402
+from oracle.oracle import ReferenceCUDA  # noqa: E402
+
+
+def run(N: int = 40, seed: int = 2024):
+    dev = torch.device("cuda:0")
+    ref = ReferenceCUDA()
+    rng = np.random.default_rng(seed)
+    orbit = scenes.orbit_c2w(12)
+    lines, bad = [], 0
+    for case in range(N):
+        P = int(rng.choice([1, 7, 100, 1500, 8000, 30000]))
+        W, H = int(rng.integers(8, 700)), int(rng.integers(8, 500))
+        D = int(rng.integers(0, 4))
+        M = (D + 1) ** 2 + int(rng.choice([0, 0, 1, 5]))
+        use_sh = bool(rng.random() < 0.7)
+        use_cov = bool(rng.random() < 0.25)
+        mod = float(rng.choice([1.0, 1.0, 0.5, 1.7]))
+        cl = scenes.tiny_cloud(P, seed=1000 + case, sh_degree=D, M=M, spread=float(rng.choice([0.4, 0.8, 2.0])),
+                               scale=float(rng.choice([0.01, 0.05, 0.2])))
+        v = scenes.make_view(orbit[int(rng.integers(0, 12))], W, H, fov_deg=float(rng.choice([30.0, 45.0, 60.0])))
+        tanx, tany = v.tanfovx, v.tanfovy * float(rng.choice([1.0, 0.75]))
+        t = lambda a: torch.as_tensor(np.asarray(a, np.float32)).to(dev)
+        bg = t(rng.random(3))
+        means, opac = cl["means3D"].to(dev), cl["opacities"].to(dev)
+        kw = {}
+        if use_sh:
+            kw["shs"] = cl["shs"].to(dev)
+        else:
+            kw["colors_precomp"] = t(rng.random((P, 3)))
+        if use_cov:
+            A = rng.standard_normal((P, 3, 3)).astype(np.float32) * 0.05
+            S = A @ A.transpose(0, 2, 1)
+            kw["cov3D_precomp"] = t(np.stack([S[:, 0, 0], S[:, 0, 1], S[:, 0, 2], S[:, 1, 1], S[:, 1, 2], S[:, 2, 2]], 1))
+        else:
+            kw["scales"], kw["rotations"] = cl["scales"].to(dev), cl["rotations"].to(dev)
+        leaves = {k: x.clone().requires_grad_(True) for k, x in dict(means3D=means, opacities=opac, **kw).items()}
+        rs = GaussianRasterizationSettings(H, W, tanx, tany, bg, mod, t(v.viewmatrix), t(v.projmatrix), D, t(v.campos),
+                                           False, False)
+        m2 = torch.zeros_like(leaves["means3D"], requires_grad=True)
+        color, radii = GaussianRasterizer(rs)(leaves["means3D"], m2, leaves["opacities"], shs=leaves.get("shs"),
+                                              colors_precomp=leaves.get("colors_precomp"), scales=leaves.get("scales"),
+                                              rotations=leaves.get("rotations"), cov3D_precomp=leaves.get("cov3D_precomp"))
+        rc, rr, R = ref.forward(means3D=means, opacities=opac, W=W, H=H, viewmatrix=t(v.viewmatrix),
+                                projmatrix=t(v.projmatrix), campos=t(v.campos), bg=bg, tanfovx=tanx, tanfovy=tany,
+                                sh_degree=D, scale_modifier=mod, **kw)
+        wgt = torch.from_numpy(np.random.default_rng(case).standard_normal((3, H, W)).astype(np.float32)).to(dev)
+        (color * wgt).sum().backward()
+        g = ref.backward(wgt)
+        names = dict(means3D="dL_dmeans3D", opacities="dL_dopacity", shs="dL_dsh", colors_precomp="dL_dcolors",
+                     scales="dL_dscales", rotations="dL_drotations", cov3D_precomp="dL_dcov3D")
+        gerr = 0.0
+        for k, x in leaves.items():
+            b = g[names[k]].reshape(x.grad.shape)
+            gerr = max(gerr, float((x.grad - b).abs().max() / (b.abs().max() + 1e-30)))
+        gerr = max(gerr, float((m2.grad - g["dL_dmeans2D"]).abs().max() / (g["dL_dmeans2D"].abs().max() + 1e-30)))
+        same_img, same_rad = bool(torch.equal(color.detach(), rc)), bool(torch.equal(radii, rr))
+        ok = same_img and same_rad and gerr < 1e-4
+        bad += not ok
+        lines.append(f"{case:3d} P={P:6d} {W}x{H} D={D} M={M} sh={int(use_sh)} cov={int(use_cov)} mod={mod} R={R:8d} "
+                     f"img_equal={same_img} maxdiff={float((color.detach() - rc).abs().max()):.2e} radii_equal={same_rad} "
+                     f"grad_rel={gerr:.1e} {'' if ok else '<-- CHECK'}")
+    lines.append(f"{N} cases, {bad} to check")
+
+    return lines, bad
+
+
+if __name__ == "__main__":
+    lines, bad = run(int(sys.argv[1]) if len(sys.argv) > 1 else 40)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    open(os.path.join(ROOT, "gpurun_out", "fuzz_vs_reference.txt"), "w").write("\n".join(lines) + "\n")
+    print("\n".join(lines))
