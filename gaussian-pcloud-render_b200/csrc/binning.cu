@@ -268,6 +268,17 @@ __global__ void __launch_bounds__(SORT_THREADS, SORT_MIN_BLOCKS) depth_pass_kern
     const uint32_t base = chunk * GS_SORT_CHUNK + warp * (GS_SORT_CHUNK / SORT_WARPS);
     const uint32_t tl_slot = (uint32_t)(shift / 8) * 1024u + chunk;
     BIN_MARK(tl_slot, 0);
+    // A digit shared by ALL keys makes the pass the identity permutation (the top byte of the depths of an object
+    // that lies within one binade of camera distance, e.g. every frame of C1-C3): copy the chunk, skip ranking and
+    // chain.  The global histogram is complete before this kernel starts, so every CTA takes the same branch.
+    if (hist[(key_in[0] >> shift) & 255u] == P) {
+        const uint32_t beg = chunk * GS_SORT_CHUNK, n = min((uint32_t)GS_SORT_CHUNK, P - beg);
+        for (uint32_t t = tid; t < n; t += SORT_THREADS) {
+            key_out[beg + t] = key_in[beg + t];
+            idx_out[beg + t] = first_pass ? beg + t : idx_in[beg + t];
+        }
+        return;
+    }
 
     uint32_t k[SORT_ROUNDS], v[SORT_ROUNDS];
     uint16_t rk[SORT_ROUNDS];
