@@ -206,10 +206,10 @@ __global__ void __launch_bounds__(1024) depth_hist_kernel(const uint32_t* __rest
 #pragma unroll
                 for (int p = 0; p < 4; p++) {
                     const uint32_t d = (k[u] >> (8 * p)) & 255u;
-                    if (p < 2) {
-                        atomicAdd(&s[p][d], 1u);  // low digits: nearly uniform, few conflicts
-                    } else {                      // high digits: heavily repeated, aggregate within the warp first
-                        const unsigned m = match_bits<8>(act, d);
+                    if (p < 3) {
+                        atomicAdd(&s[p][d], 1u);  // mantissa digits: spread out, few conflicts
+                    } else {  // top byte (sign + exponent): a handful of distinct values, aggregate within the warp
+                        const unsigned m = __match_any_sync(act, d);
                         if (lane == __ffs(m) - 1) atomicAdd(&s[p][d], (uint32_t)__popc(m));
                     }
                 }
@@ -763,6 +763,9 @@ extern "C" int gs_debug_bin_timeline(void* dev_buf) {
 }
 #endif
 
+#ifndef HIST_CTAS
+#define HIST_CTAS 64
+#endif
 #define GS_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return e_; } while (0)
 
 cudaError_t gs_launch_depth_sort(const GsFrame& f, const GsGeom& g) {
@@ -773,7 +776,7 @@ cudaError_t gs_launch_depth_sort(const GsFrame& f, const GsGeom& g) {
         attr_set = true;
     }
     const unsigned chunks = (unsigned)g.sort_chunks;
-    depth_hist_kernel<<<(unsigned)min((size_t)64, gs_div_up(P, 8192)), 1024, 0, f.stream>>>(g.key[0], P, g.dhist);
+    depth_hist_kernel<<<(unsigned)min((size_t)HIST_CTAS, gs_div_up(P, 4096)), 1024, 0, f.stream>>>(g.key[0], P, g.dhist);
     gs_note_launch();
     GS_TRY(cudaGetLastError());
     int side = 0;

@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 for v in "$@"; do
   lib=$PWD/gaussian-pcloud-render_b200/libgsplat_b200${v:+_$v}.so
   [ "$v" = "base" ] && lib=$PWD/gaussian-pcloud-render_b200/libgsplat_b200.so
-  ( GSPLAT_B200_LIB=$lib timeout 300 python bench.py --no-cpu-baseline --steps 240 2>> gpurun_out/bench.err | tail -1 ) > gpurun_out/bench_v_$v.json
+  ( GSPLAT_B200_LIB=$lib timeout 300 python bench.py --no-cpu-baseline --steps 600 2>> gpurun_out/bench.err | tail -1 ) > gpurun_out/bench_v_$v.json
   python - <<PY
 import json
 d=json.load(open("gpurun_out/bench_v_$v.json"))
