@@ -252,6 +252,11 @@ __global__ void __launch_bounds__(BF_WARPS * 32, (K == 0) ? BF_PX2_OCC : 2) blen
         const uint32_t total = range.y - range.x;
         const uint32_t* __restrict__ lst = list + range.x;
 
+#ifdef GS_TIMELINE
+        const unsigned long long tl_t0 = gtime();
+        unsigned tl_batches = 0, tl_hits = 0;
+        long long tl_wait = 0, tl_loop = 0;
+#endif
         bool doneA = !insA, doneB = !insB;
         f2 T2 = bc(1.0f);
         float c0A = 0.f, c0B = 0.f, c1A = 0.f, c1B = 0.f, c2A = 0.f, c2B = 0.f;
@@ -293,8 +298,15 @@ __global__ void __launch_bounds__(BF_WARPS * 32, (K == 0) ? BF_PX2_OCC : 2) blen
                 fx0 = (float)(bx0 + __ffs(cols) - 1); fx1 = (float)(bx0 + 31 - __clz(cols));
                 fy0 = (float)(by0 + __ffs(rows) - 1); fy1 = (float)(by0 + 31 - __clz(rows));
             }
+#ifdef GS_TIMELINE
+            tl_batches++;
+            const long long tl_c0 = clock64();
+#endif
             cp_async_wait<1>();
             __syncwarp();
+#ifdef GS_TIMELINE
+            tl_wait += clock64() - tl_c0;
+#endif
             {
                 int nst = stage + 2; if (nst >= BF_STAGES) nst -= BF_STAGES;
                 if (base + 64 + lane < total) {
@@ -319,6 +331,10 @@ __global__ void __launch_bounds__(BF_WARPS * 32, (K == 0) ? BF_PX2_OCC : 2) blen
                 hit = !(bound < b.z);
             }
             unsigned mask = __ballot_sync(GS_FULL, hit);
+#ifdef GS_TIMELINE
+            tl_hits += __popc(mask);
+            const long long tl_c1 = clock64();
+#endif
             while (mask) {
                 const int j = __ffs(mask) - 1;
                 mask &= mask - 1;
@@ -369,9 +385,21 @@ __global__ void __launch_bounds__(BF_WARPS * 32, (K == 0) ? BF_PX2_OCC : 2) blen
                 if (okB && !stopB) lastB = base + (uint32_t)j + 1u;
                 if (__all_sync(GS_FULL, doneA && doneB)) break;
             }
+#ifdef GS_TIMELINE
+            tl_loop += clock64() - tl_c1;
+#endif
             if (__all_sync(GS_FULL, doneA && doneB)) break;
         }
         cp_async_wait<0>();
+#ifdef GS_TIMELINE
+        if (g_timeline && lane == 0) {
+            unsigned long long* tl = g_timeline + 6ull * unit;
+            tl[0] = tl_t0; tl[1] = gtime();
+            tl[2] = ((unsigned long long)smid() << 32) | total;
+            tl[3] = ((unsigned long long)tl_batches << 32) | tl_hits;
+            tl[4] = (unsigned long long)tl_wait; tl[5] = (unsigned long long)tl_loop;
+        }
+#endif
         const f2 C0 = pk(c0A, c0B), C1 = pk(c1A, c1B), C2 = pk(c2A, c2B);
 
         const float TA = lo(T2), TB = hi(T2);
