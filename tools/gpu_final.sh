@@ -13,3 +13,8 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 4
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:blend_forward -s 2 -c 1 -f \
     -o gpurun_out/prof_blend_fwd python tools/profile_frame.py --frames 4 > gpurun_out/ncu_blend.log 2>&1
 cat gpurun_out/pytest_gpu.log gpurun_out/smoke.log; cut -c1-600 gpurun_out/bench_b200.json; echo; cut -c1-300 gpurun_out/bench_reference.json
+# side measurements quoted in DESIGN.md section 5
+( timeout 300 python tools/bench_head.py 2>&1 | tail -1 ) > gpurun_out/bench_head.log
+( timeout 300 python tools/bench_supersample.py 2>&1 | tail -1 ) > gpurun_out/bench_supersample.log
+( timeout 300 python tools/bench_backward.py uniform 2>&1 | tail -1 ) > gpurun_out/bench_backward.log
+( timeout 300 python tools/bench_passes.py 2>&1 | tail -1 ) > gpurun_out/bench_passes.log
