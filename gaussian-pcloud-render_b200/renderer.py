@@ -171,6 +171,39 @@ class ViewBatch:
         return (row[0:16], row[16:32], row[32:35], self.tanfov, self.tanfov)
 
 
+def render_passes(fr: "FrameRenderer", views: "ViewBatch", normals: Optional[torch.Tensor] = None) -> dict:
+    """The four raster passes of the reference caller's `render()` for every view of a batch
+    (simple_raw_render.py:411-522): world position (`xyz_w`, colours = the Gaussian centres), RGB from the SH
+    coefficients (`rgb`), hit map (`hitmap`, colours = 1) and -- if `normals` (P,3) is given -- the camera-facing
+    normal map (`normal`).  One preprocess / sort / binning and ONE list walk per view instead of four rasterizer
+    calls; with `fr.downsample == 2` the bilinear x0.5 of `_rasterize` (:281-284) happens in the blend epilogue.
+    Returns (N, h, w, 3) tensors (permuted views of (N,3,h,w) storage, as the reference returns them), bit-identical
+    to the reference call sequence.
+
+    The normal pass reproduces `normalize_camera_normal` including its quirk: the flipped normals of view j are the
+    input of view j+1 (`colors_precomp_i` is reassigned inside the view loop, :264-268)."""
+    N = len(views)
+    h, w = fr.H // fr.downsample, fr.W // fr.downsample
+    dev = fr.dev
+    names = ["rgb", "xyz_w", "hitmap"] + (["normal"] if normals is not None else [])
+    out = {n: torch.empty((N, 3, h, w), dtype=torch.float32, device=dev) for n in names}
+    ones = torch.ones_like(fr.means3D)
+    nrm = None if normals is None else normals.to(dev, torch.float32).contiguous()
+    keep = []
+    for k in range(N):
+        view = views[k]
+        extra = [(fr.means3D, out["xyz_w"][k]), (ones, out["hitmap"][k])]
+        if nrm is not None:
+            camera_dir = fr.means3D - view[2].reshape(1, 3)                      # means3D - camera origin
+            sgn = (torch.sum(camera_dir * nrm, -1, keepdim=True) > 0).float() * 2 - 1
+            nrm = nrm * (-1) * sgn
+            keep.append(nrm)  # stays alive until the stream has consumed it
+            extra.append((nrm, out["normal"][k]))
+        fr.enqueue(view, out_color=out["rgb"][k], extra_passes=extra, slot=k)
+    fr._keep_passes = keep
+    return {n: t.permute(0, 2, 3, 1) for n, t in out.items()}
+
+
 class FramePipeline:
     """Several frames in flight on separate CUDA streams, each with its own workspaces (the cloud is shared).
 

@@ -567,6 +567,48 @@ def test_packed_sh_without_zero_tail_renders_the_same_frame():
         assert torch.equal(b, theirs)
 
 
+def test_render_passes_equals_the_reference_call_sequence():
+    """renderer.render_passes (all SURVEY 8f rows together: device-built views, four passes in one list walk,
+    super-sample epilogue) against the reference caller's sequence of 4 x N drop-in rasterizer calls +
+    F.interpolate + permute (simple_raw_render.py:227-288, 411-522), including the cumulative normal flipping."""
+    dev = _dev()
+    import torch.nn.functional as F
+    from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer
+    from renderer import FrameRenderer, ViewBatch, render_passes
+    P, hw, ss, fov = 30000, 128, 2, 45.0
+    cl = scenes.human_cloud(P, scale_factor=200.0, seed=41, opacity="uniform")
+    normals = torch.nn.functional.normalize(torch.from_numpy(
+        np.random.default_rng(9).standard_normal((P, 3)).astype(np.float32)), dim=-1)
+    c2w = scenes.orbit_c2w(12)[:5]
+    vb = ViewBatch(c2w, fov, dev)
+    fr = FrameRenderer(cl, hw * ss, hw * ss, [1, 1, 1], dev, capacity=6_000_000, downsample=ss)
+    got = render_passes(fr, vb, normals=normals)
+    torch.cuda.synchronize()
+    assert all(fr.status(k)[2] == 0 for k in range(len(vb)))
+    # the reference caller's flow with the drop-in module
+    d = {k: cl[k].to(dev) for k in ("means3D", "opacities", "scales", "rotations", "shs")}
+    bg = torch.ones(3, device=dev)
+    nrm = normals.to(dev)
+    want = {k: [] for k in ("rgb", "xyz_w", "hitmap", "normal")}
+    for k in range(len(vb)):
+        vm, pm, cp, tanx, tany = vb[k]
+        rs = GaussianRasterizationSettings(hw * ss, hw * ss, tanx, tany, bg, 1.0, vm.reshape(1, 4, 4),
+                                           pm.reshape(1, 4, 4), 1, cp.reshape(1, 1, 3), False, False)
+        camera_dir = d["means3D"] - cp.reshape(1, 1, 3)
+        sgn = (torch.sum(camera_dir * nrm, -1, keepdim=True) > 0).float() * 2 - 1
+        nrm = nrm * (-1) * sgn[0]
+        for name, kw in (("xyz_w", dict(colors_precomp=d["means3D"])), ("rgb", dict(shs=d["shs"])),
+                         ("hitmap", dict(colors_precomp=torch.ones_like(d["means3D"]))),
+                         ("normal", dict(colors_precomp=nrm))):
+            img, _ = GaussianRasterizer(rs)(d["means3D"], torch.zeros_like(d["means3D"]), d["opacities"],
+                                            scales=d["scales"], rotations=d["rotations"], **kw)
+            want[name].append(img)
+    for name in want:
+        ref = F.interpolate(torch.stack(want[name], 0), size=(hw, hw), mode="bilinear", align_corners=False)
+        ref = ref.permute(0, 2, 3, 1)
+        assert got[name].shape == (len(vb), hw, hw, 3) and torch.equal(got[name], ref), name
+
+
 def test_peer_store_tile_sharding_two_gpus():
     """Tile-row shards written by the blend epilogue into every rank's symmetric-memory image (NVLink peer stores +
     one barrier) assemble the single-GPU frame bit for bit.  Needs two GPUs (skipped on the one-GPU test box;
