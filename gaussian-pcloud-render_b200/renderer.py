@@ -171,36 +171,50 @@ class ViewBatch:
         return (row[0:16], row[16:32], row[32:35], self.tanfov, self.tanfov)
 
 
-def render_passes(fr: "FrameRenderer", views: "ViewBatch", normals: Optional[torch.Tensor] = None) -> dict:
+def render_passes(fr, views: "ViewBatch", normals: Optional[torch.Tensor] = None) -> dict:
     """The four raster passes of the reference caller's `render()` for every view of a batch
     (simple_raw_render.py:411-522): world position (`xyz_w`, colours = the Gaussian centres), RGB from the SH
     coefficients (`rgb`), hit map (`hitmap`, colours = 1) and -- if `normals` (P,3) is given -- the camera-facing
     normal map (`normal`).  One preprocess / sort / binning and ONE list walk per view instead of four rasterizer
-    calls; with `fr.downsample == 2` the bilinear x0.5 of `_rasterize` (:281-284) happens in the blend epilogue.
-    Returns (N, h, w, 3) tensors (permuted views of (N,3,h,w) storage, as the reference returns them), bit-identical
-    to the reference call sequence.
+    calls; with `downsample == 2` the bilinear x0.5 of `_rasterize` (:281-284) happens in the blend epilogue.
+    `fr` is a FrameRenderer (views one after the other on the current stream) or a FramePipeline (views round-robin
+    on its lanes).  Returns (N, h, w, 3) tensors (permuted views of (N,3,h,w) storage, as the reference returns
+    them), bit-identical to the reference call sequence; valid once the current stream has caught up.
 
     The normal pass reproduces `normalize_camera_normal` including its quirk: the flipped normals of view j are the
     input of view j+1 (`colors_precomp_i` is reassigned inside the view loop, :264-268)."""
+    pipe = fr if isinstance(fr, FramePipeline) else None
+    first = pipe.lanes[0] if pipe is not None else fr
     N = len(views)
-    h, w = fr.H // fr.downsample, fr.W // fr.downsample
-    dev = fr.dev
+    h, w = first.H // first.downsample, first.W // first.downsample
+    dev = first.dev
     names = ["rgb", "xyz_w", "hitmap"] + (["normal"] if normals is not None else [])
     out = {n: torch.empty((N, 3, h, w), dtype=torch.float32, device=dev) for n in names}
-    ones = torch.ones_like(fr.means3D)
-    nrm = None if normals is None else normals.to(dev, torch.float32).contiguous()
-    keep = []
-    for k in range(N):
-        view = views[k]
-        extra = [(fr.means3D, out["xyz_w"][k]), (ones, out["hitmap"][k])]
-        if nrm is not None:
-            camera_dir = fr.means3D - view[2].reshape(1, 3)                      # means3D - camera origin
+    ones = torch.ones_like(first.means3D)
+    per_view_normals = []
+    if normals is not None:  # the flips chain from view to view: all of them first, on the current stream
+        nrm = normals.to(dev, torch.float32).contiguous()
+        for k in range(N):
+            camera_dir = first.means3D - views[k][2].reshape(1, 3)               # means3D - camera origin
             sgn = (torch.sum(camera_dir * nrm, -1, keepdim=True) > 0).float() * 2 - 1
             nrm = nrm * (-1) * sgn
-            keep.append(nrm)  # stays alive until the stream has consumed it
-            extra.append((nrm, out["normal"][k]))
-        fr.enqueue(view, out_color=out["rgb"][k], extra_passes=extra, slot=k)
-    fr._keep_passes = keep
+            per_view_normals.append(nrm)
+    if pipe is not None:
+        pipe.begin()
+    for k in range(N):
+        extra = [(first.means3D, out["xyz_w"][k]), (ones, out["hitmap"][k])]
+        if normals is not None:
+            extra.append((per_view_normals[k], out["normal"][k]))
+        if pipe is None:
+            fr.enqueue(views[k], out_color=out["rgb"][k], extra_passes=extra, slot=k)
+        else:
+            lane = pipe.count % len(pipe.lanes)
+            pipe.count += 1
+            with torch.cuda.stream(pipe.streams[lane]):
+                pipe.lanes[lane].enqueue(views[k], out_color=out["rgb"][k], extra_passes=extra, slot=k)
+    if pipe is not None:
+        pipe.end()
+    first._keep_passes = (per_view_normals, ones)  # alive until the streams have consumed them
     return {n: t.permute(0, 2, 3, 1) for n, t in out.items()}
 
 

@@ -187,7 +187,8 @@ def test_edge_cases_empty_and_api_quirks(golden):
     assert torch.equal(c1, c2)
     c1.sum().backward()
     c2.sum().backward()
-    assert torch.allclose(l1["scales"].grad, scl.grad, rtol=1e-4, atol=1e-6)
+    # two runs of the same kernels: only the order of the atomic additions differs
+    assert float((l1["scales"].grad - scl.grad).abs().max()) <= GRAD_RTOL * float(scl.grad.abs().max()) + 1e-12
 
 
 def test_prefiltered_violation_raises(golden):
@@ -446,8 +447,8 @@ def test_supersample_epilogue_backward_matches_autograd_through_interpolate():
     (half * wgt).sum().backward()
     for k in la:
         ga, gb = la[k].grad, lb[k].grad
-        assert float((ga - gb).abs().max()) <= 2e-5 * float(ga.abs().max()) + 1e-12, k
-    assert float((m2a.grad - m2b.grad).abs().max()) <= 2e-5 * float(m2a.grad.abs().max()) + 1e-12
+        assert float((ga - gb).abs().max()) <= GRAD_RTOL * float(ga.abs().max()) + 1e-12, k  # atomics order
+    assert float((m2a.grad - m2b.grad).abs().max()) <= GRAD_RTOL * float(m2a.grad.abs().max()) + 1e-12
 
 
 def test_supersample_epilogue_rejects_odd_raster():
@@ -607,6 +608,12 @@ def test_render_passes_equals_the_reference_call_sequence():
         ref = F.interpolate(torch.stack(want[name], 0), size=(hw, hw), mode="bilinear", align_corners=False)
         ref = ref.permute(0, 2, 3, 1)
         assert got[name].shape == (len(vb), hw, hw, 3) and torch.equal(got[name], ref), name
+    from renderer import FramePipeline
+    pipe = FramePipeline(cl, hw * ss, hw * ss, [1, 1, 1], dev, depth=3, capacity=6_000_000, downsample=ss)
+    piped = render_passes(pipe, vb, normals=normals)
+    torch.cuda.synchronize()
+    for name in got:
+        assert torch.equal(piped[name], got[name]), name
 
 
 def test_peer_store_tile_sharding_two_gpus():

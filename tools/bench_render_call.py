@@ -19,7 +19,7 @@ sys.path.insert(0, os.path.join(ROOT, "gaussian-pcloud-render_b200"))
 import bench  # noqa: E402
 import scenes  # noqa: E402
 from oracle.oracle import ReferenceCUDA  # noqa: E402
-from renderer import FrameRenderer, ViewBatch, render_passes  # noqa: E402
+from renderer import FramePipeline, FrameRenderer, ViewBatch, render_passes  # noqa: E402
 
 dev = torch.device("cuda:0")
 cloud, _, w = bench.make_workload("C1")
@@ -29,9 +29,12 @@ normals = F.normalize(torch.randn(P, 3, generator=torch.Generator().manual_seed(
 fr = FrameRenderer(cloud, W, H, [1.0, 1.0, 1.0], dev, capacity=12_000_000, downsample=2)
 
 
-def ours():
+pipe = FramePipeline(cloud, W, H, [1.0, 1.0, 1.0], dev, depth=4, capacity=12_000_000, downsample=2)
+
+
+def ours(target=fr):
     vb = ViewBatch(c2w, 45.0, dev)  # includes the upload of the 12 camera matrices
-    return render_passes(fr, vb, normals=normals)
+    return render_passes(target, vb, normals=normals)
 
 
 d = {k: cloud[k].to(dev) for k in ("means3D", "opacities", "scales", "rotations", "shs")}
@@ -75,7 +78,7 @@ def timeit(fn, n):
 
 
 out = {"workload": f"one render(): {P} Gaussians, 12 views x 4 passes, raster {W}x{H} -> {W // 2}x{H // 2}",
-       "this_library_ms": timeit(ours, 20)}
+       "this_library_ms": timeit(ours, 20), "this_library_4_lanes_ms": timeit(lambda: ours(pipe), 20)}
 if ref is not None:
     out["reference_flow_ms"] = timeit(theirs, 3)
     a, b = ours(), theirs(ViewBatch(c2w, 45.0, dev))
