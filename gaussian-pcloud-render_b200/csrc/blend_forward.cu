@@ -129,6 +129,12 @@ __device__ __forceinline__ float box4(float v) {
     return 0.25f * (h + __shfl_xor_sync(GS_FULL, h, 8));
 }
 
+#ifndef BF_THR_TEST
+#define BF_THR_TEST 0
+#endif
+#ifndef BF_DONE_PER_HIT
+#define BF_DONE_PER_HIT 0
+#endif
 #ifndef BF_SLOT_NUM  // fraction of the CTA slots the blend grid may occupy
 #define BF_SLOT_NUM 3
 #define BF_SLOT_DEN 5
@@ -353,8 +359,13 @@ __global__ void __launch_bounds__(BF_WARPS * 32, (K == 0) ? BF_PX2_OCC : 2) blen
                 // (a packed FP32x2 transcription of libdevice's expf was bit-identical but not faster: FP32x2
                 // instructions save issue slots, not FMA-pipe cycles)
                 float alphaA = fminf(0.99f, gb.y * expf(pA)), alphaB = fminf(0.99f, gb.y * expf(pB));
+#if BF_THR_TEST
                 bool okA = !doneA && !(pA > 0.0f) && !(pA < gb.z) && !(alphaA < 1.0f / 255.0f);
                 bool okB = !doneB && !(pB > 0.0f) && !(pB < gb.z) && !(alphaB < 1.0f / 255.0f);
+#else           // power below the record's cut-off already implies alpha < 1/255 (the cut-off has a safety margin)
+                bool okA = !doneA && !(pA > 0.0f) && !(alphaA < 1.0f / 255.0f);
+                bool okB = !doneB && !(pB > 0.0f) && !(alphaB < 1.0f / 255.0f);
+#endif
                 if (!__any_sync(GS_FULL, okA || okB)) continue;
                 alphaA = okA ? alphaA : 0.0f;  // alpha 0 leaves T and the colour exactly unchanged
                 alphaB = okB ? alphaB : 0.0f;
@@ -383,7 +394,9 @@ __global__ void __launch_bounds__(BF_WARPS * 32, (K == 0) ? BF_PX2_OCC : 2) blen
                 T2 = pk(stopA ? lo(T2) : lo(tt2), stopB ? hi(T2) : hi(tt2));
                 if (okA && !stopA) lastA = base + (uint32_t)j + 1u;
                 if (okB && !stopB) lastB = base + (uint32_t)j + 1u;
+#if BF_DONE_PER_HIT
                 if (__all_sync(GS_FULL, doneA && doneB)) break;
+#endif          // otherwise: looked at once per batch below; hits after the last live pixel fail the vote above
             }
 #ifdef GS_TIMELINE
             tl_loop += clock64() - tl_c1;
