@@ -28,6 +28,18 @@ for (P, W, H, ds) in ((6000, 200, 136, 1), (6000, 208, 144, 2), (40, 33, 17, 1))
     fr.enqueue_pass(vd, torch.empty_like(fr.color), colors_precomp=ex[0][0])
     torch.cuda.synchronize()
     print("ok", P, W, H, ds, int((radii > 0).sum()), fr.status())
+# camera set-up, head decode and the caller-level pass loop
+from diff_gaussian_rasterization import _C
+from renderer import ViewBatch, render_passes
+vb = ViewBatch(scenes.orbit_c2w(12)[:3], 45.0, dev)
+cl = scenes.human_cloud(3000, scale_factor=120.0, seed=5, opacity="uniform")
+fr = FrameRenderer(cl, 96, 64, [1, 1, 1], dev, capacity=1_000_000, downsample=2)
+out = render_passes(fr, vb, normals=torch.nn.functional.normalize(torch.randn(3000, 3), dim=-1))
+for C_, kw in ((8, {}), (26, dict(use_offset=True, use_dc_offset=True, est_normal=True, sh_ac_coeffs=3)), (0, dict(use_rotation=False, use_scale=False, use_opacity=False))):
+    hd = _C.decode_head(torch.randn(777, C_, device=dev), torch.rand(777, 3, device=dev), torch.rand(777, 3, device=dev) * 1000,
+                        scale_factor=448, xyz_offset=512, **kw)
+torch.cuda.synchronize()
+print("ok extras", out["rgb"].shape, hd["shs"].shape)
 PY
 for tool in memcheck racecheck synccheck; do
   echo "== $tool"
