@@ -616,6 +616,41 @@ def test_render_passes_equals_the_reference_call_sequence():
         assert torch.equal(piped[name], got[name]), name
 
 
+def test_head_to_image_chain_equals_the_reference_flow():
+    """INTEGRATION.md section 4 end to end: head features -> gs_decode_head -> resident renderer (packed SH, degree 0)
+    gives the image of the reference's flow (torch head expressions on the GPU, SH padded to 13 coefficients,
+    degree 1, drop-in rasterizer), bit for bit."""
+    dev = _dev()
+    from diff_gaussian_rasterization import _C
+    from oracle import head
+    from renderer import FrameRenderer, ViewBatch
+    P, W, H = 40000, 400, 304
+    rng = np.random.default_rng(77)
+    base = scenes.human_cloud(P, scale_factor=256.0, seed=3)
+    prim = torch.round(base["means3D"] * 256.0 + 512.0)                      # voxel coordinates, as the decoder emits
+    feat = torch.from_numpy((0.15 * rng.standard_normal((P, 8))).astype(np.float32))
+    feat[:, 7] = torch.from_numpy(rng.random(P).astype(np.float32))          # opacity column
+    rgb = torch.from_numpy(rng.random((P, 3)).astype(np.float32))
+    g = _C.decode_head(feat.to(dev), rgb.to(dev), prim.to(dev), scale_factor=256, xyz_offset=512)
+    with torch.device(dev):                                                  # the reference's expressions, on the GPU
+        r = head.decode_head(feat.to(dev), rgb.to(dev), prim.to(dev), scale_factor=256, xyz_offset=512)
+    assert r["shs"].shape == (P, 13, 3) and g["shs"].shape == (P, 1, 3) and g["sh_degree"] == 0
+    vb = ViewBatch(scenes.orbit_c2w(12)[3:4], 45.0, dev)
+    fr = FrameRenderer(dict(means3D=g["means3D"], opacities=g["opacities"], scales=g["scales"],
+                            rotations=g["rotations"], shs=g["shs"], sh_degree=g["sh_degree"]), W, H, [1, 1, 1], dev,
+                       capacity=8_000_000)
+    img = fr.enqueue(vb[0]).clone()
+    torch.cuda.synchronize()
+    assert fr.status()[2] == 0
+    vm, pm, cp, tanx, tany = vb[0]
+    kw = dict(means3D=r["means3D"], opacities=r["opacities"], W=W, H=H, viewmatrix=vm.cpu().numpy(),
+              projmatrix=pm.cpu().numpy(), campos=cp.cpu().numpy(), bg=np.ones(3, np.float32), tanfovx=tanx, tanfovy=tany,
+              sh_degree=1, shs=r["shs"], scales=r["scales"], rotations=r["rotations"])
+    want, radii, _, _ = _render(kw, dev)
+    assert torch.equal(img, want) and torch.equal(fr.radii, radii)
+    assert int((radii > 0).sum()) > P // 2
+
+
 def test_peer_store_tile_sharding_two_gpus():
     """Tile-row shards written by the blend epilogue into every rank's symmetric-memory image (NVLink peer stores +
     one barrier) assemble the single-GPU frame bit for bit.  Needs two GPUs (skipped on the one-GPU test box;
