@@ -33,18 +33,24 @@ def test_library_exports_every_declared_symbol():
 def test_ctypes_structs_match_c_layout():
     from diff_gaussian_rasterization import _C
     fields = [f for f, _ in _C.GsScene._fields_]
+    hfields = [f for f, _ in _C.GsHeadLayout._fields_]
     prog = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', "int main(void){",
             'printf("%zu %zu %zu\\n", sizeof(GsScene), sizeof(GsBuffer), sizeof(GsStatus));']
     prog += [f'printf("%zu\\n", offsetof(GsScene, {f}));' for f in fields]
+    prog += ['printf("%zu %d\\n", sizeof(GsHeadLayout), GS_VIEW_STRIDE);']
+    prog += [f'printf("%zu\\n", offsetof(GsHeadLayout, {f}));' for f in hfields]
     prog += ["return 0;}"]
     with tempfile.TemporaryDirectory() as d:
         src, exe = os.path.join(d, "p.c"), os.path.join(d, "p")
         open(src, "w").write("\n".join(prog))
         subprocess.run(["/usr/bin/gcc", "-std=c11", "-o", exe, src], check=True)
         out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout.split()
-    sizes, offs = [int(x) for x in out[:3]], [int(x) for x in out[3:]]
+    sizes, offs = [int(x) for x in out[:3]], [int(x) for x in out[3:3 + len(fields)]]
     assert sizes == [C.sizeof(_C.GsScene), C.sizeof(_C.GsBuffer), C.sizeof(_C.GsStatus)]
     assert offs == [getattr(_C.GsScene, f).offset for f in fields]
+    rest = [int(x) for x in out[3 + len(fields):]]
+    assert rest[:2] == [C.sizeof(_C.GsHeadLayout), _C.GS_VIEW_STRIDE]
+    assert rest[2:] == [getattr(_C.GsHeadLayout, f).offset for f in hfields]
 
 
 def test_argument_errors_without_gpu():

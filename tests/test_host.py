@@ -118,3 +118,21 @@ def test_view_parallel_sharding_world2_gloo():
         p.join(timeout=60)
     assert res[0][1] == [0, 2, 4, 6, 8, 10, 12] and res[1][1] == [1, 3, 5, 7, 9, 11]
     assert res[0][2] == [1] * 13 and res[1][2] == [1] * 13
+
+
+def test_projection_entries_match_the_camera_oracle():
+    """The four scalars the binding hands to gs_make_views are the non-trivial entries of getProjectionMatrix
+    (simple_raw_render.py:50-69) as restated in oracle/camera.py; the struct mirrors of the new entry points exist."""
+    import ctypes as C
+    import math
+
+    import numpy as np
+    from diff_gaussian_rasterization import _C
+    from oracle import camera
+    for fx, fy in ((45.0, 45.0), (40.0, 40.0), (60.0, 35.0)):
+        P = camera.projection_matrix(0.01, 100, np.pi * fx / 180, np.pi * fy / 180)
+        got = np.array(_C.projection_entries(fx, fy), np.float64).astype(np.float32)
+        assert np.array_equal(got, np.array([P[0, 0], P[1, 1], P[2, 2], P[2, 3]], np.float32))
+        assert P[3, 2] == 1.0 and P[0, 2] == 0.0 and P[1, 2] == 0.0
+    assert _C.GS_VIEW_STRIDE == 48 and C.sizeof(_C.GsHeadLayout) == 13 * 4
+    assert math.isclose(_C.projection_entries(90.0, 90.0)[0], 1.0, rel_tol=1e-12)
