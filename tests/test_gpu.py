@@ -451,6 +451,33 @@ def test_supersample_epilogue_backward_matches_autograd_through_interpolate():
     assert float((m2a.grad - m2b.grad).abs().max()) <= GRAD_RTOL * float(m2a.grad.abs().max()) + 1e-12
 
 
+@pytest.mark.parametrize("W,H", [(64, 48), (330, 190), (34, 18)])
+def test_supersample_epilogue_on_an_empty_frame(W, H):
+    """Every Gaussian culled (behind the camera): all tiles take the fill path, the half-resolution image is the
+    background everywhere -- including the partial tiles at the right / bottom edge -- and nothing is written outside."""
+    dev = _dev()
+    from diff_gaussian_rasterization import GaussianRasterizer
+    cl = scenes.tiny_cloud(50, seed=3, sh_degree=1)
+    v = scenes.make_view(scenes.orbit_c2w(12)[0], W, H)
+    kw = dict(means3D=cl["means3D"] + torch.from_numpy(np.asarray(v.campos, np.float32)) * 3.0, opacities=cl["opacities"],
+              W=W, H=H, viewmatrix=v.viewmatrix, projmatrix=v.projmatrix, campos=v.campos,
+              bg=np.array([0.25, 0.5, 0.75], np.float32), tanfovx=v.tanfovx, tanfovy=v.tanfovy, sh_degree=1,
+              shs=cl["shs"], scales=cl["scales"], rotations=cl["rotations"])
+    rs = _settings(kw, dev)
+    t = lambda k: torch.as_tensor(kw[k]).to(dev).float()
+    guard = torch.full((3 * (H // 2) * (W // 2) + 64,), -7.0, device=dev)
+    from diff_gaussian_rasterization import _C
+    out = guard[:3 * (H // 2) * (W // 2)].view(3, H // 2, W // 2)
+    n, color, radii, *_ = _C.rasterize_gaussians(rs.bg, t("means3D"), torch.Tensor([]), t("opacities"), t("scales"),
+                                                t("rotations"), 1.0, torch.Tensor([]), rs.viewmatrix, rs.projmatrix,
+                                                rs.tanfovx, rs.tanfovy, H, W, t("shs"), 1, rs.campos, False, False,
+                                                out_color=out, downsample=2)
+    torch.cuda.synchronize()
+    assert n == 0 and int((radii > 0).sum()) == 0
+    want = torch.tensor([0.25, 0.5, 0.75], device=dev).view(3, 1, 1).expand(3, H // 2, W // 2)
+    assert torch.equal(color, want) and bool((guard[3 * (H // 2) * (W // 2):] == -7.0).all())
+
+
 def test_supersample_epilogue_rejects_odd_raster():
     dev = _dev()
     from diff_gaussian_rasterization import GaussianRasterizer
