@@ -121,12 +121,37 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
+def bind_host_to_gpu_numa(cuda_index):
+    """Multi-GPU runs: keep this rank's host threads -- and with them the first-touch placement of its pinned
+    buffers -- on the CPUs NVML reports as local to its GPU, so the per-step uploads of the e2e measurement do not
+    cross the socket interconnect.  Best effort: any failure leaves the affinity as it is."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        p = torch.cuda.get_device_properties(cuda_index)
+        try:
+            bus = "%08x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+            h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(cuda_index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if len(cpus) >= 4:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return 0
+
+
 def dist_setup(n):
     if n <= 1:
         return 0, 1
     import torch.distributed as dist
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
+    bind_host_to_gpu_numa(torch.cuda.current_device())
     dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
     return rank, world
 
