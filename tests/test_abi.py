@@ -102,6 +102,16 @@ def test_no_cpu_fallback():
         GaussianRasterizer(rs)(x, x, torch.ones(4, 1), colors_precomp=x, scales=x, rotations=torch.zeros(4, 4))
     with pytest.raises(RuntimeError, match="no CPU path"):
         GaussianRasterizer(rs).markVisible(x)
+    # the widened entry points refuse host tensors as well
+    with pytest.raises((RuntimeError, ValueError)):
+        pkg_C = __import__("diff_gaussian_rasterization")._C
+        pkg_C.make_views(torch.eye(4)[None], 45.0, 45.0)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        __import__("diff_gaussian_rasterization")._C.decode_head(torch.zeros(4, 8), torch.zeros(4, 3), torch.zeros(4, 3),
+                                                              scale_factor=256, xyz_offset=512)
     import diff_gaussian_rasterization as pkg
-    src = open(pkg.__file__).read() + open(pkg._C.__file__).read()
+    import renderer
+    src = open(pkg.__file__).read() + open(pkg._C.__file__).read() + open(renderer.__file__).read()
     assert "oracle" not in src.replace("no CPU or eager fallback", "")
+    import sharding
+    assert "oracle" not in open(sharding.__file__).read()
