@@ -770,11 +770,11 @@ extern "C" int gs_debug_bin_timeline(void* dev_buf) {
 
 cudaError_t gs_launch_depth_sort(const GsFrame& f, const GsGeom& g) {
     const uint32_t P = (uint32_t)f.s.P;
-    static bool attr_set = false;
-    if (!attr_set) {
-        GS_TRY(cudaFuncSetAttribute(depth_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_SMEM));
-        attr_set = true;
-    }
+    static GsPerDevice per_dev;
+    const int* dv = nullptr;
+    GS_TRY(per_dev.get(&dv, [](int, int*) {
+        return cudaFuncSetAttribute(depth_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_SMEM);
+    }));
     const unsigned chunks = (unsigned)g.sort_chunks;
     depth_hist_kernel<<<(unsigned)min((size_t)HIST_CTAS, gs_div_up(P, 4096)), 1024, 0, f.stream>>>(g.key[0], P, g.dhist);
     gs_note_launch();
@@ -798,19 +798,21 @@ cudaError_t gs_launch_depth_sort(const GsFrame& f, const GsGeom& g) {
 #ifndef PART_GRID_MULT
 #define PART_GRID_MULT 4
 #endif
-static int g_part_grid = 0;
+static GsPerDevice g_part_dev;  // value[0] = grid size of the partition passes on this device
 
 cudaError_t gs_launch_tile_lists(const GsFrame& f, const GsGeom& g, const GsBinning& b, size_t Rcap, size_t RowCap,
                                  const GsImage& im) {
     const uint32_t P = (uint32_t)f.s.P;
-    if (g_part_grid == 0) {
-        int dev = 0, sms = 0;
-        GS_TRY(cudaGetDevice(&dev));
+    const int* dv = nullptr;
+    GS_TRY(g_part_dev.get(&dv, [](int dev, int* v) {
+        int sms = 0;
         GS_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         GS_TRY(cudaFuncSetAttribute(range_partition_kernel<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PART_SMEM(256)));
         GS_TRY(cudaFuncSetAttribute(range_partition_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, PART_SMEM(256)));
-        g_part_grid = sms * PART_GRID_MULT;
-    }
+        v[0] = sms * PART_GRID_MULT;
+        return cudaSuccess;
+    }));
+    const int g_part_grid = dv[0];
     const unsigned grid1 = (unsigned)min((size_t)g_part_grid, g.row_chunks);
     const unsigned grid2 = (unsigned)min((size_t)g_part_grid, b.col_chunks);
     const unsigned long long rowcap = RowCap;

@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(BB_WARPS * 32, 3) blend_backward_kernel(
     }
 }
 
-int g_bwd_grid = 0;
+GsPerDevice g_bwd_dev;  // value[0] = resident CTAs of the kernel on this device
 
 }  // namespace
 
@@ -278,18 +278,20 @@ cudaError_t gs_launch_blend_backward(const GsFrame& f, const GsGeom& g, const Gs
                                      float* dL_dcolor) {
     const uint32_t num_tiles = (uint32_t)f.gx * (uint32_t)(f.row1 - f.row0);
     if (num_tiles == 0) return cudaSuccess;
-    if (g_bwd_grid == 0) {
-        int dev = 0, sms = 0, per_sm = 0;
-        cudaError_t e = cudaGetDevice(&dev);
-        if (e != cudaSuccess) return e;
-        e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int* dv = nullptr;
+    cudaError_t e = g_bwd_dev.get(&dv, [](int dev, int* v) {
+        int sms = 0, per_sm = 0;
+        cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (e != cudaSuccess) return e;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, blend_backward_kernel, BB_WARPS * 32, 0);
         if (e != cudaSuccess) return e;
-        g_bwd_grid = sms * (per_sm > 0 ? per_sm : 1);
-    }
+        v[0] = sms * (per_sm > 0 ? per_sm : 1);
+        return cudaSuccess;
+    });
+    if (e != cudaSuccess) return e;
+    const int g_bwd_grid = dv[0];
     unsigned int* queue = &g.hdr->tickets[10];  // the forward pass left the header in place; only the queue restarts
-    cudaError_t e = cudaMemsetAsync(queue, 0, sizeof(unsigned int), f.stream);
+    e = cudaMemsetAsync(queue, 0, sizeof(unsigned int), f.stream);
     if (e != cudaSuccess) return e;
     const unsigned grid = (unsigned)min((uint32_t)g_bwd_grid, num_tiles);
     blend_backward_kernel<<<grid, BB_WARPS * 32, 0, f.stream>>>(im.ranges, im.order, b.list, g.rec, f.s.width, f.s.height,

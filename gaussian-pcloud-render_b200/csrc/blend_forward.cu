@@ -55,7 +55,8 @@ __device__ __forceinline__ unsigned smid() {
 // Upper bound of power(d) = -0.5 (A dx^2 + C dy^2) - B dx dy over the box [xlo,xhi] x [ylo,yhi] of d = mean - pixel,
 // plus a rounding allowance.  Exact box maximum of a concave quadratic: 0 if the box contains the origin, otherwise
 // the best of the 1-D maxima on the (at most two) box edges that face the origin.  nBA = -B/A, nBC = -B/C
-// (NaN when the conic is not positive definite -> the comparison in the caller fails -> instance is kept).
+// (only meaningful for a positive definite conic; preprocess stores the cut-off -inf otherwise, so the caller's
+// `bound < cut-off` is false and the instance is kept whatever this function returns).
 __device__ __forceinline__ float box_max_power(float A, float B, float C, float nBA, float nBC, float xlo, float xhi,
                                                float ylo, float yhi) {
     const bool in_x = (xlo <= 0.f) && (xhi >= 0.f);
@@ -466,24 +467,28 @@ __global__ void __launch_bounds__(BF_WARPS * 32, (K == 0) ? BF_PX2_OCC : 2) blen
     }
 }
 
-int g_blend_grid[4] = {0, 0, 0, 0};
+GsPerDevice g_blend_dev[4];  // per extra-pass count K: value[0] = resident CTAs of the kernel on this device
 
 template <int K>
 cudaError_t launch_blend(const GsFrame& f, const GsGeom& g, const GsBinning& b, const GsImage& im, float* out_color,
                          uint32_t num_tiles) {
     const size_t smem = sizeof(BfStage<K>) * BF_STAGES * BF_WARPS;
-    if (g_blend_grid[K] == 0) {
-        int dev = 0, sms = 0, per_sm = 0;
-        cudaError_t e = cudaGetDevice(&dev);
+    const int* dv = nullptr;
+    {
+        cudaError_t e = g_blend_dev[K].get(&dv, [smem](int dev, int* v) {
+            int sms = 0, per_sm = 0;
+            cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            if (e != cudaSuccess) return e;
+            e = cudaFuncSetAttribute(blend_forward_px2_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, blend_forward_px2_kernel<K>, BF_WARPS * 32, smem);
+            if (e != cudaSuccess) return e;
+            v[0] = sms * (per_sm > 0 ? per_sm : 1);
+            return cudaSuccess;
+        });
         if (e != cudaSuccess) return e;
-        e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(blend_forward_px2_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, blend_forward_px2_kernel<K>, BF_WARPS * 32, smem);
-        if (e != cudaSuccess) return e;
-        g_blend_grid[K] = sms * (per_sm > 0 ? per_sm : 1);
     }
+    const int resident = dv[0];
     BfTargets tg;
     tg.n = f.s.num_peers > 0 ? f.s.num_peers : 1;
     tg.ds = f.s.downsample == 2 ? 1 : 0;
@@ -493,7 +498,7 @@ cudaError_t launch_blend(const GsFrame& f, const GsGeom& g, const GsBinning& b, 
     for (int k = 0; k < 3; k++) ex.out[k] = f.s.extra_out[k];
     // grid x 8 warps x quota covers the upper bound of units (4 per tile); quota >= 16, grid <= 60 % of the slots
     const uint32_t units_max = num_tiles * 4u;
-    const uint32_t slots = (uint32_t)((g_blend_grid[K] * BF_SLOT_NUM + BF_SLOT_DEN - 1) / BF_SLOT_DEN);
+    const uint32_t slots = (uint32_t)((resident * BF_SLOT_NUM + BF_SLOT_DEN - 1) / BF_SLOT_DEN);
     uint32_t quota = (units_max + BF_WARPS * slots - 1) / (BF_WARPS * slots);
     if (quota < 16u) quota = 16u;
     const unsigned grid = (units_max + BF_WARPS * quota - 1) / (BF_WARPS * quota);

@@ -169,6 +169,39 @@ struct GsImage {
     }
 };
 
+// ---- one-time, PER-DEVICE launcher set-up -----------------------------------------------------------------------
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize), occupancy and the SM count are properties of a (kernel, device)
+// pair, so every launcher keeps its derived values per device ordinal; the first launch on a device runs `init`
+// under a mutex, later launches read the cached values (one acquire load).  Safe for a process that renders on
+// several GPUs and for several host threads.
+#include <atomic>
+#include <mutex>
+#define GS_MAX_DEVICES 64
+struct GsPerDevice {
+    std::mutex mu;
+    std::atomic<bool> ready[GS_MAX_DEVICES];
+    int value[GS_MAX_DEVICES][4];
+    GsPerDevice() { for (auto& r : ready) r.store(false); }
+    // init(device, int value[4]) -> cudaError_t; on success *out points at this device's values
+    template <typename F>
+    cudaError_t get(const int** out, F init) {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        if (dev < 0 || dev >= GS_MAX_DEVICES) return cudaErrorInvalidDevice;
+        if (!ready[dev].load(std::memory_order_acquire)) {
+            std::lock_guard<std::mutex> lk(mu);
+            if (!ready[dev].load(std::memory_order_relaxed)) {
+                e = init(dev, value[dev]);
+                if (e != cudaSuccess) return e;
+                ready[dev].store(true, std::memory_order_release);
+            }
+        }
+        *out = value[dev];
+        return cudaSuccess;
+    }
+};
+
 // launch bookkeeping (gs_launch_count) and error text
 void gs_note_launch();
 void gs_set_error(const char* what, cudaError_t e);

@@ -182,9 +182,11 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreArgs a) {
             // may skip the exponential with no change to the result (alpha < 1/255 is skipped anyway).
             const float thr = -logf(255.0f * op) - 1.0e-3f;
             // op <= 0: alpha <= 0, always skipped (thr 0 skips every power < 0); NaN opacity: never skip.
-            const float thr_rec = (op > 0.f) ? thr : ((op <= 0.f) ? 0.0f : -INFINITY);
-            // -B/A and -B/C for the blend kernels' box-maximum cull; NaN (= never cull) unless the conic is PD
+            // -B/A and -B/C for the blend kernels' box-maximum cull.  The box maximum is only valid for a positive
+            // definite conic (concave exponent): anything else (det < 0 from fp32 cancellation on huge thin splats, a
+            // non-PSD cov3D_precomp) gets the cut-off -inf, i.e. is never culled and always evaluated per pixel.
             const bool pd = det > 0.f && conic.x > 0.f && conic.z > 0.f;
+            const float thr_rec = !pd ? -INFINITY : ((op > 0.f) ? thr : ((op <= 0.f) ? 0.0f : -INFINITY));
             const float nBA = pd ? -conic.y / conic.x : __int_as_float(0x7fc00000);
             const float nBC = pd ? -conic.y / conic.z : __int_as_float(0x7fc00000);
             GsRec r;
@@ -401,12 +403,13 @@ cudaError_t gs_launch_preprocess(const GsFrame& f, const GsGeom& g, const GsImag
     const bool staged = sh_dense && s.P >= 256 && s.scales && s.rotations && s.shs && !s.cov3D_precomp && !s.colors_precomp &&
                         stage_bytes <= 100 * 1024 && al16(s.means3D) && al16(s.scales) && al16(s.rotations) &&
                         al16(s.opacities) && al16(s.shs);
-    static bool attr_set = false;
-    if (staged && !attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(preprocess_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             100 * 1024);
+    if (staged) {
+        static GsPerDevice per_dev;
+        const int* dv = nullptr;
+        cudaError_t e = per_dev.get(&dv, [](int, int*) {
+            return cudaFuncSetAttribute(preprocess_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        });
         if (e != cudaSuccess) return e;
-        attr_set = true;
     }
     if (staged) preprocess_kernel<true><<<(unsigned)gs_div_up(s.P, 256), 256, stage_bytes, f.stream>>>(a);
     else preprocess_kernel<false><<<(unsigned)gs_div_up(s.P, 256), 256, 0, f.stream>>>(a);
