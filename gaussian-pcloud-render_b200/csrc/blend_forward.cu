@@ -30,6 +30,22 @@
 // reconverging per instance), a warp vote that skips the exponentials nobody needs (+6 %), a packed FP32x2
 // transcription of expf (bit-identical, not faster: FP32x2 saves issue slots, not FMA-pipe cycles), 4 or 5 CTAs
 // per SM instead of 3 (slower tail, no throughput gain).
+// Round 2, three bit-identical restructurings of the tail, all measured and NOT kept (profiles/r02a_*): (1) "lane per
+// Gaussian" -- once <= 24 pixels of a block are live, queue the surviving instances in a shared-memory FIFO, let lane j
+// evaluate alpha of instance j for every live pixel (16 instances x 2 half-warps, four pixels in flight per lane) and
+// let lane r walk the 16 alphas of ITS pixel in list order with the reference's exact T / C recurrence: 2.4x fewer
+// cycles per instance (80 against 190), but the longest blocks keep > 32 live pixels for the first half of their walk
+// (silhouette blocks lie mostly OUTSIDE the body), and FIFO + alpha matrix take the kernel from 37 to 74 KB of shared
+// memory per CTA, which leaves no room for the binning kernels of the next frames: single frame 0.60 -> 0.60 ms,
+// six frames in flight -17 %; (2) evaluating the alphas of 4 or 8 queued instances together before blending them in
+// order (independent expf chains): +45 % instructions, the same 0.135 us per instance; (3) producer / consumer warp
+// pairs (one warp walks and culls, its partner blends; FIFO, named barrier per pair): the consumer is the bottleneck,
+// 0.63-0.69 ms.  What the per-unit timelines say: the long blocks are the FIRST units started, share their scheduler
+// with five other warps for the 250 us in which the queue of fresh units drains -- whatever their instruction-level
+// parallelism, they get a sixth of the issue slots -- and half of all unit-time is still outstanding at that point,
+// spread over ~1000 half-finished walks.  Shortening the frame below ~0.45 ms therefore needs the remaining walks
+// re-distributed over the idle warps (alpha digests handed from helper warps to the owning warp through L2), not a
+// faster walk; not built.
 //
 // Bound: FP32 issue, not HBM.  Algorithmic HBM bytes: 40*sum(need_t) + 20*N + 8*Tn.
 #include "gs_common.cuh"
