@@ -44,6 +44,15 @@ struct Profiler {
     bool on = false;
     bool armed = false;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t bev[3] = {nullptr, nullptr, nullptr};  // backward: before blend, between the stages, after preprocess
+    bool barmed = false;
+    void bmark(int k, cudaStream_t st) {
+        if (!on) return;
+        for (auto& e : bev)
+            if (!e && cudaEventCreate(&e) != cudaSuccess) return;
+        cudaEventRecord(bev[k], st);
+        barmed = (k == 2) ? true : barmed;
+    }
     bool ensure() {
         for (auto& e : ev)
             if (!e && cudaEventCreate(&e) != cudaSuccess) return false;
@@ -84,6 +93,8 @@ int make_frame(const GsScene* s, void* stream, GsFrame& f, bool forward = true) 
         f.row0 = s->tile_row_begin < 0 ? 0 : s->tile_row_begin;
         f.row1 = s->tile_row_end > f.gy ? f.gy : s->tile_row_end;
         if (f.row1 < f.row0) f.row1 = f.row0;
+    } else if (s->tile_row_begin != 0 || s->tile_row_end != 0) {
+        f.row0 = f.row1 = 0;  // empty shard: every tile rectangle is clipped away, nothing is binned or blended
     }
     if (f.gx > GS_MAX_GRID || f.gy > GS_MAX_GRID) return GS_ERR_UNSUPPORTED;  // at most 4096 x 4096 pixels
     if ((unsigned long long)s->P >= (1ull << 30)) return GS_ERR_UNSUPPORTED;  // instance counters stay well inside 32 bits
@@ -161,6 +172,7 @@ int64_t gs_forward(const GsScene* scene, GsBuffer geometry, GsBuffer binning, Gs
     t_prof.mark(0, f.stream);
     GS_STAGE(gs_launch_preprocess(f, g, im, radii));
     t_prof.mark(1, f.stream);
+    if (f.row1 == f.row0) return 0;  // empty tile-row shard: radii are done, there is nothing to bin or blend
     // read the instance / row-item counts back while the depth sort (which does not depend on them) is already
     // queued behind the copy
     GS_CU(cudaMemcpyAsync(t_ctx.pinned, g.hdr, 32, cudaMemcpyDeviceToHost, f.stream));
@@ -201,6 +213,7 @@ int32_t gs_forward_nosync(const GsScene* scene, char* geometry, char* binning, i
     t_prof.mark(0, f.stream);
     GS_STAGE(gs_launch_preprocess(f, g, im, radii));
     t_prof.mark(1, f.stream);
+    if (f.row1 == f.row0) return GS_OK;  // empty tile-row shard
     GS_STAGE(gs_launch_depth_sort(f, g));
     t_prof.mark(2, f.stream);
     GS_STAGE(gs_launch_tile_lists(f, g, b, (size_t)cap, rowcap, im));
@@ -229,12 +242,19 @@ int32_t gs_forward_recolor(const GsScene* scene, char* geometry, char* binning, 
     return GS_OK;
 }
 
-void gs_profile_enable(int32_t on) { t_prof.on = on != 0; t_prof.armed = false; }
+void gs_profile_enable(int32_t on) { t_prof.on = on != 0; t_prof.armed = false; t_prof.barmed = false; }
 
 int32_t gs_profile_read(float* ms4) {
     if (!ms4 || !t_prof.on || !t_prof.armed) return GS_ERR_INVALID;
     GS_CU(cudaEventSynchronize(t_prof.ev[4]));
     for (int k = 0; k < 4; k++) GS_CU(cudaEventElapsedTime(&ms4[k], t_prof.ev[k], t_prof.ev[k + 1]));
+    return GS_OK;
+}
+
+int32_t gs_profile_read_backward(float* ms2) {
+    if (!ms2 || !t_prof.on || !t_prof.barmed) return GS_ERR_INVALID;
+    GS_CU(cudaEventSynchronize(t_prof.bev[2]));
+    for (int k = 0; k < 2; k++) GS_CU(cudaEventElapsedTime(&ms2[k], t_prof.bev[k], t_prof.bev[k + 1]));
     return GS_OK;
 }
 
@@ -245,29 +265,46 @@ int32_t gs_read_status(const char* geometry, GsStatus* out, void* stream) {
     return GS_OK;
 }
 
-int32_t gs_backward(const GsScene* scene, int64_t num_rendered, const int32_t* radii, const char* geometry,
-                    const char* binning, const char* image, const float* dL_dpix, float* dL_dmean2D,
-                    float* dL_dconic, float* dL_dopacity, float* dL_dcolor, float* dL_dmean3D, float* dL_dcov3D,
-                    float* dL_dsh, float* dL_dscale, float* dL_drot, void* stream) {
+int32_t gs_backward_stage(const GsScene* scene, int64_t num_rendered, const int32_t* radii, const char* geometry,
+                          const char* binning, const char* image, const float* dL_dpix, float* dL_dmean2D,
+                          float* dL_dconic, float* dL_dopacity, float* dL_dcolor, float* dL_dmean3D, float* dL_dcov3D,
+                          float* dL_dsh, float* dL_dscale, float* dL_drot, int32_t stages, void* stream) {
     GsFrame f;
     const int rc = make_frame(scene, stream, f, false);
     if (rc != GS_OK) return rc;
+    if ((stages & ~(GS_BWD_BLEND | GS_BWD_PREPROCESS)) || stages == 0) return GS_ERR_INVALID;
     if (f.s.P == 0) return GS_OK;
-    if (!geometry || !image || !radii || !dL_dpix || !dL_dmean2D || !dL_dconic || !dL_dopacity || !dL_dcolor ||
-        !dL_dmean3D || !dL_dcov3D || num_rendered < 0)
-        return GS_ERR_INVALID;
-    if (f.s.shs && !dL_dsh) return GS_ERR_INVALID;
-    if (f.s.scales && (!dL_dscale || !dL_drot)) return GS_ERR_INVALID;
+    const bool blend = stages & GS_BWD_BLEND, pre = stages & GS_BWD_PREPROCESS;
+    if (!geometry || !image || !dL_dmean2D || !dL_dconic || !dL_dcolor || num_rendered < 0) return GS_ERR_INVALID;
+    if (blend && (!dL_dpix || !dL_dopacity)) return GS_ERR_INVALID;
+    if (pre) {
+        if (!radii || !dL_dmean3D || !dL_dcov3D) return GS_ERR_INVALID;
+        if (f.s.shs && !dL_dsh) return GS_ERR_INVALID;
+        if (f.s.scales && (!dL_dscale || !dL_drot)) return GS_ERR_INVALID;
+    }
     GsGeom g(const_cast<char*>(geometry), f.s.P);
     GsImage im(const_cast<char*>(image), (size_t)f.s.width * f.s.height, f.gx, f.gy);
-    if (num_rendered > 0) {
+    t_prof.bmark(0, f.stream);
+    if (blend && num_rendered > 0) {
         if (!binning) return GS_ERR_INVALID;
         GsBinning b(const_cast<char*>(binning), (size_t)num_rendered, 0);  // only `list` (first array) is used
         GS_STAGE(gs_launch_blend_backward(f, g, b, im, dL_dpix, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor));
     }
-    GS_STAGE(gs_launch_preprocess_backward(f, g, radii, dL_dmean2D, dL_dconic, dL_dcolor, dL_dmean3D, dL_dcov3D, dL_dsh,
-                                          dL_dscale, dL_drot));
+    t_prof.bmark(1, f.stream);
+    if (pre)
+        GS_STAGE(gs_launch_preprocess_backward(f, g, radii, dL_dmean2D, dL_dconic, dL_dcolor, dL_dmean3D, dL_dcov3D, dL_dsh,
+                                              dL_dscale, dL_drot));
+    t_prof.bmark(2, f.stream);
     return GS_OK;
+}
+
+int32_t gs_backward(const GsScene* scene, int64_t num_rendered, const int32_t* radii, const char* geometry,
+                    const char* binning, const char* image, const float* dL_dpix, float* dL_dmean2D,
+                    float* dL_dconic, float* dL_dopacity, float* dL_dcolor, float* dL_dmean3D, float* dL_dcov3D,
+                    float* dL_dsh, float* dL_dscale, float* dL_drot, void* stream) {
+    return gs_backward_stage(scene, num_rendered, radii, geometry, binning, image, dL_dpix, dL_dmean2D, dL_dconic,
+                             dL_dopacity, dL_dcolor, dL_dmean3D, dL_dcov3D, dL_dsh, dL_dscale, dL_drot,
+                             GS_BWD_BLEND | GS_BWD_PREPROCESS, stream);
 }
 
 int32_t gs_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, const float* projmatrix,

@@ -84,6 +84,8 @@ def lib() -> C.CDLL:
         L.gs_read_status.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.gs_backward.restype = C.c_int32
         L.gs_backward.argtypes = [C.POINTER(GsScene), C.c_int64] + [C.c_void_p] * 15
+        L.gs_backward_stage.restype = C.c_int32
+        L.gs_backward_stage.argtypes = [C.POINTER(GsScene), C.c_int64] + [C.c_void_p] * 14 + [C.c_int32, C.c_void_p]
         L.gs_mark_visible.restype = C.c_int32
         L.gs_mark_visible.argtypes = [C.c_int32] + [C.c_void_p] * 5
         L.gs_make_views.restype = C.c_int32
@@ -105,6 +107,8 @@ def lib() -> C.CDLL:
         L.gs_profile_enable.argtypes = [C.c_int32]
         L.gs_profile_read.restype = C.c_int32
         L.gs_profile_read.argtypes = [C.c_void_p]
+        L.gs_profile_read_backward.restype = C.c_int32
+        L.gs_profile_read_backward.argtypes = [C.c_void_p]
         L.gs_last_error.restype = C.c_char_p
         L.gs_abi_version.restype = C.c_int32
         _lib = L
@@ -140,13 +144,15 @@ class _Growable:
     Sizes are rounded up to 1/8-octave buckets so that PyTorch's caching allocator finds a block of the same size
     again on the next frame (the instance count, hence the binning buffer, changes from view to view)."""
 
-    def __init__(self, device):
+    def __init__(self, device, stream=None):
         self.t = torch.empty(0, dtype=torch.uint8, device=device)
 
         def _resize(_user, nbytes):
             n = int(nbytes)
             if n > self.t.numel():
                 step = max(1 << 20, 1 << max(0, n.bit_length() - 4))
+                if stream is not None and self.t.numel():
+                    self.t.record_stream(stream)  # pooled: earlier frames of this stream may still read the old block
                 self.t = torch.empty(((n + step - 1) // step) * step, dtype=torch.uint8, device=self.t.device)
             return self.t.data_ptr()
 
@@ -155,15 +161,20 @@ class _Growable:
 
 
 # Workspaces that may be recycled from call to call: only used when the caller states that no backward pass will
-# consume the buffers of this forward (see _RasterizeGaussians.forward); grow-only, one set per device.
+# consume the buffers of this forward (see _RasterizeGaussians.forward).  Grow-only, one set per (device, stream):
+# frames queued on different streams of one device are in flight at the same time and must not share scratch
+# memory; a buffer that is replaced by a larger one is handed back to the caching allocator only after the stream
+# that may still be reading it has been told (record_stream).
 _WORKSPACE_POOL = {}
 
 
 def _pooled_workspaces(dev):
-    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    index = dev.index if dev.index is not None else torch.cuda.current_device()
+    stream = torch.cuda.current_stream(dev)
+    key = (dev.type, index, stream.cuda_stream)
     ws = _WORKSPACE_POOL.get(key)
     if ws is None:
-        ws = _WORKSPACE_POOL[key] = (_Growable(dev), _Growable(dev), _Growable(dev))
+        ws = _WORKSPACE_POOL[key] = (_Growable(dev, stream), _Growable(dev, stream), _Growable(dev, stream))
     return ws
 
 
@@ -231,7 +242,11 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
 def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rotations, scale_modifier, cov3D_precomp,
                                  viewmatrix, projmatrix, tan_fovx, tan_fovy, dL_dout_color, sh, degree, campos,
                                  geomBuffer, R, binningBuffer, imageBuffer, debug,
-                                 tile_rows: Optional[Tuple[int, int]] = None, downsample: int = 1):
+                                 tile_rows: Optional[Tuple[int, int]] = None, downsample: int = 1, grad_group=None):
+    """grad_group: tile-row sharded backward -- a torch.distributed process group over which the per-Gaussian
+    partial gradients of the blend stage are summed (ONE all-reduce of a (P, 11) buffer) before the per-Gaussian
+    stage runs, so that every rank returns the gradients of the WHOLE frame; dL_dout_color is the full (3,H,W)
+    gradient on every rank, of which only this rank's tile rows are read."""
     L = lib()
     dev = means3D.device
     P = int(means3D.size(0))
@@ -239,8 +254,12 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
     M = int(sh.size(1)) if (sh is not None and sh.numel() != 0) else 0
     with torch.cuda.device(dev):
         z = lambda *s: torch.zeros(s, dtype=torch.float32, device=dev)
-        dL_dmeans3D, dL_dmeans2D, dL_dcolors = z(P, 3), z(P, 3), z(P, 3)
-        dL_dconic, dL_dopacity, dL_dcov3D = z(P, 2, 2), z(P, 1), z(P, 6)
+        # the four arrays the blend stage accumulates into live in one buffer: a sharded backward sums them over the
+        # ranks with a single collective
+        partial = z(P * 11)
+        dL_dmeans2D, dL_dconic = partial[:3 * P].view(P, 3), partial[3 * P:7 * P].view(P, 2, 2)
+        dL_dopacity, dL_dcolors = partial[7 * P:8 * P].view(P, 1), partial[8 * P:].view(P, 3)
+        dL_dmeans3D, dL_dcov3D = z(P, 3), z(P, 6)
         dL_dsh, dL_dscales, dL_drotations = z(P, M, 3), z(P, 3), z(P, 4)
         if P != 0:
             # note: unlike rasterize_points.cu:169,171 scales/rotations are made contiguous here too
@@ -254,10 +273,17 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
                                opacities=None, scales=sc_, rotations=rot_, cov3D_precomp=cov_, viewmatrix=view_,
                                projmatrix=proj_, campos=cam_, tile_rows=tile_rows, downsample=downsample)
             stream = torch.cuda.current_stream(dev).cuda_stream
-            _check(L.gs_backward(C.byref(scene), int(R), _ptr(radii_), _ptr(geomBuffer), _ptr(binningBuffer),
-                                 _ptr(imageBuffer), _ptr(dpix_), _ptr(dL_dmeans2D), _ptr(dL_dconic), _ptr(dL_dopacity),
-                                 _ptr(dL_dcolors), _ptr(dL_dmeans3D), _ptr(dL_dcov3D), _ptr(dL_dsh), _ptr(dL_dscales),
-                                 _ptr(dL_drotations), stream), "rasterize_gaussians_backward")
+            args = (C.byref(scene), int(R), _ptr(radii_), _ptr(geomBuffer), _ptr(binningBuffer), _ptr(imageBuffer),
+                    _ptr(dpix_), _ptr(dL_dmeans2D), _ptr(dL_dconic), _ptr(dL_dopacity), _ptr(dL_dcolors),
+                    _ptr(dL_dmeans3D), _ptr(dL_dcov3D), _ptr(dL_dsh), _ptr(dL_dscales), _ptr(dL_drotations))
+            if grad_group is None:
+                _check(L.gs_backward(*args, stream), "rasterize_gaussians_backward")
+            else:
+                import torch.distributed as dist
+                _check(L.gs_backward_stage(*args, GS_BWD_BLEND, stream), "rasterize_gaussians_backward (blend stage)")
+                dist.all_reduce(partial, group=grad_group)
+                _check(L.gs_backward_stage(*args, GS_BWD_PREPROCESS, stream),
+                       "rasterize_gaussians_backward (per-Gaussian stage)")
     return dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations
 
 
@@ -275,6 +301,7 @@ def mark_visible(means3D, viewmatrix, projmatrix):
 
 
 GS_VIEW_STRIDE = 48
+GS_BWD_BLEND, GS_BWD_PREPROCESS = 1, 2
 
 
 def projection_entries(fovx_deg: float, fovy_deg: float, znear: float = 0.01, zfar: float = 100.0):

@@ -12,7 +12,9 @@ so `from diff_gaussian_rasterization import GaussianRasterizationSettings, Gauss
 `debug=True` behaviour (inputs dumped to snapshot_fw.dump / snapshot_bw.dump when the library raises).
 
 Extensions (defaults = reference behaviour): `GaussianRasterizer(settings, tile_rows=(r0, r1))` restricts binning
-and blending to tile rows [r0, r1) (multi-GPU path); `GaussianRasterizer(settings, downsample=2)` returns
+and blending to tile rows [r0, r1) (multi-GPU path); with `grad_group=<process group>` the backward of
+such a shard sums the per-Gaussian partial gradients over the ranks (one all-reduce) so that every rank returns the
+gradients of the whole frame; `GaussianRasterizer(settings, downsample=2)` returns
 the (3, H/2, W/2) image the reference's caller computes with `F.interpolate(..., mode="bilinear")` after a
 super-sampled render (simple_raw_render.py:281-284), folded into the blend epilogue, differentiable.
 """
@@ -30,15 +32,16 @@ def cpu_deep_copy_tuple(input_tuple):
 
 
 def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
-                        raster_settings, tile_rows: Optional[Tuple[int, int]] = None, downsample: int = 1):
+                        raster_settings, tile_rows: Optional[Tuple[int, int]] = None, downsample: int = 1,
+                        grad_group=None):
     return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
-                                     cov3Ds_precomp, raster_settings, tile_rows, downsample)
+                                     cov3Ds_precomp, raster_settings, tile_rows, downsample, grad_group)
 
 
 class _RasterizeGaussians(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
-                raster_settings, tile_rows=None, downsample=1):
+                raster_settings, tile_rows=None, downsample=1, grad_group=None):
         rs = raster_settings
         args = (rs.bg, means3D, colors_precomp, opacities, scales, rotations, rs.scale_modifier, cov3Ds_precomp,
                 rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, rs.image_height, rs.image_width, sh,
@@ -61,6 +64,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         ctx.num_rendered = num_rendered
         ctx.tile_rows = tile_rows
         ctx.downsample = downsample
+        ctx.grad_group = grad_group
         ctx.save_for_backward(colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, geomBuffer,
                               binningBuffer, imgBuffer)
         ctx.mark_non_differentiable(radii)
@@ -77,13 +81,15 @@ class _RasterizeGaussians(torch.autograd.Function):
         if rs.debug:
             cpu_args = cpu_deep_copy_tuple(args)
             try:
-                grads_c = _C.rasterize_gaussians_backward(*args, tile_rows=ctx.tile_rows, downsample=ctx.downsample)
+                grads_c = _C.rasterize_gaussians_backward(*args, tile_rows=ctx.tile_rows, downsample=ctx.downsample,
+                                                          grad_group=ctx.grad_group)
             except Exception as ex:
                 torch.save(cpu_args, "snapshot_bw.dump")
                 print("\nAn error occured in backward. Writing snapshot_bw.dump for debugging.\n")
                 raise ex
         else:
-            grads_c = _C.rasterize_gaussians_backward(*args, tile_rows=ctx.tile_rows, downsample=ctx.downsample)
+            grads_c = _C.rasterize_gaussians_backward(*args, tile_rows=ctx.tile_rows, downsample=ctx.downsample,
+                                                          grad_group=ctx.grad_group)
         (grad_means2D, grad_colors_precomp, grad_opacities, grad_means3D, grad_cov3Ds_precomp, grad_sh, grad_scales,
          grad_rotations) = grads_c
 
@@ -92,7 +98,7 @@ class _RasterizeGaussians(torch.autograd.Function):
 
         return (grad_means3D, grad_means2D, _like(grad_sh, sh), _like(grad_colors_precomp, colors_precomp),
                 grad_opacities, _like(grad_scales, scales),
-                _like(grad_rotations, rotations), _like(grad_cov3Ds_precomp, cov3Ds_precomp), None, None, None)
+                _like(grad_rotations, rotations), _like(grad_cov3Ds_precomp, cov3Ds_precomp), None, None, None, None)
 
 
 class GaussianRasterizationSettings(NamedTuple):
@@ -111,11 +117,13 @@ class GaussianRasterizationSettings(NamedTuple):
 
 
 class GaussianRasterizer(nn.Module):
-    def __init__(self, raster_settings, tile_rows: Optional[Tuple[int, int]] = None, downsample: int = 1):
+    def __init__(self, raster_settings, tile_rows: Optional[Tuple[int, int]] = None, downsample: int = 1,
+                 grad_group=None):
         super().__init__()
         self.raster_settings = raster_settings
         self.tile_rows = tile_rows
         self.downsample = downsample
+        self.grad_group = grad_group
 
     def markVisible(self, positions):
         # Mark visible points (based on frustum culling for camera) with a boolean
@@ -147,4 +155,4 @@ class GaussianRasterizer(nn.Module):
             cov3D_precomp = torch.Tensor([])
 
         return rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp,
-                                   raster_settings, self.tile_rows, self.downsample)
+                                   raster_settings, self.tile_rows, self.downsample, self.grad_group)

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define GS_ABI_VERSION 3
+#define GS_ABI_VERSION 4
 
 enum {
     GS_OK = 0,
@@ -52,7 +52,8 @@ typedef struct GsScene {
     int32_t prefiltered;
     int32_t debug;          /* !=0: synchronise and check for CUDA errors after every stage (auxiliary.h:166-173) */
     /* Tile-row shard (multi-GPU): only tile rows [tile_row_begin, tile_row_end) are binned and
-     * blended; pixels of other rows are left untouched.  0,0 = the whole frame. */
+     * blended; pixels of other rows are left untouched.  0,0 = the whole frame.  begin == end != 0 is an EMPTY shard
+     * (work-balanced partitions can produce one): radii are still computed, nothing is binned, blended or stored. */
     int32_t tile_row_begin, tile_row_end;
     const float* background;     /* [3] */
     const float* means3D;        /* [P][3] */
@@ -140,6 +141,17 @@ int32_t gs_backward(const GsScene* scene, int64_t num_rendered, const int32_t* r
                     float* dL_dconic, float* dL_dopacity, float* dL_dcolor, float* dL_dmean3D, float* dL_dcov3D,
                     float* dL_dsh, float* dL_dscale, float* dL_drot, void* stream);
 
+/* The two stages of gs_backward as separate calls, for callers that exchange data in between: a tile-row sharded
+ * backward runs GS_BWD_BLEND on every rank over its own rows, sums the four per-Gaussian partial arrays
+ * dL_dmean2D / dL_dconic / dL_dopacity / dL_dcolor over the ranks (a Gaussian's tiles span ranks, backward.cu:523-554
+ * accumulates into (P, .) arrays), then runs GS_BWD_PREPROCESS.  Same arguments as gs_backward; pointers a stage does
+ * not touch may be NULL.  gs_backward(...) == gs_backward_stage(..., GS_BWD_BLEND | GS_BWD_PREPROCESS). */
+enum { GS_BWD_BLEND = 1, GS_BWD_PREPROCESS = 2 };
+int32_t gs_backward_stage(const GsScene* scene, int64_t num_rendered, const int32_t* radii, const char* geometry,
+                          const char* binning, const char* image, const float* dL_dpix, float* dL_dmean2D,
+                          float* dL_dconic, float* dL_dopacity, float* dL_dcolor, float* dL_dmean3D, float* dL_dcov3D,
+                          float* dL_dsh, float* dL_dscale, float* dL_drot, int32_t stages, void* stream);
+
 /* present[i] = 1 if point i passes the reference's frustum test (near plane only, auxiliary.h:154). */
 int32_t gs_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, const float* projmatrix,
                         uint8_t* present, void* stream);
@@ -193,6 +205,8 @@ int64_t gs_fetch(const GsScene* scene, const char* geometry, const char* binning
  * ms4 = {preprocess, depth sort, tile binning, blend forward}.  Off by default; enabling costs 5 event records. */
 void gs_profile_enable(int32_t on);
 int32_t gs_profile_read(float* ms4);
+/* Same for the most recent backward on this host thread: ms2 = {blend backward, preprocess backward}. */
+int32_t gs_profile_read_backward(float* ms2);
 
 /* Number of kernels launched by this library since load (bench.py's "gpu_launches"). */
 int64_t gs_launch_count(void);
