@@ -2,14 +2,22 @@
 """bench.py -- frames/s of the Gaussian-splat rasterizer hot path on BASELINE.json's headline configuration
 (THuman-shaped 800K-point cloud, 1920x1080, fov 45, forward; "C2" of BASELINE.md), N GPUs of one node.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference|cpu-port] [--workload C2|C1|C4]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference|cpu-port] [--workload C2|C1|C3|C4]
 
 A step = one full forward frame (preprocess -> depth sort -> tile binning -> blend) of one view of a 120-view
 orbit (consecutive steps use consecutive views, so no frame re-uses the previous frame's L2 contents for its
 instance lists; the per-frame input set, 160 MB of Gaussian attributes, exceeds the 126 MB L2).
   value : frames/s with the cloud resident in HBM (gs_forward_nosync, CUDA events, max over ranks)
-  e2e   : frames/s through the drop-in GaussianRasterizer API with HOST buffers: every step copies the
-          Gaussian attributes + camera from pinned host memory to the device and the rendered image back.
+  e2e   : frames/s with HOST buffers: every step copies the Gaussian attributes + camera from pinned host memory to
+          the device and the rendered image back (streaming API, packed host layout; the padded layout and the serial
+          drop-in call are reported next to it).  N > 1: the cloud crosses PCIe once per step and NODE (each rank
+          uploads 1/N of it, one NVLink all-gather per array completes it on every GPU).
+  single_frame_ms / dropin_serial_fps : one frame at a time (latency), the drop-in module called serially.
+  extra_workloads : C3 (forward + backward, with a roofline record of the blend-backward kernel) and C4 (5M random
+          Gaussians, 2048^2) measured in the same run, both arms, so the driver's two lines give their ratios too.
+  tiles (N > 1) : the north star's split -- ONE frame sharded by tile rows over the N GPUs, image assembled on every
+          GPU by peer stores from the blend epilogue (or one NCCL all-gather); asserted bit-identical to the
+          single-GPU frame before it is timed.
   roofline     : the blend-forward kernel; algorithmic bytes 40*sum(need_t) + 20*N + 8*Tn,
                  kernel time from CUDA events recorded inside the library on the launching stream.
   cpu_baseline : the C/OpenMP oracle port (oracle/gs_oracle.c) on this host's cores, bounded sample.
@@ -47,12 +55,14 @@ WORKLOADS = {
     "C1": dict(desc="THuman-256 synthetic (221712 pts voxelised 1/256, sf 256), 1024x1024 (512^2 x ss2), 12-view orbit",
                P=221712, W=1024, H=1024, views=12),
     "C4": dict(desc="5M random Gaussians, SH degree 3, 2048x2048, 8-view orbit", P=5_000_000, W=2048, H=2048, views=8),
+    "C3": dict(desc="THuman-800K synthetic (799957 pts, sf 448), 1920x1080, fov 45, forward + backward (gradients to "
+                    "means / scales / rotations / opacity / SH), 120-view orbit", P=799957, W=1920, H=1080, views=120),
 }
 
 
 def make_workload(name):
     w = WORKLOADS[name]
-    if name == "C2":
+    if name in ("C2", "C3"):
         cloud = scenes.human_cloud(w["P"], scale_factor=448.0, seed=0)
     elif name == "C1":
         cloud = scenes.human_cloud(w["P"], scale_factor=256.0, seed=0, voxelize=256)
@@ -182,9 +192,198 @@ def algorithmic_blend_bytes(n_contrib_hw: torch.Tensor, W, H):
 
 
 # ------------------------------------------------------------------------------------------------------------
+def _median_ms(fn, n, warm=4):
+    """Median over n calls of the per-call device time, one call at a time (fn(i) queues call i)."""
+    for i in range(warm):
+        fn(i)
+    torch.cuda.synchronize()
+    ts = []
+    for i in range(n):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn(warm + i)
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return float(np.median(ts))
+
+
+def c3_leg_b200(cloud, views, w, dev, need_sum, n=24):
+    """Config C3: forward + backward through the drop-in module (autograd), one view at a time; plus the roofline
+    record of blend_backward_kernel (algorithmic bytes 112*sum(need_t) + 20*N) with the kernel time from
+    CUDA events recorded inside the library on the launching stream."""
+    from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer, _C
+    W, H, nv = w["W"], w["H"], len(views)
+    L = _C.lib()
+    d = {k: cloud[k].to(dev).requires_grad_(True) for k in ("means3D", "opacities", "scales", "rotations", "shs")}
+    wgt = torch.from_numpy(np.random.default_rng(7).standard_normal((3, H, W)).astype(np.float32)).to(dev)
+    bg = torch.ones(3, device=dev)
+    t = lambda a: torch.from_numpy(a).to(dev)
+    vd = [(t(v.viewmatrix), t(v.projmatrix), t(v.campos)) for v in views]
+
+    def settings(k):
+        return GaussianRasterizationSettings(H, W, views[k].tanfovx, views[k].tanfovy, bg, 1.0, vd[k][0], vd[k][1],
+                                             cloud["sh_degree"], vd[k][2], False, False)
+
+    def step(i, backward=True):
+        k = (5 + 7 * i) % nv
+        m2 = torch.zeros_like(d["means3D"], requires_grad=True)
+        color, _ = GaussianRasterizer(settings(k))(d["means3D"], m2, d["opacities"], shs=d["shs"], scales=d["scales"],
+                                                   rotations=d["rotations"])
+        if backward:
+            for x in d.values():
+                x.grad = None
+            color.backward(wgt)
+
+    fwd_ms = _median_ms(lambda i: step(i, False), n)
+    both_ms = _median_ms(step, n)
+    # kernel times of the backward stages: the binding called directly (the profiler's events are per host thread and
+    # autograd runs backward on its own thread)
+    L.gs_profile_enable(1)
+    ms2, tot, bsum = np.zeros(2, dtype=np.float32), np.zeros(2), 0.0
+    nprof = min(n, 12)
+    with torch.no_grad():
+        for i in range(nprof):
+            k = (5 + 7 * i) % nv
+            rs = settings(k)
+            R, _c, radii, gb, bb, ib = _C.rasterize_gaussians(bg, d["means3D"], None, d["opacities"], d["scales"],
+                                                              d["rotations"], 1.0, None, rs.viewmatrix, rs.projmatrix,
+                                                              rs.tanfovx, rs.tanfovy, H, W, d["shs"], rs.sh_degree,
+                                                              rs.campos, False, False)
+            _C.rasterize_gaussians_backward(bg, d["means3D"], radii, None, d["scales"], d["rotations"], 1.0, None,
+                                            rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, wgt, d["shs"],
+                                            rs.sh_degree, rs.campos, gb, R, bb, ib, False)
+            L.gs_profile_read_backward(ms2.ctypes.data)
+            tot += ms2
+            bsum += 112.0 * need_sum[k] + 20.0 * W * H
+    L.gs_profile_enable(0)
+    peaks = _peaks()
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    kms = tot[0] / nprof
+    ach = (bsum / nprof) / (kms * 1e-3) / 1e9
+    return {"workload": "C3: " + WORKLOADS["C3"]["desc"], "fwd_ms": fwd_ms, "fwd_bwd_ms": both_ms,
+            "bwd_ms": both_ms - fwd_ms, "value": 1e3 / both_ms, "unit": "frames/s (forward + backward, one view at a time)",
+            "views": n, "api": "diff_gaussian_rasterization.GaussianRasterizer + autograd (drop-in)",
+            "roofline": {"bound": "hbm", "kernel": "blend_backward_kernel", "achieved": ach, "peak": peak,
+                         "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                         "peak_source": "measured" if peaks else "fallback", "kernel_ms": float(kms),
+                         "algorithmic_bytes": bsum / nprof,
+                         "stage_ms": {"blend_backward": float(kms), "preprocess_backward": float(tot[1] / nprof)},
+                         "note": "issue + L2-atomic bound, not HBM bound; kernel time from a per-frame-synchronised pass"}}
+
+
+def _peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:  # noqa: BLE001
+        return {}
+
+
+def frames_leg_b200(name, dev, streams=4, steps=24):
+    """A forward-only workload measured the way the headline is (cloud resident, frames in flight) plus one frame at
+    a time; used for the extra_workloads record of the default line."""
+    from renderer import FramePipeline
+    cloud, views, w = make_workload(name)
+    pipe = FramePipeline(cloud, w["W"], w["H"], [1.0, 1.0, 1.0], dev, depth=streams)
+    vdev = [pipe.upload_view(v) for v in views]
+    pipe.calibrate(vdev)
+    nv = len(vdev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def run(n, off):
+        pipe.begin()
+        for i in range(n):
+            pipe.enqueue(vdev[(off + i) % nv], slot=i)
+        pipe.end()
+
+    run(2 * streams, 0)
+    torch.cuda.synchronize()
+    e0.record()
+    run(steps, 3)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    fr = pipe.lanes[0]
+    single = _median_ms(lambda i: fr.enqueue(vdev[i % nv]), min(steps, 16), warm=2)
+    for i in range(min(steps, fr.SLOTS)):
+        if pipe.lanes[(2 * streams + i) % pipe.depth].status(i)[2] != 0:
+            raise RuntimeError(f"{name}: frame {i} failed")
+    return {"workload": f"{name}: {w['desc']}", "value": 1e3 / ms, "unit": "frames/s", "ms_per_step": ms,
+            "frames_in_flight": streams, "steps": steps, "single_frame_ms": single}
+
+
+def tiles_leg(args, rank, world, fr, vdev, parts, W, H, dev, steps):
+    """The north star's split of ONE frame: every rank bins + blends a work-balanced range of tile rows and the image
+    is assembled on every GPU (peer stores from the blend epilogue + one symmetric-memory barrier, or one NCCL
+    all-gather).  The assembled frame is compared bit for bit with the frame this rank renders alone before timing."""
+    import torch.distributed as dist
+    nv = len(vdev)
+    peer = None
+    if args.exchange == "peer":
+        try:
+            peer = sharding.PeerFrame(H, W, dev)
+        except Exception as ex:  # noqa: BLE001
+            if rank == 0:
+                print(f"[bench] symmetric memory unavailable ({ex!r}); using the NCCL all-gather", file=sys.stderr)
+
+    def frame(i):
+        v, rows = vdev[i % nv], parts[i % nv]
+        r0, r1 = rows[rank]
+        if peer is not None:
+            img, ptrs, peer_barrier = peer.next()
+            if r1 > r0:
+                fr.enqueue(v, tile_rows=(r0, r1), slot=i, peer_out=ptrs)
+            peer_barrier()
+            return img
+        if r1 > r0:
+            fr.enqueue(v, tile_rows=(r0, r1), slot=i)
+        sharding.exchange_image(fr.color, rows, rank)
+        return fr.color
+
+    # ---- correctness first: assembled == single-GPU frame, on every rank, for a few views
+    ok = torch.ones(1, dtype=torch.int32, device=dev)
+    share = None
+    for k in sorted({0, nv // 3, (2 * nv) // 3}):
+        full = fr.render(vdev[k]).clone()
+        total_rendered = fr.status()[0]
+        barrier(world)
+        img = frame(k)
+        torch.cuda.synchronize()
+        barrier(world)
+        if not torch.equal(img, full):
+            ok.zero_()
+        if share is None:
+            mine = torch.tensor([fr.status(k)[0] if parts[k][rank][1] > parts[k][rank][0] else 0], dtype=torch.float64,
+                                device=dev)
+            allr = [torch.zeros_like(mine) for _ in range(world)]
+            dist.all_gather(allr, mine)
+            share = [float(x.item()) / max(1, total_rendered) for x in allr]
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if int(ok.item()) != 1:
+        raise RuntimeError("tile-row sharded frame differs from the single-GPU frame")
+    # ---- one frame at a time on one GPU (the latency this split is meant to cut), then the sharded frames
+    single_ms = _median_ms(lambda i: fr.enqueue(vdev[i % nv]), min(steps, 24), warm=3)
+    for i in range(3):
+        frame(i)
+    barrier(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        frame(3 + i)
+    e1.record()
+    barrier(world)
+    ms = max_over_ranks(e0.elapsed_time(e1), world, dev) / steps
+    single_ms = max_over_ranks(single_ms, world, dev)
+    return {"value": 1e3 / ms, "unit": "frames/s", "ms_per_frame": ms, "scaling": "strong", "steps": steps,
+            "exchange": ("blend epilogue stores into all ranks' images over NVLink + one symmetric-memory barrier per frame"
+                         if peer is not None else "one NCCL all-gather per frame"),
+            "bit_identical_to_single_gpu_frame": True, "num_rendered_share_per_rank": share,
+            "single_gpu_frame_ms": single_ms, "speedup_vs_single_gpu_frame": single_ms / ms}
+
+
 def run_b200(args, rank, world):
     from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer, _C
-    from renderer import FramePipeline, FrameRenderer
+    from renderer import FramePipeline, FrameRenderer  # noqa: F401
     dev = torch.device("cuda", torch.cuda.current_device())
     cloud, views, w = make_workload(args.workload)
     W, H = w["W"], w["H"]
@@ -193,12 +392,13 @@ def run_b200(args, rank, world):
     tiles_mode = world > 1 and args.parallel == "tiles"
     pipe = FramePipeline(cloud, W, H, [1.0, 1.0, 1.0], dev, depth=1 if tiles_mode else args.streams)
     fr = pipe.lanes[0]
+    in_flight = pipe.depth
     vdev = [fr.upload_view(v) for v in views]
     nv = len(vdev)
 
     # calibration (untimed): instance capacity, per-view blend bytes, and per-view balanced row partitions
     pipe.calibrate(vdev[:: max(1, nv // 12)])
-    blend_bytes, parts, rendered = [], [], []
+    blend_bytes, parts, rendered, need_sum = [], [], [], []
     for v in vdev:
         fr.render(v)
         nr = fr.status()[0]
@@ -207,10 +407,23 @@ def run_b200(args, rank, world):
         ncon = _C.fetch("n_contrib", scene, fr.geom, fr.binning, fr.img, fr.capacity).view(H, W).to(dev)
         b, need = algorithmic_blend_bytes(ncon, W, H)
         blend_bytes.append(b)
-        if tiles_mode:
+        need_sum.append(float(need.sum()))
+        if world > 1:
             rng = _C.fetch("ranges", scene, fr.geom, fr.binning, fr.img, fr.capacity).view(-1, 2).to(torch.int64)
             inst = (rng[:, 1] - rng[:, 0]).view(gy, -1)
             parts.append(balanced_rows(sharding.row_cost(need.cpu().numpy(), inst.numpy()), world))
+
+    if args.workload == "C3":  # forward + backward is the whole job of this workload
+        out = None
+        rec = c3_leg_b200(cloud, views, w, dev, need_sum, n=max(8, min(args.steps, 40)))
+        if rank == 0:
+            out = {"metric": "frames/sec (C3: forward + backward)", "value": rec["value"], "unit": "frames/s",
+                   "n_gpus": 1, "steps": rec["views"], "warmup": args.warmup, "ms_per_step": rec["fwd_bwd_ms"],
+                   "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                   "data": "synthetic", "config": {"workload": rec["workload"], "parallelism": "single GPU"},
+                   "c3": rec, "roofline": rec["roofline"], "gpu_launches": int(L.gs_launch_count()), "cpu_baseline": None}
+        return out
+
     peer = None
     if tiles_mode and args.exchange == "peer":
         try:  # frame images in symmetric memory: the blend kernel stores its rows into every rank's image
@@ -219,9 +432,11 @@ def run_b200(args, rank, world):
             if rank == 0:
                 print(f"[bench] symmetric memory unavailable ({ex!r}); using the NCCL all-gather", file=sys.stderr)
 
+    lanes_used = []
+
     def frame(i, slot):
         if not tiles_mode:  # view-parallel: this rank's i-th frame is view rank + i*world of the orbit
-            pipe.enqueue(vdev[(rank + i * world) % nv], slot=slot)
+            lanes_used.append(pipe.enqueue(vdev[(rank + i * world) % nv], slot=slot)[0])
         else:
             v = vdev[i % nv]
             rows = parts[i % nv]
@@ -241,14 +456,14 @@ def run_b200(args, rank, world):
         clocks.start()
         clocks.wait_first()
     pipe.begin()
-    for i in range(max(args.warmup, 3)):
+    for i in range(args.warmup):
         frame(i, i)
     pipe.end()
     barrier(world)
     launches0 = L.gs_launch_count()
-    stage_ms = np.zeros(4)
     barrier(world)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    del lanes_used[:]
     clocks.mark(True)
     e0.record()
     pipe.begin()
@@ -262,8 +477,8 @@ def run_b200(args, rank, world):
     launches = L.gs_launch_count() - launches0
     clk = clocks.stop() if rank == 0 else None
     L.gs_profile_enable(0)
-    for i in range(min(args.steps, fr.SLOTS)):
-        ln = pipe.lanes[(args.warmup + i) % pipe.depth] if not tiles_mode else fr
+    for i in range(max(0, args.steps - fr.SLOTS), args.steps):  # the status slot of frame i is on the lane that ran it
+        ln = pipe.lanes[lanes_used[i]] if not tiles_mode else fr
         code = ln.status(i)[2]
         if code != 0 and not (tiles_mode and ln.status(i)[0] == 0):
             raise RuntimeError(f"frame {i} failed with status {code}")
@@ -273,7 +488,7 @@ def run_b200(args, rank, world):
 
     # blend-kernel time: a separate, per-frame-synchronised pass (reading the events needs a sync per frame and
     # would serialise the main loop), same frames
-    roof = None
+    roof, single_frame_ms = None, None
     if world == 1:
         L.gs_profile_enable(1)
         ms4 = np.zeros(4, dtype=np.float32)
@@ -287,11 +502,8 @@ def run_b200(args, rank, world):
             bsum += blend_bytes[(args.warmup + i) % nv]
         L.gs_profile_enable(0)
         stage_avg = tot / nprof
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:  # noqa: BLE001
-            pass
+        single_frame_ms = _median_ms(lambda i: fr.enqueue(vdev[(args.warmup + i) % nv]), min(max(args.steps, 8), 48), warm=2)
+        peaks = _peaks()
         peak = float(peaks.get("hbm_gbs", 6650.0))
         ach = (bsum / nprof) / (stage_avg[3] * 1e-3) / 1e9
         ncu = {}
@@ -304,19 +516,30 @@ def run_b200(args, rank, world):
                 "peak_source": "measured" if peaks else "fallback",
                 "ncu": {k: ncu.get(k) for k in ("issue_active_pct", "l2_hit_pct", "warp_instructions", "source")} if ncu else None,
                 "kernel_ms": float(stage_avg[3]), "algorithmic_bytes": bsum / nprof,
+                "kernel_ms_source": "separate pass, ONE frame at a time with a synchronisation per frame (CUDA events "
+                                    "inside the library on the launching stream); the headline `value` overlaps "
+                                    f"{in_flight} frames, so ms_per_step can be smaller than kernel_ms",
                 "stage_ms": {"preprocess": float(stage_avg[0]), "depth_sort": float(stage_avg[1]),
                              "tile_binning": float(stage_avg[2]), "blend_forward": float(stage_avg[3])},
                 "note": "blend is FP32-issue/MUFU bound, not HBM bound (SURVEY.md 8d); HBM figure reported as the metric asks"}
 
-    # ---- e2e: drop-in API, host buffers (every step: all inputs pinned host -> device, image device -> host) ----
+    tiles = None
+    if world > 1 and not tiles_mode and not args.no_tiles:
+        tiles = tiles_leg(args, rank, world, fr, vdev, parts, W, H, dev, steps=max(8, min(args.steps, 120)))
+
+    # ---- e2e: host buffers (every step: all inputs pinned host -> device, image device -> host) ----
     host = {k: cloud[k].contiguous().pin_memory() for k in ("means3D", "opacities", "scales", "rotations", "shs")}
+    packed = scenes.pack_cloud(cloud)
+    host_packed = dict(host, shs=packed["shs"].contiguous().pin_memory())
     hviews = [(torch.from_numpy(v.viewmatrix).pin_memory(), torch.from_numpy(v.projmatrix).pin_memory(),
                torch.from_numpy(v.campos).pin_memory()) for v in views]
     bg = torch.ones(3, device=dev)
     img_host = torch.empty((3, H, W), dtype=torch.float32).pin_memory()
     ddev = {k: torch.empty_like(t, device=dev) for k, t in host.items()}  # preallocated: no allocator noise
     vdev2 = [torch.empty(4, 4, device=dev), torch.empty(4, 4, device=dev), torch.empty(3, device=dev)]
-    h2d = sum(t.numel() * 4 for t in host.values()) + (16 + 16 + 3) * 4
+    cam_bytes = (16 + 16 + 3) * 4
+    h2d = sum(t.numel() * 4 for t in host.values()) + cam_bytes
+    h2d_packed = sum(t.numel() * 4 for t in host_packed.values()) + cam_bytes
     d2h = 3 * H * W * 4
 
     def e2e_frame(i, upload_cloud=True):
@@ -355,47 +578,72 @@ def run_b200(args, rank, world):
 
     # the same steps through the streaming API of this package (renderer.FramePipeline.enqueue_host -> C ABI
     # gs_forward_nosync): every step still uploads all its inputs and downloads its image, but the copies of one
-    # frame overlap the kernels of the others
-    def e2e_pipelined(steps):
+    # frame overlap the kernels of the others.  fan_out (N > 1): the N ranks render N views of the same cloud per
+    # step, so the cloud crosses PCIe once per step and node (1/N per rank) and NVLink completes it on every GPU.
+    def e2e_pipelined(steps, hcloud, dcloud, fan_out=False):
         if tiles_mode:
             return None
-        hp = FramePipeline(cloud, W, H, [1.0, 1.0, 1.0], dev, depth=3, capacity=fr.capacity)
+        import torch.distributed as dist
+        hp = FramePipeline(dcloud, W, H, [1.0, 1.0, 1.0], dev, depth=3, capacity=fr.capacity)
         outs = [torch.empty((3, H, W), dtype=torch.float32).pin_memory() for _ in range(hp.depth)]
+        group = dist.group.WORLD if (fan_out and world > 1) else None
+        used = []
 
         def go(n, off):
             hp.begin()
             for i in range(n):
                 k = (rank + (off + i) * world) % nv
-                hp.enqueue_host(host, hviews[k], (views[k].tanfovx, views[k].tanfovy), outs[hp.count % hp.depth], slot=i)
+                used.append(hp.enqueue_host(hcloud, hviews[k], (views[k].tanfovx, views[k].tanfovy),
+                                            outs[hp.count % hp.depth], slot=i, group=group))
             hp.end()
 
         go(4, 0)
         barrier(world)
+        del used[:]
         e0.record()
         go(steps, 4)
         e1.record()
         barrier(world)
-        for i in range(min(steps, fr.SLOTS)):
-            if hp.lanes[(4 + i) % hp.depth].status(i)[2] != 0:
+        for i in range(max(0, steps - fr.SLOTS), steps):
+            if hp.lanes[used[i]].status(i)[2] != 0:
                 raise RuntimeError("pipelined e2e frame failed")
         t = max_over_ranks(e0.elapsed_time(e1), world, dev)
         return steps * world / (t / 1e3)
 
     e2e_steps = max(3, min(args.steps, 40))
     serial = e2e_run(e2e_steps)
-    piped = e2e_pipelined(e2e_steps)
-    e2e = {"value": piped if piped is not None else serial, "unit": "frames/s", "h2d_bytes_per_step": h2d,
+    piped_full = e2e_pipelined(e2e_steps, host, cloud)
+    piped = e2e_pipelined(e2e_steps, host_packed, packed, fan_out=True)
+    fan = world > 1 and piped is not None
+    e2e = {"value": piped if piped is not None else serial, "unit": "frames/s",
+           "h2d_bytes_per_step": (-(-(h2d_packed - cam_bytes) // world) + cam_bytes) if fan else (h2d_packed if piped is not None else h2d),
            "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-           "api": ("renderer.FramePipeline.enqueue_host (3 frames in flight; C ABI gs_forward_nosync), pinned host inputs -> "
-                   "device -> pinned host image every step") if piped is not None else
+           "api": (("renderer.FramePipeline.enqueue_host (3 frames in flight; C ABI gs_forward_nosync), pinned host inputs -> "
+                    "device -> pinned host image every step; host cloud in the packed layout gs_decode_head emits (SH "
+                    f"array without its all-zero coefficients: {h2d_packed} instead of {h2d} bytes per cloud, same frame "
+                    "bit for bit)") +
+                   (f"; the {world} ranks render {world} views of the same cloud per step, each uploads 1/{world} of it and "
+                    "one NVLink all-gather per attribute array completes it on every GPU (bytes are per rank)" if fan else ""))
+                  if piped is not None else
                   "diff_gaussian_rasterization.GaussianRasterizer (drop-in), pinned host inputs -> device -> host image",
+           # the reference's own host layout (13 SH coefficients per point, 12 of them zero), every rank uploads all of it
+           "padded_layout": {"value": piped_full, "unit": "frames/s", "h2d_bytes_per_step": h2d,
+                             "api": "renderer.FramePipeline.enqueue_host, the reference's (P,13,3) SH array uploaded as is"},
            # the drop-in module called frame after frame, nothing overlapped (how the reference arm is driven too)
-           "dropin_serial": {"value": serial, "unit": "frames/s",
+           "dropin_serial": {"value": serial, "unit": "frames/s", "h2d_bytes_per_step": h2d,
                              "api": "diff_gaussian_rasterization.GaussianRasterizer, one frame at a time"},
            # for information: the reference's callers keep the Gaussians on the device and upload only the camera
            # per view (simple_raw_render.py:79-112, 261-277); same API, camera up + image down every step
            "resident_cloud": {"value": e2e_run(e2e_steps, upload_cloud=False), "unit": "frames/s",
-                              "h2d_bytes_per_step": (16 + 16 + 3) * 4, "d2h_bytes_per_step": d2h}}
+                              "h2d_bytes_per_step": cam_bytes, "d2h_bytes_per_step": d2h}}
+
+    extra = None
+    if world == 1 and args.workload == "C2" and not args.no_extra:
+        del pipe, ddev
+        torch.cuda.empty_cache()
+        extra = {"C3": c3_leg_b200(cloud, views, w, dev, need_sum, n=max(8, min(args.steps, 24)))}
+        torch.cuda.empty_cache()
+        extra["C4"] = frames_leg_b200("C4", dev)
 
     out = None
     if rank == 0:
@@ -410,9 +658,11 @@ def run_b200(args, rank, world):
                             if peer is not None else "one NCCL all-gather per frame") if tiles_mode
                            else f"view-parallel x{world}: rank r renders views r, r+{world}, ... (no collective)"),
                           "l2_policy": "inputs larger than L2 (160 MB of attributes per frame; consecutive steps render different views)",
-                          "frames_in_flight": pipe.depth,
+                          "frames_in_flight": in_flight,
                           "mean_num_rendered": float(np.mean(rendered))},
-               "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu}
+               "single_frame_ms": single_frame_ms, "dropin_serial_fps": serial,
+               "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "tiles": tiles,
+               "extra_workloads": extra, "cpu_baseline": cpu}
     return out
 
 
@@ -448,7 +698,69 @@ def run_reference(args, rank, world):
         return run_cpu_port(args, cloud, views, w, impl="reference",
                             note="oracle/_ref/libgs_ref.so or GPU missing: the oracle port stands in")
     dev = torch.device("cuda", torch.cuda.current_device())
+
+    def c3_leg(ref, cloud, views, w, n):
+        """forward + backward of the reference library, one view at a time (config C3)."""
+        W, H, nv = w["W"], w["H"], len(views)
+        d = {k: cloud[k].to(dev) for k in ("means3D", "opacities", "scales", "rotations", "shs")}
+        wgt = torch.from_numpy(np.random.default_rng(7).standard_normal((3, H, W)).astype(np.float32)).to(dev)
+        bg = torch.ones(3, device=dev)
+        t = lambda a: torch.from_numpy(a).to(dev)
+        vd = [(t(v.viewmatrix), t(v.projmatrix), t(v.campos)) for v in views]
+
+        def step(i, backward=True):
+            k = (5 + 7 * i) % nv
+            ref.forward(means3D=d["means3D"], opacities=d["opacities"], W=W, H=H, viewmatrix=vd[k][0], projmatrix=vd[k][1],
+                        campos=vd[k][2], bg=bg, tanfovx=views[k].tanfovx, tanfovy=views[k].tanfovy,
+                        sh_degree=cloud["sh_degree"], shs=d["shs"], scales=d["scales"], rotations=d["rotations"])
+            if backward:
+                ref.backward(wgt, sync=False)
+
+        for k in range(0, nv, 4):  # size the reference's growable buffers before anything is timed
+            step(k, False)
+        fwd = _median_ms(lambda i: step(i, False), n)
+        both = _median_ms(step, n)
+        return {"workload": "C3: " + WORKLOADS["C3"]["desc"], "fwd_ms": fwd, "fwd_bwd_ms": both, "bwd_ms": both - fwd,
+                "value": 1e3 / both, "unit": "frames/s (forward + backward, one view at a time)", "views": n}
+
+    def frames_leg(ref, name, steps):
+        cloud, views, w = make_workload(name)
+        d = {k: cloud[k].to(dev) for k in ("means3D", "opacities", "scales", "rotations", "shs")}
+        bg = torch.ones(3, device=dev)
+        t = lambda a: torch.from_numpy(a).to(dev)
+        vd = [(t(v.viewmatrix), t(v.projmatrix), t(v.campos)) for v in views]
+        nv = len(views)
+
+        def fr(i):
+            k = i % nv
+            ref.forward(means3D=d["means3D"], opacities=d["opacities"], W=w["W"], H=w["H"], viewmatrix=vd[k][0],
+                        projmatrix=vd[k][1], campos=vd[k][2], bg=bg, tanfovx=views[k].tanfovx, tanfovy=views[k].tanfovy,
+                        sh_degree=cloud["sh_degree"], shs=d["shs"], scales=d["scales"], rotations=d["rotations"])
+
+        for k in range(nv):
+            fr(k)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fr(3 + i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        return {"workload": f"{name}: {w['desc']}", "value": 1e3 / ms, "unit": "frames/s", "ms_per_step": ms,
+                "frames_in_flight": 1, "steps": steps, "single_frame_ms": ms}
+
     ref = ReferenceCUDA()
+    if args.workload == "C3":
+        rec = c3_leg(ref, cloud, views, w, max(8, min(args.steps, 40)))
+        return {"impl": "reference", "metric": "frames/sec (C3: forward + backward)", "value": rec["value"],
+                "unit": "frames/s", "n_gpus": 1, "steps": rec["views"], "warmup": args.warmup,
+                "ms_per_step": rec["fwd_bwd_ms"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": {"workload": rec["workload"], "parallelism": "single GPU"},
+                "c3": rec, "gpu_launches": 0,
+                "e2e": {"value": rec["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "cpu_baseline": {"value": rec["value"], "unit": "frames/s", "cores": 1, "kind": "reference",
+                                 "sample": "the reference has no CPU path: its CUDA kernels ran on the B200"}}
     d = {k: cloud[k].to(dev) for k in ("means3D", "opacities", "scales", "rotations", "shs")}
     bg = torch.ones(3, device=dev)
     vd = [(torch.from_numpy(v.viewmatrix).to(dev), torch.from_numpy(v.projmatrix).to(dev),
@@ -465,6 +777,10 @@ def run_reference(args, rank, world):
     clocks = ClockSampler(torch.cuda.current_device())
     clocks.start()
     clocks.wait_first()
+    # untimed: one sweep over the orbit sizes the reference's growable scratch buffers for the largest view, so that no
+    # timed frame pays a cudaFree + cudaMalloc (oracle/ref_shim.cu grows with 25 % headroom, never shrinks)
+    for k in range(0, nv, 2):
+        frame(k)
     for i in range(args.warmup):
         frame(i)
     torch.cuda.synchronize()
@@ -505,14 +821,25 @@ def run_reference(args, rank, world):
     torch.cuda.synchronize()
     e2e_ms = e0.elapsed_time(e1)
     value = args.steps / (ms / 1e3)
+    extra = None
+    if args.workload == "C2" and not args.no_extra:
+        del ddev
+        torch.cuda.empty_cache()
+        extra = {"C3": c3_leg(ref, cloud, views, w, max(8, min(args.steps, 24)))}
+        del ref
+        torch.cuda.empty_cache()
+        extra["C4"] = frames_leg(ReferenceCUDA(), "C4", 16)
     return {"impl": "reference", "metric": "frames/sec at 1080p, 800K Gaussians" if args.workload == "C2" else f"frames/sec ({args.workload})",
             "value": value, "unit": "frames/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "device": "cuda:0 (the reference's implementation of this path is CUDA-only)",
-            "config": {"workload": f"{args.workload}: {w['desc']}",
+            "config": {"workload": f"{args.workload}: {w['desc']}", "parallelism": "single GPU", "frames_in_flight": 1,
+                       "l2_policy": "inputs larger than L2 (160 MB of attributes per frame; consecutive steps render different views)",
                        "reference": "unmodified diff-gaussian-rasterization (forward.cu/backward.cu/rasterizer_impl.cu + CUB) compiled for sm_100a, driven through oracle/ref_shim.cu"},
+            "single_frame_ms": ms / args.steps, "dropin_serial_fps": e2e_steps / (e2e_ms / 1e3),
             "e2e": {"value": e2e_steps / (e2e_ms / 1e3), "unit": "frames/s",
                     "h2d_bytes_per_step": sum(t.numel() * 4 for t in host.values()) + 35 * 4, "d2h_bytes_per_step": 3 * H * W * 4},
+            "extra_workloads": extra,
             "cpu_baseline": {"value": value, "unit": "frames/s", "cores": 1, "kind": "reference",
                              "sample": f"{args.steps} frames; the reference has no CPU path, so its own CUDA kernels ran on the B200 (host threads: 1)"},
             "clocks": clk, "gpu_launches": 0}
@@ -538,6 +865,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference", "cpu-port"])
     ap.add_argument("--workload", default="C2", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra_workloads record (C3, C4) of the default line")
+    ap.add_argument("--no-tiles", action="store_true", help="N > 1: skip the tile-row sharded record next to the view-parallel value")
     ap.add_argument("--streams", type=int, default=6, help="frames in flight (one CUDA stream + workspace each)")
     ap.add_argument("--parallel", default="views", choices=["views", "tiles"], help="multi-GPU sharding (N > 1)")
     ap.add_argument("--exchange", default="peer", choices=["peer", "allgather"],

@@ -242,11 +242,13 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
 def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rotations, scale_modifier, cov3D_precomp,
                                  viewmatrix, projmatrix, tan_fovx, tan_fovy, dL_dout_color, sh, degree, campos,
                                  geomBuffer, R, binningBuffer, imageBuffer, debug,
-                                 tile_rows: Optional[Tuple[int, int]] = None, downsample: int = 1, grad_group=None):
+                                 tile_rows: Optional[Tuple[int, int]] = None, downsample: int = 1, grad_group=None,
+                                 grad_reduce=None):
     """grad_group: tile-row sharded backward -- a torch.distributed process group over which the per-Gaussian
     partial gradients of the blend stage are summed (ONE all-reduce of a (P, 11) buffer) before the per-Gaussian
     stage runs, so that every rank returns the gradients of the WHOLE frame; dL_dout_color is the full (3,H,W)
-    gradient on every rank, of which only this rank's tile rows are read."""
+    gradient on every rank, of which only this rank's tile rows are read.  grad_reduce: the same hook as a callable
+    `f(partial)` that sums the flat (11 P) buffer over the shards in place (used instead of grad_group)."""
     L = lib()
     dev = means3D.device
     P = int(means3D.size(0))
@@ -276,12 +278,15 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
             args = (C.byref(scene), int(R), _ptr(radii_), _ptr(geomBuffer), _ptr(binningBuffer), _ptr(imageBuffer),
                     _ptr(dpix_), _ptr(dL_dmeans2D), _ptr(dL_dconic), _ptr(dL_dopacity), _ptr(dL_dcolors),
                     _ptr(dL_dmeans3D), _ptr(dL_dcov3D), _ptr(dL_dsh), _ptr(dL_dscales), _ptr(dL_drotations))
-            if grad_group is None:
+            if grad_group is None and grad_reduce is None:
                 _check(L.gs_backward(*args, stream), "rasterize_gaussians_backward")
             else:
-                import torch.distributed as dist
                 _check(L.gs_backward_stage(*args, GS_BWD_BLEND, stream), "rasterize_gaussians_backward (blend stage)")
-                dist.all_reduce(partial, group=grad_group)
+                if grad_reduce is not None:
+                    grad_reduce(partial)
+                else:
+                    import torch.distributed as dist
+                    dist.all_reduce(partial, group=grad_group)
                 _check(L.gs_backward_stage(*args, GS_BWD_PREPROCESS, stream),
                        "rasterize_gaussians_backward (per-Gaussian stage)")
     return dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations

@@ -278,7 +278,7 @@ class FramePipeline:
     def begin(self) -> None:
         """Orders the lanes behind the work already queued on the current stream."""
         ev = torch.cuda.current_stream(self.dev).record_event()
-        for st in self.streams:
+        for st in self.streams + ([self._feed] if hasattr(self, "_feed") else []):
             st.wait_event(ev)
 
     def enqueue(self, view_dev, slot: int = 0, tile_rows=None):
@@ -304,26 +304,69 @@ class FramePipeline:
             out = self.lanes[k].enqueue_graph(view_row)
         return k, out
 
-    def enqueue_host(self, host_cloud: dict, host_view, tanfov, out_host: torch.Tensor, slot: int = 0) -> int:
+    _ATTRS = ("means3D", "opacities", "scales", "rotations", "shs")
+
+    def _own_inputs(self, ln, rows: int) -> None:
+        """Private device copies of the Gaussian attributes for one lane (`rows` >= P rows each; the renderer reads
+        the first P)."""
+        if getattr(ln, "_in_rows", 0) == rows:
+            return
+        ln._in = {}
+        for n in self._ATTRS:
+            t = getattr(ln, n)
+            ln._in[n] = torch.empty((rows,) + tuple(t.shape[1:]), dtype=torch.float32, device=self.dev)
+            setattr(ln, n, ln._in[n][: ln.P])
+        ln._view_dev = (torch.empty(4, 4, device=self.dev), torch.empty(4, 4, device=self.dev),
+                        torch.empty(3, device=self.dev))
+        ln._in_rows = rows
+        ln._consumed = None  # event: the lane's last frame has read its inputs
+
+    def enqueue_host(self, host_cloud: dict, host_view, tanfov, out_host: torch.Tensor, slot: int = 0,
+                     group=None) -> int:
         """One frame whose inputs live in (pinned) HOST memory: uploads the Gaussian attributes and the camera of
         this frame on the lane's stream, renders, and downloads the image into `out_host` (pinned, (3,H,W)).
         Copies of one frame overlap the kernels of the frames on the other lanes.  Returns the lane index; the
-        image is valid once the lane's stream (or `end()` + the current stream) has been synchronised."""
+        image is valid once the lane's stream (or `end()` + the current stream) has been synchronised.
+
+        group (a torch.distributed process group of the GPUs of one node that all render views of the SAME cloud in
+        lock step -- the view-parallel orbit): the cloud crosses PCIe once per step and node instead of
+        once per rank: every rank uploads rows [r S, (r+1) S) of each attribute array (S = ceil(P / world)) and one
+        all-gather per array over NVLink completes the copy on every GPU."""
         k = self.count % len(self.lanes)
         self.count += 1
         ln = self.lanes[k]
-        if not getattr(ln, "_own_inputs", False):  # private device copies of the inputs for this lane
-            for n in ("means3D", "opacities", "scales", "rotations", "shs"):
-                setattr(ln, n, torch.empty_like(getattr(ln, n)))
-            ln._view_dev = (torch.empty(4, 4, device=self.dev), torch.empty(4, 4, device=self.dev),
-                            torch.empty(3, device=self.dev))
-            ln._own_inputs = True
+        if group is None:
+            self._own_inputs(ln, ln.P)
+            with torch.cuda.stream(self.streams[k]):
+                for n in self._ATTRS:
+                    getattr(ln, n).copy_(host_cloud[n], non_blocking=True)
+                for dst, src in zip(ln._view_dev, host_view):
+                    dst.copy_(src, non_blocking=True)
+                out = ln.enqueue(ln._view_dev + (tanfov[0], tanfov[1]), slot=slot)
+                out_host.copy_(out, non_blocking=True)
+            return k
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        S = (ln.P + world - 1) // world
+        self._own_inputs(ln, S * world)
+        if not hasattr(self, "_feed"):  # all collectives of this pipeline are issued from ONE stream, in step order
+            self._feed = torch.cuda.Stream(self.dev)
+        a, b = min(ln.P, rank * S), min(ln.P, (rank + 1) * S)
+        with torch.cuda.stream(self._feed):
+            if ln._consumed is not None:
+                self._feed.wait_event(ln._consumed)  # frame i - depth of this lane has read the old inputs
+            for n in self._ATTRS:
+                buf = ln._in[n]
+                if b > a:
+                    buf[a:b].copy_(host_cloud[n][a:b], non_blocking=True)
+                dist.all_gather_into_tensor(buf, buf[rank * S:(rank + 1) * S], group=group)
+            fed = self._feed.record_event()
         with torch.cuda.stream(self.streams[k]):
-            for n in ("means3D", "opacities", "scales", "rotations", "shs"):
-                getattr(ln, n).copy_(host_cloud[n], non_blocking=True)
+            self.streams[k].wait_event(fed)
             for dst, src in zip(ln._view_dev, host_view):
                 dst.copy_(src, non_blocking=True)
             out = ln.enqueue(ln._view_dev + (tanfov[0], tanfov[1]), slot=slot)
+            ln._consumed = self.streams[k].record_event()
             out_host.copy_(out, non_blocking=True)
         return k
 

@@ -142,6 +142,24 @@ def random_cloud(P: int, seed: int = 1, sh_degree: int = 3, extent: float = 1.0,
                 opacities=torch.from_numpy(op), shs=torch.from_numpy(sh), sh_degree=sh_degree)
 
 
+def pack_cloud(cloud: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """The same cloud without the SH coefficients that are zero for every point, and the SH degree that is left.
+    The reference's head stores a DC colour plus 12 zero coefficients per point and renders with degree 1
+    (models/model_v2.py:358-365); the rasterizer accepts any coefficient stride >= (degree + 1)^2, and terms with zero
+    coefficients add exactly 0, so the packed cloud renders the same frame bit for bit
+    (tests/test_gpu.py::test_packed_sh_without_zero_tail_renders_the_same_frame).  This is the layout gs_decode_head
+    emits; 56 instead of 200 bytes per point for the pcrender shape."""
+    sh = cloud["shs"]
+    nz = (sh != 0).flatten(2).any(2).any(0).nonzero()
+    used = int(nz.max()) + 1 if nz.numel() else 1
+    deg = 0 if used <= 1 else 1 if used <= 4 else 2 if used <= 9 else 3
+    deg = min(deg, int(cloud["sh_degree"]))
+    out = dict(cloud)
+    out["shs"] = sh[:, : (deg + 1) ** 2].contiguous()
+    out["sh_degree"] = deg
+    return out
+
+
 def tiny_cloud(P: int, seed: int = 0, sh_degree: int = 3, M: Optional[int] = None, spread: float = 0.6,
                scale: float = 0.05, opacity_lo: float = 0.05, depth_ties: bool = False) -> Dict[str, torch.Tensor]:
     """Small general-purpose test cloud around the origin (anisotropic, un-normalised quats, mixed opacity)."""

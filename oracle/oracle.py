@@ -208,7 +208,11 @@ class ReferenceCUDA:
         M = 0 if shs is None or shs.numel() == 0 else shs.shape[1]
         color = torch.zeros((3, H, W), dtype=torch.float32, device=means3D.device)
         radii = torch.zeros((P,), dtype=torch.int32, device=means3D.device)
-        torch.cuda.synchronize()
+        # The reference launches on the legacy default stream, which is torch's default stream: no synchronisation is
+        # needed (the reference's own binding has none, rasterize_points.cu:35-115).  Only a caller on a side stream
+        # has to be ordered in front of it.
+        if torch.cuda.current_stream(means3D.device) != torch.cuda.default_stream(means3D.device):
+            torch.cuda.current_stream(means3D.device).synchronize()
         R = self.lib.gsref_forward(self.state, C.c_int(P), C.c_int(sh_degree), C.c_int(M), self._dp(a["bg"]), C.c_int(W),
                                    C.c_int(H), self._dp(a["means3D"]), self._dp(a["shs"]), self._dp(a["colors_precomp"]),
                                    self._dp(a["opacities"]), self._dp(a["scales"]), C.c_float(scale_modifier),
@@ -221,7 +225,7 @@ class ReferenceCUDA:
                           scale_modifier=scale_modifier, radii=radii)
         return color, radii, R
 
-    def backward(self, dL_dcolor):
+    def backward(self, dL_dcolor, sync=True):
         import torch
         m = self._meta
         a, P, M = m["a"], m["P"], m["M"]
@@ -230,7 +234,8 @@ class ReferenceCUDA:
         g = dict(dL_dmeans2D=z(P, 3), dL_dconic=z(P, 2, 2), dL_dopacity=z(P, 1), dL_dcolors=z(P, 3),
                  dL_dmeans3D=z(P, 3), dL_dcov3D=z(P, 6), dL_dsh=z(P, M, 3), dL_dscales=z(P, 3), dL_drotations=z(P, 4))
         dpix = dL_dcolor.contiguous().float()
-        torch.cuda.synchronize()
+        if torch.cuda.current_stream(dev) != torch.cuda.default_stream(dev):
+            torch.cuda.current_stream(dev).synchronize()
         rc = self.lib.gsref_backward(
             self.state, C.c_int(P), C.c_int(m["D"]), C.c_int(M), self._dp(a["bg"]), C.c_int(m["W"]), C.c_int(m["H"]),
             self._dp(a["means3D"]), self._dp(a["shs"]), self._dp(a["colors_precomp"]), self._dp(a["scales"]),
@@ -241,7 +246,8 @@ class ReferenceCUDA:
             self._dp(g["dL_dsh"]), self._dp(g["dL_dscales"]), self._dp(g["dL_drotations"]), C.c_int(0))
         if rc != 0:
             raise RuntimeError("reference backward failed")
-        torch.cuda.synchronize()
+        if sync:
+            torch.cuda.synchronize()
         return g
 
     _DT = dict(depths=np.float32, means2D=np.float32, cov3D=np.float32, conic_opacity=np.float32, rgb=np.float32,
