@@ -304,6 +304,7 @@ def frames_leg_b200(name, dev, streams=4, steps=24):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
     fr = pipe.lanes[0]
+    fr.team_after = 0  # one frame at a time: latency mode
     single = _median_ms(lambda i: fr.enqueue(vdev[i % nv]), min(steps, 16), warm=2)
     for i in range(min(steps, fr.SLOTS)):
         if pipe.lanes[(2 * streams + i) % pipe.depth].status(i)[2] != 0:
@@ -485,6 +486,7 @@ def run_b200(args, rank, world):
     ms = max_over_ranks(ms, world, dev)
     frames_total = args.steps * (1 if tiles_mode else world)
     value = frames_total / (ms / 1e3)
+    fr.team_after = 0  # from here on lane 0 renders one frame at a time: latency mode (scheduling only, same results)
 
     # blend-kernel time: a separate, per-frame-synchronised pass (reading the events needs a sync per frame and
     # would serialise the main loop), same frames

@@ -235,7 +235,8 @@ int32_t gs_forward_recolor(const GsScene* scene, char* geometry, char* binning, 
     GsImage im(image, (size_t)f.s.width * f.s.height, f.gx, f.gy);
     GsBinning b(binning, 0, 0);  // only `list` (first array) is used
     // restart the blend work queue; everything else in the header stays as the frame left it
-    GS_CU(cudaMemsetAsync(&g.hdr->tickets[6], 0, sizeof(unsigned int), f.stream));
+    GS_CU(cudaMemsetAsync(&g.hdr->tickets[6], 0, 6 * sizeof(unsigned int), f.stream));  // blend queue + team counters (6-11)
+    GS_CU(cudaMemsetAsync(im.park_ready, 0, GS_PARK_CAP * sizeof(unsigned), f.stream));
     GS_STAGE(gs_launch_recolor(f, g));
     GS_STAGE(gs_launch_pack_extra(f, g));
     GS_STAGE(gs_launch_blend_forward(f, g, b, im, out_color));

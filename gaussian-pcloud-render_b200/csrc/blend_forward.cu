@@ -43,16 +43,31 @@
 // 0.63-0.69 ms.  What the per-unit timelines say: the long blocks are the FIRST units started, share their scheduler
 // with five other warps for the 250 us in which the queue of fresh units drains -- whatever their instruction-level
 // parallelism, they get a sixth of the issue slots -- and half of all unit-time is still outstanding at that point,
-// spread over ~1000 half-finished walks.  Shortening the frame below ~0.45 ms therefore needs the remaining walks
-// re-distributed over the idle warps (alpha digests handed from helper warps to the owning warp through L2), not a
-// faster walk; not built.
+// spread over ~1000 half-finished walks.  (4) That re-distribution was then built (TEAM variant below, opt-in through
+// GsScene.team_after): long walks are parked and finished by CTA teams -- six warps cull + evaluate alphas four
+// instances at a time, two warps apply them in list order with the reference's exact T / C recurrence, bit-identical
+// in every test.  Measured at C2 (profiles/r02b_blend_timeline_teams_c2.txt): a team finishes a block at 0.095 us per
+// surviving instance against 0.13 (lone warp) / 0.23 (warp under contention), i.e. the serial recurrence warp with its
+// in-order issue (~19 dependent-ish instructions per instance) is the new limit, and eight warps per block cost
+// 3x the warp-time of one; frame 0.594 ms at the best hand-over threshold (96 batches) against 0.602 without teams.
+// The distribution of work is the obstacle, not a few outliers: 400 of the 4888 blocks carry > 1200 surviving
+// instances (>= 150 us of dependent chain each), the queue of fresh blocks drains at ~220 us, and everything started
+// in its second half finishes late.  Off by default.
 //
 // Bound: FP32 issue, not HBM.  Algorithmic HBM bytes: 40*sum(need_t) + 20*N + 8*Tn.
+#include <cstdlib>
+
 #include "gs_common.cuh"
 
 namespace {
 
 #define BF_WARPS 8
+#ifndef BF_TEAM_AFTER
+#define BF_TEAM_AFTER 0   // library default of GsScene.team_after: 0 = teams off (measured: no gain at C2, see below)
+#endif
+#ifndef BF_TEAM_CTAS
+#define BF_TEAM_CTAS 1    // CTAs per SM that serve parked blocks from the start of the kernel (latency mode)
+#endif
 
 #ifdef GS_TIMELINE  // developer build only (make timeline): per-unit start/end time, SM, batches, hits
 __device__ unsigned long long* g_timeline = nullptr;
@@ -146,6 +161,440 @@ __device__ __forceinline__ float box4(float v) {
     return 0.25f * (h + __shfl_xor_sync(GS_FULL, h, 8));
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Teams (latency mode, template parameter TEAM): a pixel block whose list walk is still running after `team_after`
+// batches is parked by its warp (state of the 64 pixels to global memory) and finished by a CTA working as a team.
+// What one warp cannot shorten is the per-instance chain -- exponent, expf, tests, blend: ~58 dependent instructions
+// for the 64 pixels of a block -- so eight warps split it along the only cut that keeps the result bit for bit: the
+// alpha of an instance at a pixel does not depend on the compositing state, the transmittance recurrence does.
+// Warps 1..7 ("producers") walk the list, batch b to producer b mod 7: gather the records (cp.async, two batches in
+// flight per warp), cull against the block, evaluate alpha of every surviving instance for all 64 pixels with exactly
+// the operations of the warp-per-block path, two instances at a time, and append them to a shared-memory FIFO whose
+// entries are numbered in LIST order (the hit counts of the batches are chained from producer to producer).  Warp 0
+// (the "consumer") owns T, colour, done flags and contributor index of the 64 pixels and applies the FIFO batch by
+// batch with the reference's recurrence -- test_T = T (1 - alpha), stop test, C = fma(c alpha, T, C): ~25
+// instructions per instance instead of ~58, overlapped with the seven producers.  Flow control: a producer waits
+// until the FIFO has room for its whole batch (consumer's head counter) and until the consumer is less than two
+// rounds behind; the consumer waits for the batch flag of the producer whose turn it is.  When every pixel is done the
+// consumer raises `stop`.  The cull box shrinks to the live pixels as in the warp-per-block path (published by the
+// consumer; a producer that still sees the older, larger box only evaluates alphas the consumer then ignores).
+// Roles are given out by ARRIVAL order of the CTAs (first n_fresh arrivals work the fresh queue, later ones serve
+// parked blocks from the start), so a team CTA only ever waits for CTAs that are already running; a CTA that runs
+// out of fresh blocks becomes a team too.  Everybody leaves when all fresh CTAs are done and the parked queue is empty.
+#define TM_PROD 6    // producer warps (warps 2..7); warps 0 and 1 are the consumers of pixel rows 0-3 / 4-7 of the block
+#define TM_RING 128  // FIFO entries (power of two)
+#define TM_STAGES 2
+#define TM_FAR 0x40000000u  // a consumer whose pixels are all done reports "everything consumed"
+struct TmStage {
+    float4 a[32], b[32], c[32];
+};
+struct TmShared {
+    TmStage ring[TM_PROD][TM_STAGES];
+    float fa[2][TM_RING][32];    // alpha of the entry's instance at pixel (lane & 7, (lane >> 3) + 4 c) (0 = skip)
+    float4 fc[TM_RING];          // r, g, b, list position + 1
+    volatile unsigned tok_seq[8], tok_cum[8];  // producer q: tok_cum[q] = FIFO entry number of batch tok_seq[q]'s first hit
+    volatile unsigned bflag[8];                // producer q has published all its batches < bflag[q]
+    volatile unsigned bcnt[8][2];              // hits of producer q's batch, by round parity
+    volatile unsigned head[2], cbatch[2];      // per consumer: entries consumed, batches whose count it has read
+    volatile unsigned stop;
+    volatile float box[2][4];                  // per consumer: bounding box of its live pixels (x0 > x1: none)
+    unsigned slot;
+};
+
+#ifndef TM_SLEEP_NS
+#define TM_SLEEP_NS 0
+#endif
+__device__ __forceinline__ void tm_sleep() {
+#if TM_SLEEP_NS > 0
+    __nanosleep(TM_SLEEP_NS);
+#endif
+}
+__device__ __forceinline__ unsigned ldv(const unsigned* p) { return *reinterpret_cast<const volatile unsigned*>(p); }
+
+// alpha of instance j of a staged batch at the two pixels of this lane (0 = the reference skips it there)
+__device__ __forceinline__ float2 tm_alpha(const TmStage& st, int j, float pfx, f2 pfy2) {
+    const float4 ga = st.a[j], gb = st.b[j];
+    const float dx = ga.x - pfx;
+    const f2 dy2 = sub2(bc(ga.y), pfy2);
+    f2 t1 = mul2(bc(gb.x), dy2);
+    t1 = mul2(dy2, t1);
+    const float t2 = ga.z * dx, t3n = (-ga.w) * dx;
+    const f2 t3 = mul2(dy2, bc(t3n));
+    const f2 sm = fma2(bc(dx), bc(t2), t1);
+    const f2 p2 = fma2(sm, bc(-0.5f), t3);
+    const float pA = lo(p2), pB = hi(p2);
+    const float alphaA = fminf(0.99f, gb.y * expf(pA)), alphaB = fminf(0.99f, gb.y * expf(pB));
+    const bool okA = !(pA > 0.0f) && !(alphaA < 1.0f / 255.0f);
+    const bool okB = !(pB > 0.0f) && !(alphaB < 1.0f / 255.0f);
+    return make_float2(okA ? alphaA : 0.0f, okB ? alphaB : 0.0f);
+}
+
+struct TmPix {  // consumer state of one lane's pixel
+    float T, c0, c1, c2;
+    uint32_t last;
+    bool done;
+};
+// The warp-per-block path's blend step with ok = !done && (the alpha passed its tests), arranged so that the
+// loop-carried chain is done -> select -> multiply -> compare: the factor (1 - alpha) does not depend on the state
+// (a skipped pixel multiplies by exactly 1), the colour terms hang off the chain.  Same operations on the same
+// operands as the warp-per-block path: T (1 - alpha), the stop test, fma(c alpha, T, C).
+__device__ __forceinline__ void tm_apply(TmPix& s, float al, float4 gc) {
+    const float om = __fsub_rn(1.0f, al);  // 1 - alpha (alpha = 0: the instance skips this pixel)
+    const float T = s.T;
+    const float tt = __fmul_rn(T, s.done ? 1.0f : om);
+    const bool stop = tt < 0.0001f;  // T itself never is: only a hit can stop
+    s.done = s.done || stop;
+    s.T = stop ? T : tt;
+    const float a = s.done ? 0.0f : al;  // done before or stopped here
+    s.c0 = __fmaf_rn(__fmul_rn(gc.x, a), T, s.c0);
+    s.c1 = __fmaf_rn(__fmul_rn(gc.y, a), T, s.c1);
+    s.c2 = __fmaf_rn(__fmul_rn(gc.z, a), T, s.c2);
+    if (a != 0.0f) s.last = __float_as_uint(gc.w);
+}
+
+// bounding box of the live pixels of one consumer (rows ly0 .. ly0 + 3 of the block); x0 > x1 if none is live
+__device__ __forceinline__ unsigned tm_live_box(bool done, int bx0, int by0, float box[4]) {
+    const unsigned alive = __ballot_sync(GS_FULL, !done);
+    const unsigned cols = (alive | (alive >> 8) | (alive >> 16) | (alive >> 24)) & 0xffu;
+    unsigned rows = 0;
+#pragma unroll
+    for (int r = 0; r < 4; r++) rows |= ((alive >> (8 * r)) & 0xffu) ? (1u << r) : 0u;
+    if (alive) {
+        box[0] = (float)(bx0 + __ffs(cols) - 1); box[1] = (float)(bx0 + 31 - __clz(cols));
+        box[2] = (float)(by0 + __ffs(rows) - 1); box[3] = (float)(by0 + 31 - __clz(rows));
+    } else {
+        box[0] = 1.0f; box[1] = 0.0f; box[2] = 1.0f; box[3] = 0.0f;
+    }
+    return alive;
+}
+
+// One parked block, all eight warps of the CTA.  Called between two __syncthreads of the caller.
+__device__ __forceinline__ void team_block(TmShared& S, unsigned slot, const uint2* __restrict__ ranges,
+                                           const uint32_t* __restrict__ order, const uint32_t* __restrict__ list,
+                                           const GsRec* __restrict__ rec, int W, int H, int gx,
+                                           const float* __restrict__ bg, float* __restrict__ final_T,
+                                           uint32_t* __restrict__ n_contrib, const BfTargets& tg,
+                                           const uint2* __restrict__ park_units, const float* __restrict__ park_state) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lx = lane & 7, ly = lane >> 3;
+    const uint2 pu = __ldcg(park_units + slot);
+    const uint32_t unit = pu.x, base0 = pu.y;
+    const uint32_t tile = order[unit >> 2];
+    const int sub = unit & 3;
+    const int tile_x = tile % gx, tile_y = tile / gx;
+    const int bx0 = tile_x * GS_TILE + (sub & 1) * 8, by0 = tile_y * GS_TILE + (sub >> 1) * 8;
+    const uint2 range = ranges[tile];
+    const uint32_t total = range.y - range.x;
+    const uint32_t* __restrict__ lst = list + range.x;
+    const uint32_t first_b = base0 >> 5, nb = (total + 31u) >> 5;
+    const float* stp = park_state + (size_t)slot * GS_PARK_WORDS + lane;
+    if (warp < 2) {  // initial cull boxes from the saved done flags
+        const unsigned flags = __float_as_uint(__ldcg(stp + 320));
+        float box[4];
+        tm_live_box((flags >> warp) & 1u, bx0, by0 + 4 * warp, box);
+        if (lane < 4) S.box[warp][lane] = box[lane];
+    }
+    __syncthreads();
+#ifdef GS_TIMELINE
+    const unsigned long long tl_t0 = gtime();
+    unsigned tl_hits = 0;
+#endif
+    if (warp < 2) {
+        // ---------------------------------------------------------------- consumer c: pixel rows 4c .. 4c + 3
+        const int c = warp;
+        const int px = bx0 + lx, py = by0 + ly + 4 * c;
+        TmPix s;
+        s.T = __ldcg(stp + 32 * c);
+        s.c0 = __ldcg(stp + 64 + 32 * c); s.c1 = __ldcg(stp + 128 + 32 * c); s.c2 = __ldcg(stp + 192 + 32 * c);
+        s.last = __float_as_uint(__ldcg(stp + 256 + 32 * c));
+        s.done = (__float_as_uint(__ldcg(stp + 320)) >> c) & 1u;
+        const float (*fa)[32] = S.fa[c];
+        // The FIFO as a stream: `pub` entries are published (batch flags are looked at without waiting as long as
+        // entries are left), entries are applied four at a time -- eight loads in flight, four short dependent steps.
+        unsigned e = 0, pub = 0, groups = 0;
+        uint32_t bnext = first_b;
+        int q = 0, par = 0;
+        bool live = __any_sync(GS_FULL, !s.done);
+#ifdef GS_TIMELINE
+        long long tl_cwait = 0;
+#endif
+        while (live) {
+#ifdef GS_TIMELINE
+            const long long tl_c0 = clock64();
+#endif
+            while (bnext < nb) {
+                if (S.bflag[q] < bnext + 1u) {
+                    if (e < pub) break;
+                    continue;  // nothing left to apply: wait for the producer whose turn it is
+                }
+                pub += S.bcnt[q][par];
+                bnext++;
+                if (lane == 0) S.cbatch[c] = bnext;  // (a run of batches without hits must not stall the producers)
+                if (++q == TM_PROD) { q = 0; par ^= 1; }
+                if (pub - e >= 4u) break;
+            }
+#ifdef GS_TIMELINE
+            tl_cwait += clock64() - tl_c0;
+#endif
+            if (e == pub) break;  // bnext == nb: the list is finished
+            __syncwarp();
+            const unsigned n = min(pub - e, 4u);
+            float al[4];
+            float4 g[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const unsigned r = (e + (unsigned)u) & (TM_RING - 1);
+                al[u] = fa[r][lane];
+                g[u] = S.fc[r];
+                if ((unsigned)u >= n) {  // not published yet: applies as a no-op
+                    al[u] = 0.0f;
+                    g[u] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) tm_apply(s, al[u], g[u]);
+            e += n;
+#ifdef GS_TIMELINE
+            tl_hits += n;
+#endif
+            __syncwarp();
+            if (lane == 0) S.head[c] = e;
+            groups++;
+            if ((groups & 3u) == 0u) {
+                float box[4];
+                live = tm_live_box(s.done, bx0, by0 + 4 * c, box) != 0u;
+                if ((!live || (groups & 31u) == 0u) && lane < 4) S.box[c][lane] = box[lane];  // shrink the cull box
+            }
+        }
+        if (lane == 0) {  // this half of the block is finished: nothing more to wait for on its behalf
+            S.head[c] = TM_FAR; S.cbatch[c] = TM_FAR;
+            __threadfence_block();
+            if (S.head[c ^ 1] == TM_FAR) S.stop = 1u;  // both halves: producers still at work quit
+        }
+        // ---- epilogue (the stores of the warp-per-block path)
+        const float bg0 = bg[0], bg1 = bg[1], bg2 = bg[2];
+        const bool ins = px < W && py < H;
+        const float T = s.T;
+        const size_t pid = (size_t)W * py + px;
+        if (ins) { final_T[pid] = T; n_contrib[pid] = s.last; }
+        float o[3];
+        o[0] = s.c0 + T * bg0; o[1] = s.c1 + T * bg1; o[2] = s.c2 + T * bg2;
+        size_t oplane = (size_t)H * W, op = pid;
+        bool wr = ins;
+        if (tg.ds) {
+#pragma unroll
+            for (int k = 0; k < 3; k++) o[k] = box4(o[k]);
+            const int W2 = W >> 1;
+            oplane = (size_t)W2 * (H >> 1);
+            op = (size_t)W2 * (py >> 1) + (px >> 1);
+            wr = ins && (lane & 9) == 0;
+        }
+        if (wr) {
+            _Pragma("unroll") for (int k = 0; k < 8; k++) if (k < tg.n) {
+                float* oc = tg.img[k];
+                oc[op] = o[0]; oc[oplane + op] = o[1]; oc[2 * oplane + op] = o[2];
+            }
+        }
+#ifdef GS_TIMELINE
+        if (g_timeline && lane == 0 && c == 0) {
+            unsigned long long* tl = g_timeline + 12ull * unit;
+            tl[6] = tl_t0; tl[7] = gtime(); tl[8] = ((unsigned long long)(nb - first_b) << 32) | tl_hits;
+            tl[9] = (unsigned long long)tl_cwait;
+        }
+#endif
+    } else {
+        // ---------------------------------------------------------------- producer q: batches first_b + q, + 6, ...
+        const int q = warp - 2;
+        TmStage* __restrict__ ring = S.ring[q];
+        const int px = bx0 + lx, pyA = by0 + ly, pyB = by0 + ly + 4;
+        const float pfx = (float)px;
+        const f2 pfy2 = pk((float)pyA, (float)pyB);
+        uint32_t b = first_b + (uint32_t)q;
+#pragma unroll
+        for (int p = 0; p < TM_STAGES; p++) {
+            const uint32_t en = (b + (uint32_t)p * TM_PROD) * 32u + lane;
+            if (en < total) {
+                const GsRec* r = rec + lst[en];
+                cp_async16(&ring[p].a[lane], &r->a);
+                cp_async16(&ring[p].b[lane], &r->b);
+                cp_async16(&ring[p].c[lane], &r->c);
+            }
+            cp_async_commit();
+        }
+        int stage = 0, par = 0;
+        bool quit = false;
+#ifdef GS_TIMELINE
+        long long tl_rec = 0, tl_tok = 0, tl_room = 0, tl_eval = 0;
+        const long long tl_p0 = clock64();
+#endif
+        for (; b < nb; b += TM_PROD, par ^= 1) {
+            if (S.stop != 0u) break;
+#ifdef GS_TIMELINE
+            long long tl_a = clock64();
+#endif
+            cp_async_wait<TM_STAGES - 1>();
+            __syncwarp();
+#ifdef GS_TIMELINE
+            tl_rec += clock64() - tl_a;
+#endif
+            const TmStage& st = ring[stage];
+            const uint32_t base = b * 32u;
+            bool hit = false;
+            if (base + lane < total) {
+                const float4 a = st.a[lane], bb = st.b[lane];
+                const float nBA = st.c[lane].w;
+                // union of the two consumers' live boxes (an empty one has x0 > x1 and is ignored)
+                const float ax0 = S.box[0][0], ax1 = S.box[0][1], ay0 = S.box[0][2], ay1 = S.box[0][3];
+                const float bx0f = S.box[1][0], bx1f = S.box[1][1], by0f = S.box[1][2], by1f = S.box[1][3];
+                const bool ea = ax0 > ax1, eb = bx0f > bx1f;
+                const float x0 = ea ? bx0f : (eb ? ax0 : fminf(ax0, bx0f)), x1 = ea ? bx1f : (eb ? ax1 : fmaxf(ax1, bx1f));
+                const float y0 = ea ? by0f : (eb ? ay0 : fminf(ay0, by0f)), y1 = ea ? by1f : (eb ? ay1 : fmaxf(ay1, by1f));
+                const float bound = box_max_power(a.z, a.w, bb.x, nBA, bb.w, a.x - x1, a.x - x0, a.y - y1, a.y - y0);
+                hit = !(ea && eb) && !(bound < bb.z);
+            }
+            unsigned mask = __ballot_sync(GS_FULL, hit);
+            const unsigned cnt = __popc(mask);
+            // FIFO entry number of this batch's first hit: chained from the producer of the previous batch
+            unsigned cum = 0u;
+#ifdef GS_TIMELINE
+            tl_a = clock64();
+#endif
+            if (b != first_b) {
+                while (S.tok_seq[q] != b) {
+                    if (S.stop != 0u) { quit = true; break; }
+                    tm_sleep();
+                }
+                cum = S.tok_cum[q];
+            }
+            if (quit) break;
+            if (lane == 0) {
+                const int nq = (q + 1 == TM_PROD) ? 0 : q + 1;
+                S.tok_cum[nq] = cum + cnt;
+                __threadfence_block();
+                S.tok_seq[nq] = b + 1u;
+            }
+#ifdef GS_TIMELINE
+            tl_tok += clock64() - tl_a;
+            tl_a = clock64();
+#endif
+            // room for the whole batch, and both consumers have read this producer's record of two rounds ago
+            while (true) {
+                const unsigned head = min(S.head[0], S.head[1]), cb = min(S.cbatch[0], S.cbatch[1]);
+                if (cum + cnt - head <= (unsigned)TM_RING && !(b >= first_b + 2u * TM_PROD && cb + 2u * TM_PROD <= b)) break;
+                if (S.stop != 0u) { quit = true; break; }
+#ifdef TM_ROOM_SLEEP_NS
+                __nanosleep(TM_ROOM_SLEEP_NS);
+#else
+                tm_sleep();
+#endif
+            }
+            if (quit) break;
+#ifdef GS_TIMELINE
+            tl_room += clock64() - tl_a;
+            tl_a = clock64();
+#endif
+            unsigned e = cum;
+            while (mask) {  // four instances at a time: four independent exponent / expf chains
+                int j[4];
+                unsigned n = 0;
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    j[u] = mask ? __ffs(mask) - 1 : j[0];
+                    n += mask ? 1u : 0u;
+                    mask &= mask - 1;
+                }
+                float2 av[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) av[u] = tm_alpha(st, j[u], pfx, pfy2);
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    if ((unsigned)u < n) {
+                        const unsigned r = (e + (unsigned)u) & (TM_RING - 1);
+                        S.fa[0][r][lane] = av[u].x;
+                        S.fa[1][r][lane] = av[u].y;
+                        if (lane == u) {
+                            const float4 gc = st.c[j[u]];
+                            S.fc[r] = make_float4(gc.x, gc.y, gc.z, __uint_as_float(base + (uint32_t)j[u] + 1u));
+                        }
+                    }
+                }
+                e += n;
+            }
+            __syncwarp();  // every lane has written its alphas and read this stage's records
+#ifdef GS_TIMELINE
+            tl_eval += clock64() - tl_a;
+#endif
+            if (lane == 0) {
+                S.bcnt[q][par] = cnt;
+                __threadfence_block();
+                S.bflag[q] = b + 1u;
+            }
+            {
+                const uint32_t en = (b + (uint32_t)TM_STAGES * TM_PROD) * 32u + lane;
+                if (en < total) {
+                    const GsRec* r = rec + lst[en];
+                    cp_async16(&ring[stage].a[lane], &r->a);
+                    cp_async16(&ring[stage].b[lane], &r->b);
+                    cp_async16(&ring[stage].c[lane], &r->c);
+                }
+                cp_async_commit();
+            }
+            stage = (stage + 1 == TM_STAGES) ? 0 : stage + 1;
+        }
+        cp_async_wait<0>();
+#ifdef GS_TIMELINE
+        if (g_timeline && lane == 0 && q == 0) {
+            unsigned long long* tl = g_timeline + 12ull * unit;
+            tl[10] = ((unsigned long long)tl_rec << 32) | (unsigned long long)(tl_tok & 0xffffffff);
+            tl[11] = ((unsigned long long)tl_room << 32) | (unsigned long long)(tl_eval & 0xffffffff);
+            tl[5] = (unsigned long long)(clock64() - tl_p0);  // producer 0's total (overwrites the warp part's loop time)
+        }
+#endif
+    }
+}
+
+// Serves parked blocks until every fresh CTA is done and the parked queue is empty.  All eight warps of the CTA.
+__device__ __forceinline__ void team_serve(TmShared& S, GsHeader* __restrict__ hdr, unsigned n_fresh,
+                                           const unsigned* __restrict__ park_ready, const uint2* __restrict__ ranges,
+                                           const uint32_t* __restrict__ order, const uint32_t* __restrict__ list,
+                                           const GsRec* __restrict__ rec, int W, int H, int gx,
+                                           const float* __restrict__ bg, float* __restrict__ final_T,
+                                           uint32_t* __restrict__ n_contrib, const BfTargets& tg,
+                                           const uint2* __restrict__ park_units, const float* __restrict__ park_state) {
+    while (true) {
+        __syncthreads();  // the previous block is finished by everybody
+        if (threadIdx.x == 0) {
+            unsigned slot = 0xFFFFFFFFu;
+            while (true) {
+                const unsigned taken = ldv(&hdr->tickets[8]);
+                unsigned avail = min(ldv(&hdr->tickets[7]), (unsigned)GS_PARK_CAP);
+                if (taken < avail) {
+                    if (atomicCAS(&hdr->tickets[8], taken, taken + 1u) == taken) { slot = taken; break; }
+                    continue;
+                }
+                if (ldv(&hdr->tickets[9]) >= n_fresh) {  // nobody parks any more: is the count we compared with final?
+                    avail = min(ldv(&hdr->tickets[7]), (unsigned)GS_PARK_CAP);
+                    if (ldv(&hdr->tickets[8]) >= avail) break;
+                    continue;
+                }
+                __nanosleep(400);
+            }
+            if (slot != 0xFFFFFFFFu) {
+                while (ldv(park_ready + slot) == 0u) __nanosleep(100);  // the parking warp is still writing the state
+                __threadfence();
+            }
+            S.slot = slot;
+            S.head[0] = S.head[1] = 0u; S.cbatch[0] = S.cbatch[1] = 0u; S.stop = 0u;
+        }
+        if (threadIdx.x < 8) { S.tok_seq[threadIdx.x] = 0u; S.bflag[threadIdx.x] = 0u; }
+        __syncthreads();
+        const unsigned slot = S.slot;
+        if (slot == 0xFFFFFFFFu) break;
+        team_block(S, slot, ranges, order, list, rec, W, H, gx, bg, final_T, n_contrib, tg, park_units, park_state);
+    }
+}
+
 #ifndef BF_THR_TEST
 #define BF_THR_TEST 0
 #endif
@@ -159,13 +608,21 @@ __device__ __forceinline__ float box4(float v) {
 #ifndef BF_PX2_OCC
 #define BF_PX2_OCC 3
 #endif
-template <int K>
+template <int K, bool TEAM>
 __global__ void __launch_bounds__(BF_WARPS * 32, (K == 0) ? BF_PX2_OCC : 2) blend_forward_px2_kernel(
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ order, const uint32_t* __restrict__ list,
     const GsRec* __restrict__ rec, int W, int H, int gx, uint32_t num_tiles, GsHeader* __restrict__ hdr,
     const float* __restrict__ bg, float* __restrict__ final_T, uint32_t* __restrict__ n_contrib,
-    const BfTargets tg, const BfExtra ex, int quota) {
+    const BfTargets tg, const BfExtra ex, int quota, uint32_t park_at, uint2* __restrict__ park_units,
+    float* __restrict__ park_state, unsigned* __restrict__ park_ready, unsigned n_fresh) {
     extern __shared__ __align__(16) unsigned char s_ring_raw[];
+    static_assert(!TEAM || K == 0, "teams finish plain frames only");
+    __shared__ unsigned s_arrival;
+    if (TEAM) {  // roles by arrival order: a team CTA only ever waits for CTAs that are already running
+        if (threadIdx.x == 0) s_arrival = atomicAdd(&hdr->tickets[11], 1u);
+        __syncthreads();
+    }
+    const bool fresh = !TEAM || s_arrival < n_fresh;
     BfStage<K>(*s_ring)[BF_STAGES] = reinterpret_cast<BfStage<K>(*)[BF_STAGES]>(s_ring_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int lx = lane & 7, ly = lane >> 3;
@@ -180,7 +637,7 @@ __global__ void __launch_bounds__(BF_WARPS * 32, (K == 0) ? BF_PX2_OCC : 2) blen
     // Every warp serves at most `quota` units and the grid is sized for ~60 % of the CTA slots of the GPU: with several
     // frames in flight the short, latency-bound binning kernels of the next frames then find room next to this
     // kernel instead of waiting for its persistent CTAs to drain (+15 % frames/s at C2, same single-frame time).
-    for (int served = 0; served < quota; served++) {
+    for (int served = 0; fresh && served < quota; served++) {
         uint32_t unit = 0;
         if (lane == 0) unit = atomicAdd(q_fresh, 1u);
         unit = __shfl_sync(GS_FULL, unit, 0);
@@ -306,7 +763,14 @@ __global__ void __launch_bounds__(BF_WARPS * 32, (K == 0) ? BF_PX2_OCC : 2) blen
 
         int stage = 0;
         uint32_t next_check = BF_CHECK * 32;
+        uint32_t park_slot = GS_PARK_CAP, park_base = 0;
         for (uint32_t base = 0; base < total; base += 32) {
+            if (TEAM && base == park_at) {  // a long walk: hand the block over to a team (if the queue has room)
+                unsigned slot = 0;
+                if (lane == 0) slot = atomicAdd(&hdr->tickets[7], 1u);
+                slot = __shfl_sync(GS_FULL, slot, 0);
+                if (slot < GS_PARK_CAP) { park_slot = slot; park_base = base; break; }
+            }
             if (base == next_check) {  // shrink the cull box to the pixels that are still live
                 next_check += BF_CHECK * 32;
                 const unsigned aliveA = __ballot_sync(GS_FULL, !doneA), aliveB = __ballot_sync(GS_FULL, !doneB);
@@ -421,9 +885,33 @@ __global__ void __launch_bounds__(BF_WARPS * 32, (K == 0) ? BF_PX2_OCC : 2) blen
             if (__all_sync(GS_FULL, doneA && doneB)) break;
         }
         cp_async_wait<0>();
+        if (TEAM && park_slot < GS_PARK_CAP) {  // state of the 64 pixels, word-major so that the stores coalesce
+            float* st = park_state + (size_t)park_slot * GS_PARK_WORDS + lane;
+            st[0] = lo(T2); st[32] = hi(T2);
+            st[64] = c0A; st[96] = c0B; st[128] = c1A; st[160] = c1B; st[192] = c2A; st[224] = c2B;
+            st[256] = __uint_as_float(lastA); st[288] = __uint_as_float(lastB);
+            st[320] = __uint_as_float((doneA ? 1u : 0u) | (doneB ? 2u : 0u));
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) {
+                park_units[park_slot] = make_uint2(unit, park_base);
+                __threadfence();
+                *reinterpret_cast<volatile unsigned*>(park_ready + park_slot) = 1u;
+            }
+#ifdef GS_TIMELINE
+            if (g_timeline && lane == 0) {
+                unsigned long long* tl = g_timeline + 12ull * unit;
+                tl[0] = tl_t0; tl[1] = gtime();
+                tl[2] = ((unsigned long long)smid() << 32) | total;
+                tl[3] = ((unsigned long long)tl_batches << 32) | tl_hits;
+                tl[4] = (unsigned long long)tl_wait; tl[5] = (unsigned long long)tl_loop;
+            }
+#endif
+            continue;
+        }
 #ifdef GS_TIMELINE
         if (g_timeline && lane == 0) {
-            unsigned long long* tl = g_timeline + 6ull * unit;
+            unsigned long long* tl = g_timeline + 12ull * unit;
             tl[0] = tl_t0; tl[1] = gtime();
             tl[2] = ((unsigned long long)smid() << 32) | total;
             tl[3] = ((unsigned long long)tl_batches << 32) | tl_hits;
@@ -481,25 +969,39 @@ __global__ void __launch_bounds__(BF_WARPS * 32, (K == 0) ? BF_PX2_OCC : 2) blen
             }
         }
     }
+    if (TEAM) {
+        __syncthreads();  // every warp of this CTA is out of fresh blocks: the record rings are free
+        if (fresh && threadIdx.x == 0) {
+            __threadfence();
+            atomicAdd(&hdr->tickets[9], 1u);  // this CTA parks nothing any more
+        }
+        TmShared& S = *reinterpret_cast<TmShared*>(s_ring_raw);
+        team_serve(S, hdr, n_fresh, park_ready, ranges, order, list, rec, W, H, gx, bg, final_T, n_contrib, tg, park_units,
+                   park_state);
+    }
 }
 
-GsPerDevice g_blend_dev[4];  // per extra-pass count K: value[0] = resident CTAs of the kernel on this device
+// per extra-pass count K (index 4: the K = 0 kernel with teams): value[0] = resident CTAs of the kernel on this
+// device, value[1] = default hand-over threshold
+GsPerDevice g_blend_dev[5];
 
-template <int K>
+template <int K, bool TEAM>
 cudaError_t launch_blend(const GsFrame& f, const GsGeom& g, const GsBinning& b, const GsImage& im, float* out_color,
-                         uint32_t num_tiles) {
-    const size_t smem = sizeof(BfStage<K>) * BF_STAGES * BF_WARPS;
+                         uint32_t num_tiles, int team_after) {
+    const size_t ring_bytes = sizeof(BfStage<K>) * BF_STAGES * BF_WARPS;
+    const size_t smem = TEAM && sizeof(TmShared) > ring_bytes ? sizeof(TmShared) : ring_bytes;  // teams alias the rings
     const int* dv = nullptr;
     {
-        cudaError_t e = g_blend_dev[K].get(&dv, [smem](int dev, int* v) {
+        cudaError_t e = g_blend_dev[TEAM ? 4 : K].get(&dv, [smem](int dev, int* v) {
             int sms = 0, per_sm = 0;
             cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
             if (e != cudaSuccess) return e;
-            e = cudaFuncSetAttribute(blend_forward_px2_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            e = cudaFuncSetAttribute(blend_forward_px2_kernel<K, TEAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
-            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, blend_forward_px2_kernel<K>, BF_WARPS * 32, smem);
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, blend_forward_px2_kernel<K, TEAM>, BF_WARPS * 32, smem);
             if (e != cudaSuccess) return e;
             v[0] = sms * (per_sm > 0 ? per_sm : 1);
+            v[1] = sms;
             return cudaSuccess;
         });
         if (e != cudaSuccess) return e;
@@ -512,16 +1014,32 @@ cudaError_t launch_blend(const GsFrame& f, const GsGeom& g, const GsBinning& b, 
     BfExtra ex;
     ex.xrec = g.xrec;
     for (int k = 0; k < 3; k++) ex.out[k] = f.s.extra_out[k];
-    // grid x 8 warps x quota covers the upper bound of units (4 per tile); quota >= 16, grid <= 60 % of the slots
     const uint32_t units_max = num_tiles * 4u;
-    const uint32_t slots = (uint32_t)((resident * BF_SLOT_NUM + BF_SLOT_DEN - 1) / BF_SLOT_DEN);
-    uint32_t quota = (units_max + BF_WARPS * slots - 1) / (BF_WARPS * slots);
-    if (quota < 16u) quota = 16u;
-    const unsigned grid = (units_max + BF_WARPS * quota - 1) / (BF_WARPS * quota);
-    blend_forward_px2_kernel<K><<<grid, BF_WARPS * 32, smem, f.stream>>>(im.ranges, im.order, b.list, g.rec, f.s.width,
-                                                                        f.s.height, f.gx, num_tiles, g.hdr,
-                                                                        f.s.background, im.final_T, im.n_contrib, tg, ex,
-                                                                        (int)quota);
+    unsigned grid, n_fresh;
+    uint32_t quota;
+    if (TEAM) {
+        // latency mode: the whole GPU is this frame's; BF_TEAM_CTAS CTAs per SM serve parked blocks from the start, the
+        // others work the fresh queue (and become teams when it is empty).  The grid is never larger than what is
+        // resident at once, and roles go by arrival order, so a team never waits for a CTA that cannot start.
+        const unsigned teams = (unsigned)dv[1] * BF_TEAM_CTAS < (unsigned)resident ? (unsigned)dv[1] * BF_TEAM_CTAS
+                                                                                     : (unsigned)resident / 2u;
+        n_fresh = (unsigned)resident - teams;
+        quota = (units_max + BF_WARPS * n_fresh - 1) / (BF_WARPS * n_fresh);
+        if (quota < 4u) quota = 4u;
+        n_fresh = (units_max + BF_WARPS * quota - 1) / (BF_WARPS * quota);
+        grid = n_fresh + teams;
+    } else {
+        // grid x 8 warps x quota covers the upper bound of units (4 per tile); quota >= 16, grid <= 60 % of the slots
+        const uint32_t slots = (uint32_t)((resident * BF_SLOT_NUM + BF_SLOT_DEN - 1) / BF_SLOT_DEN);
+        quota = (units_max + BF_WARPS * slots - 1) / (BF_WARPS * slots);
+        if (quota < 16u) quota = 16u;
+        grid = (units_max + BF_WARPS * quota - 1) / (BF_WARPS * quota);
+        n_fresh = grid;
+    }
+    const uint32_t park_at = TEAM ? (uint32_t)team_after * 32u : 0xFFFFFFFFu;
+    blend_forward_px2_kernel<K, TEAM><<<grid, BF_WARPS * 32, smem, f.stream>>>(
+        im.ranges, im.order, b.list, g.rec, f.s.width, f.s.height, f.gx, num_tiles, g.hdr, f.s.background, im.final_T,
+        im.n_contrib, tg, ex, (int)quota, park_at, im.park_units, im.park_state, im.park_ready, n_fresh);
     gs_note_launch();
     return cudaGetLastError();
 }
@@ -532,11 +1050,23 @@ cudaError_t gs_launch_blend_forward(const GsFrame& f, const GsGeom& g, const GsB
                                     float* out_color) {
     const uint32_t num_tiles = (uint32_t)f.gx * (uint32_t)(f.row1 - f.row0);
     if (num_tiles == 0) return cudaSuccess;
+    // Teams (latency mode): GsScene.team_after > 0 = hand-over threshold in batches, 0 = library default
+    // (BF_TEAM_AFTER, or the environment variable GSPLAT_B200_TEAM_AFTER), < 0 = off (throughput mode)
+    int after = f.s.team_after;
+    if (after == 0) {
+        static const int env_after = [] {
+            const char* e = getenv("GSPLAT_B200_TEAM_AFTER");
+            return e ? atoi(e) : BF_TEAM_AFTER;
+        }();
+        after = env_after;
+    }
     switch (f.s.num_extra) {
-        case 1: return launch_blend<1>(f, g, b, im, out_color, num_tiles);
-        case 2: return launch_blend<2>(f, g, b, im, out_color, num_tiles);
-        case 3: return launch_blend<3>(f, g, b, im, out_color, num_tiles);
-        default: return launch_blend<0>(f, g, b, im, out_color, num_tiles);
+        case 1: return launch_blend<1, false>(f, g, b, im, out_color, num_tiles, 0);
+        case 2: return launch_blend<2, false>(f, g, b, im, out_color, num_tiles, 0);
+        case 3: return launch_blend<3, false>(f, g, b, im, out_color, num_tiles, 0);
+        default:
+            if (after > 0) return launch_blend<0, true>(f, g, b, im, out_color, num_tiles, after);
+            return launch_blend<0, false>(f, g, b, im, out_color, num_tiles, 0);
     }
 }
 

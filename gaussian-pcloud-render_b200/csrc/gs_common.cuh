@@ -25,6 +25,8 @@
 //     tcount [Tn] u32     instances per tile (column histogram of the row items)   } frame
 //     final_T [N] f32, n_contrib [N] u32, ranges [Tn] uint2, order [Tn] u32 (longest-list-first tile queue),
 //     tile_start [Tn+1] u32
+//     park_units [GS_PARK_CAP] uint2 (unit, list position), park_state [GS_PARK_CAP][12][32] f32: pixel blocks whose
+//     list walk the blend kernel handed over to the team kernel (blend_forward.cu)
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -51,7 +53,8 @@ struct GsHeader {  // lives at offset 0 of the geometry buffer
     unsigned int skip;           // 1 = instance / row-item capacity exceeded (no-sync mode): the frame is skipped
     unsigned int pad0;
     unsigned int tickets[16];    // 0-3 depth-sort passes, 4 row pass, 5 column pass, 6 blend work queue,
-                                 // 10 blend-backward work queue
+                                 // 7 parked blend units (count), 8 parked units taken by teams, 9 fresh CTAs done,
+                                 // 10 blend-backward work queue, 11 CTA arrival order of the blend kernel
     unsigned int pad[40];
 };
 static_assert(sizeof(GsHeader) == 256, "header is one aligned slot");
@@ -78,6 +81,8 @@ struct GsCarver {
 #endif
 #define GS_PART_CHUNK 2048   // items per CTA of the row / column partition passes
 #define GS_MAX_GRID 256      // at most 256 x 256 tiles (4096 x 4096 pixels)
+#define GS_PARK_CAP 2048     // pixel blocks per frame that can be handed to the blend team kernel
+#define GS_PARK_WORDS 384    // saved state of one pixel block: 12 words x 32 lanes
 
 static inline __host__ __device__ size_t gs_div_up(size_t a, size_t b) { return (a + b - 1) / b; }
 
@@ -148,23 +153,29 @@ struct GsBinning {
 struct GsImage {
     int* rdiff;        // [gy+1]
     uint32_t* tcount;  // [Tn]
+    unsigned* park_ready;   // [GS_PARK_CAP] 1 = the state of the parked block is written (zeroed every frame)
     float* final_T;
     uint32_t* n_contrib;
     uint2* ranges;
     uint32_t* order;  // tiles of the shard, longest instance list first (blend work queue)
     uint32_t* tile_start;   // [Tn+1]
+    uint2* park_units;      // [GS_PARK_CAP]
+    float* park_state;      // [GS_PARK_CAP][GS_PARK_WORDS]
     size_t zero_bytes, bytes;
     __host__ __device__ GsImage(char* base, size_t N, size_t gx, size_t gy) {
         GsCarver c(base);
         const size_t Tn = gx * gy;
         rdiff = c.take<int>(gy + 1);
         tcount = c.take<uint32_t>(Tn);
+        park_ready = c.take<unsigned>(GS_PARK_CAP);
         zero_bytes = c.off;
         final_T = c.take<float>(N);
         n_contrib = c.take<uint32_t>(N);
         ranges = c.take<uint2>(Tn);
         order = c.take<uint32_t>(Tn);
         tile_start = c.take<uint32_t>(Tn + 1);
+        park_units = c.take<uint2>(GS_PARK_CAP);
+        park_state = c.take<float>((size_t)GS_PARK_CAP * GS_PARK_WORDS);
         bytes = c.off + GS_ALIGN;
     }
 };

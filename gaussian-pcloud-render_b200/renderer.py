@@ -22,10 +22,14 @@ class FrameRenderer:
 
     def __init__(self, cloud: dict, width: int, height: int, bg, device, capacity: int = 0, headroom: float = 1.3,
                  tile_rows: Optional[Tuple[int, int]] = None, share: Optional["FrameRenderer"] = None,
-                 downsample: int = 1):
+                 downsample: int = 1, team_after: int = 0):
         """downsample=2: width x height is the (super-sampled) raster size, every output image is the 2x2 box mean
-        (3, height/2, width/2) -- the reference caller's bilinear x0.5, done in the blend epilogue."""
+        (3, height/2, width/2) -- the reference caller's bilinear x0.5, done in the blend epilogue.
+        team_after: blend scheduling hint (GsScene.team_after; results never change): > 0 = list walks longer than
+        that many batches are finished by CTA teams (a latency experiment, see csrc/blend_forward.cu), 0 = library
+        default (off), -1 = off."""
         self.L = _C.lib()
+        self.team_after = int(team_after)
         if downsample not in (1, 2) or (downsample == 2 and (int(width) % 2 or int(height) % 2)):
             raise ValueError("downsample must be 1 or 2 (2 needs an even raster size)")
         self.downsample = int(downsample)
@@ -68,7 +72,7 @@ class FrameRenderer:
                              colors_precomp=None, opacities=self.opacities, scales=self.scales,
                              rotations=self.rotations, cov3D_precomp=None, viewmatrix=viewmatrix,
                              projmatrix=projmatrix, campos=campos, tile_rows=tile_rows, peer_out=peer_out,
-                             extra_passes=extra_passes, downsample=self.downsample)
+                             extra_passes=extra_passes, downsample=self.downsample, team_after=self.team_after)
 
     def upload_view(self, view):
         """host View (scenes.make_view) -> device tensors; done once per camera, outside the frame loop."""
@@ -133,7 +137,7 @@ class FrameRenderer:
                               opacities=self.opacities, scales=self.scales, rotations=self.rotations,
                               cov3D_precomp=None, viewmatrix=viewmatrix, projmatrix=projmatrix, campos=campos,
                               tile_rows=tile_rows if tile_rows is not None else self.tile_rows,
-                              downsample=self.downsample)
+                              downsample=self.downsample, team_after=self.team_after)
         with torch.cuda.device(self.dev):
             st = torch.cuda.current_stream(self.dev).cuda_stream
             _C._check(self.L.gs_forward_recolor(C.byref(scene), self.geom.data_ptr(), self.binning.data_ptr(),
@@ -255,7 +259,8 @@ class FramePipeline:
         self.lanes = []
         for k in range(max(1, int(depth))):
             self.lanes.append(FrameRenderer(cloud, width, height, bg, device, capacity=capacity, headroom=headroom,
-                                            share=self.lanes[0] if self.lanes else None, downsample=downsample))
+                                            share=self.lanes[0] if self.lanes else None, downsample=downsample,
+                                            team_after=-1 if int(depth) > 1 else 0))  # frames in flight: throughput mode
         self.dev = self.lanes[0].dev
         with torch.cuda.device(self.dev):
             self.streams = [torch.cuda.Stream(self.dev) for _ in self.lanes]

@@ -83,7 +83,11 @@ typedef struct GsScene {
      * (simple_raw_render.py:411-522).  extra_out[k] receives exactly the image a separate forward with
      * colors_precomp = extra_colors[k] would produce. */
     int32_t num_extra;
-    int32_t reserved2;
+    /* Blend scheduling hint; never changes a result.  > 0: a pixel block whose list walk is still running after
+     * `team_after` batches of 32 instances is parked by its warp and finished by a CTA working as a team (six warps
+     * cull and evaluate alphas, two apply them in list order with the reference's recurrence).  0 = library default
+     * (off: measured neutral at the benchmark shapes, csrc/blend_forward.cu), < 0 = off. */
+    int32_t team_after;
     const float* extra_colors[3];  /* each [P][3] */
     float* extra_out[3];           /* each [3][H][W] */
 } GsScene;

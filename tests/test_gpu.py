@@ -902,3 +902,42 @@ def test_two_streams_one_device_no_grad_frames_do_not_share_scratch():
     torch.cuda.synchronize()
     for a, b in zip(got, want):
         assert torch.equal(a, b)
+
+
+def test_team_mode_is_bit_identical_to_the_default_schedule():
+    """GsScene.team_after (blend scheduling hint): long list walks parked and finished by CTA teams must give the frame of
+    the default schedule bit for bit -- image, final T and contributor counts.  Runs in a child process with a time
+    limit: the team path synchronises warps through shared-memory flags, and a regression there would hang, not fail."""
+    _dev()
+    import subprocess
+    import sys
+    from conftest import ROOT
+    code = r"""
+import sys, torch
+sys.path.insert(0, %r); sys.path.insert(0, %r + '/gaussian-pcloud-render_b200')
+import scenes
+from diff_gaussian_rasterization import _C
+from renderer import FrameRenderer
+dev = torch.device('cuda:0')
+cl = scenes.human_cloud(400000, scale_factor=448.0, seed=3)
+ok = True
+for W, H, ds in ((1280, 720, 1), (640, 360, 2)):
+    for k in (2, 7):
+        v = scenes.make_view(scenes.orbit_c2w(12)[k], W, H)
+        ref = FrameRenderer(cl, W, H, [1, 1, 1], dev, capacity=12_000_000, downsample=ds, team_after=-1)
+        vd = ref.upload_view(v)
+        a = ref.render(vd).clone()
+        sc = ref._scene(vd, None)
+        ta = _C.fetch('final_T', sc, ref.geom, ref.binning, ref.img, ref.capacity)
+        na = _C.fetch('n_contrib', sc, ref.geom, ref.binning, ref.img, ref.capacity)
+        for after in (1, 8, 40):
+            fr = FrameRenderer(cl, W, H, [1, 1, 1], dev, capacity=12_000_000, downsample=ds, team_after=after)
+            b = fr.render(vd)
+            sc = fr._scene(vd, None)
+            tb = _C.fetch('final_T', sc, fr.geom, fr.binning, fr.img, fr.capacity)
+            nb = _C.fetch('n_contrib', sc, fr.geom, fr.binning, fr.img, fr.capacity)
+            ok = ok and torch.equal(a, b) and torch.equal(ta, tb) and torch.equal(na, nb)
+print('TEAM OK' if ok else 'TEAM MISMATCH')
+""" % (ROOT, ROOT)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=240)
+    assert "TEAM OK" in out.stdout, out.stdout[-1500:] + out.stderr[-1500:]

@@ -55,7 +55,8 @@ rows = sharding.balanced_rows(np.ones(gy) + np.arange(gy) % 3, world)
 def grads(tile_rows, group):
     d = {k: cl[k].to(dev).requires_grad_(True) for k in ("means3D", "opacities", "scales", "rotations", "shs")}
     color, _ = GaussianRasterizer(rs, tile_rows=tile_rows, grad_group=group)(
-        d["means3D"], None, d["opacities"], shs=d["shs"], scales=d["scales"], rotations=d["rotations"])
+        d["means3D"], torch.zeros_like(d["means3D"], requires_grad=True), d["opacities"], shs=d["shs"],
+        scales=d["scales"], rotations=d["rotations"])
     color.backward(wgt)
     return {k: x.grad for k, x in d.items()}
 
