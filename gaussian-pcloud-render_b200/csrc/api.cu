@@ -350,9 +350,15 @@ int64_t gs_fetch(const GsScene* scene, const char* geometry, const char* binning
     GsBinning b(const_cast<char*>(binning), R, 0);
     const void* src = nullptr;
     size_t n = 0;
+    unsigned side = 0;
+    if (!strncmp(name, "sorted_", 7)) {  // which side of the ping-pong holds the depth order (GsHeader::sort_side[3])
+        GS_CU(cudaMemcpyAsync(&side, &g.hdr->sort_side[3], sizeof(side), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+        GS_CU(cudaStreamSynchronize((cudaStream_t)stream));
+        side &= 1u;
+    }
     if (!strcmp(name, "records")) { src = g.rec; n = sizeof(GsRec) * P; }
-    else if (!strcmp(name, "sorted_idx")) { src = g.idx[0]; n = 4 * P; }
-    else if (!strcmp(name, "sorted_key")) { src = g.key[0]; n = 4 * P; }
+    else if (!strcmp(name, "sorted_idx")) { src = g.idx[side]; n = 4 * P; }
+    else if (!strcmp(name, "sorted_key")) { src = g.key[side]; n = 4 * P; }
     else if (!strcmp(name, "cov3D")) { src = g.cov3D; n = 24 * P; }
     else if (!strcmp(name, "clamped")) { src = g.clamp; n = P; }
     else if (!strcmp(name, "tiles_touched")) { src = g.ntile; n = 4 * P; }

@@ -241,13 +241,20 @@ __global__ void __launch_bounds__(1024) depth_hist_kernel(const uint32_t* __rest
 #ifndef SORT_MIN_BLOCKS
 #define SORT_MIN_BLOCKS 2  // <= 64 registers: leaves room for blend CTAs of other frames next to a sort CTA (+6 % frames/s)
 #endif
-__global__ void __launch_bounds__(SORT_THREADS, SORT_MIN_BLOCKS) depth_pass_kernel(const uint32_t* __restrict__ key_in,
-                                                                  const uint32_t* __restrict__ idx_in,
-                                                                  uint32_t* __restrict__ key_out,
-                                                                  uint32_t* __restrict__ idx_out,
+__global__ void __launch_bounds__(SORT_THREADS, SORT_MIN_BLOCKS) depth_pass_kernel(uint32_t* __restrict__ key0,
+                                                                  uint32_t* __restrict__ idx0,
+                                                                  uint32_t* __restrict__ key1,
+                                                                  uint32_t* __restrict__ idx1,
                                                                   const uint32_t* __restrict__ hist,  // 256 totals
                                                                   const GsChain chain, unsigned* __restrict__ ticket,
-                                                                  uint32_t P, int shift, int first_pass) {
+                                                                  GsHeader* __restrict__ hdr, uint32_t P, int pass) {
+    // input side of the ping-pong = where the previous pass left its output (preprocess writes the keys to side 0)
+    const int shift = pass * GS_RADIX_BITS, first_pass = pass == 0;
+    const unsigned side = first_pass ? 0u : hdr->sort_side[pass - 1];
+    const uint32_t* __restrict__ key_in = side ? key1 : key0;
+    const uint32_t* __restrict__ idx_in = side ? idx1 : idx0;
+    uint32_t* __restrict__ key_out = side ? key0 : key1;
+    uint32_t* __restrict__ idx_out = side ? idx0 : idx1;
     extern __shared__ __align__(16) uint32_t s_sort[];
     uint32_t* s_key = s_sort;                                // [GS_SORT_CHUNK] keys in digit order
     uint32_t* s_val = s_key + GS_SORT_CHUNK;                 // [GS_SORT_CHUNK]
@@ -269,16 +276,21 @@ __global__ void __launch_bounds__(SORT_THREADS, SORT_MIN_BLOCKS) depth_pass_kern
     const uint32_t tl_slot = (uint32_t)(shift / 8) * 1024u + chunk;
     BIN_MARK(tl_slot, 0);
     // A digit shared by ALL keys makes the pass the identity permutation (the top byte of the depths of an object
-    // that lies within one binade of camera distance, e.g. every frame of C1-C3): copy the chunk, skip ranking and
-    // chain.  The global histogram is complete before this kernel starts, so every CTA takes the same branch.
+    // that lies within one binade of camera distance, e.g. every frame of C1-C3): nothing moves, the output side is
+    // the input side (only the first pass still has to write the index column).  The global histogram is complete
+    // before this kernel starts, so every CTA takes the same branch.
     if (hist[(key_in[0] >> shift) & 255u] == P) {
-        const uint32_t beg = chunk * GS_SORT_CHUNK, n = min((uint32_t)GS_SORT_CHUNK, P - beg);
-        for (uint32_t t = tid; t < n; t += SORT_THREADS) {
-            key_out[beg + t] = key_in[beg + t];
-            idx_out[beg + t] = first_pass ? beg + t : idx_in[beg + t];
+        if (first_pass) {
+            const uint32_t beg = chunk * GS_SORT_CHUNK, n = min((uint32_t)GS_SORT_CHUNK, P - beg);
+            for (uint32_t t = tid; t < n; t += SORT_THREADS) {
+                key_out[beg + t] = key_in[beg + t];
+                idx_out[beg + t] = beg + t;
+            }
         }
+        if (chunk == 0 && tid == 0) hdr->sort_side[pass] = first_pass ? 1u : side;
         return;
     }
+    if (chunk == 0 && tid == 0) hdr->sort_side[pass] = side ^ 1u;
 
     uint32_t k[SORT_ROUNDS], v[SORT_ROUNDS];
     uint16_t rk[SORT_ROUNDS];
@@ -367,10 +379,13 @@ __global__ void __launch_bounds__(SORT_THREADS, SORT_MIN_BLOCKS) depth_pass_kern
 // (Replaces a chained look-back inside the row pass: with a few hundred chunks that are all resident at once every
 // chunk had to add up all its predecessors' counters -- O(chunks^2) reads of the same hot rows, 18 us per chunk.)
 template <int NB>
-__global__ void __launch_bounds__(256) row_count_kernel(const uint32_t* __restrict__ sorted_idx,
+__global__ void __launch_bounds__(256) row_count_kernel(const uint32_t* __restrict__ idx0,
+                                                        const uint32_t* __restrict__ idx1,
+                                                        const GsHeader* __restrict__ hdr,
                                                         const ushort4* __restrict__ rect, uint32_t P, int gy,
                                                         uint32_t* __restrict__ chunk_cnt /*[gy][nchunks]*/) {
     constexpr int G = NB / 32;
+    const uint32_t* __restrict__ sorted_idx = hdr->sort_side[3] ? idx1 : idx0;  // output side of the depth sort
     __shared__ int s_d[NB + 1];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t chunk = blockIdx.x, nchunks = gridDim.x;
@@ -585,7 +600,8 @@ __global__ void __launch_bounds__(1024) plan_kernel(const uint32_t* __restrict__
 #endif
 template <int NB, int PASS>
 __global__ void __launch_bounds__(256, (NB == 128) ? PART_MIN_BLOCKS : 2) range_partition_kernel(
-    const uint32_t* __restrict__ sorted_idx, const ushort4* __restrict__ rect, uint32_t P,  // PASS 1 input
+    const uint32_t* __restrict__ idx0, const uint32_t* __restrict__ idx1,  // PASS 1 input: the depth order (either side)
+    const ushort4* __restrict__ rect, uint32_t P,
     const uint2* __restrict__ items_in,                                                      // PASS 2 input
     const int* __restrict__ rdiff, int gx, int gy, const uint32_t* __restrict__ tile_start,
     unsigned long long RowCap, const uint32_t* __restrict__ chunk_base /*[chunks][GS_MAX_GRID]*/,
@@ -600,6 +616,7 @@ __global__ void __launch_bounds__(256, (NB == 128) ? PART_MIN_BLOCKS : 2) range_
     __shared__ uint32_t s_chunk;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (PASS == 2 && hdr->skip) return;
+    const uint32_t* __restrict__ sorted_idx = (PASS == 1 && hdr->sort_side[3]) ? idx1 : idx0;
     if (warp == 0) row_tables(rdiff, gy, s_rs, s_cf, lane);
     __syncthreads();
     if ((unsigned long long)s_rs[gy] > RowCap) {  // no-sync mode: row-item buffer too small -> frame is skipped
@@ -779,19 +796,16 @@ cudaError_t gs_launch_depth_sort(const GsFrame& f, const GsGeom& g) {
     depth_hist_kernel<<<(unsigned)min((size_t)HIST_CTAS, gs_div_up(P, 4096)), 1024, 0, f.stream>>>(g.key[0], P, g.dhist);
     gs_note_launch();
     GS_TRY(cudaGetLastError());
-    int side = 0;
     for (int pass = 0; pass < 4; pass++) {
         const GsChain ch = {g.dstate + (size_t)pass * chunks, g.dagg + (size_t)pass * chunks * GS_RADIX,
                             g.dinc + (size_t)pass * chunks * GS_RADIX};
-        depth_pass_kernel<<<chunks, SORT_THREADS, SORT_SMEM, f.stream>>>(g.key[side], g.idx[side], g.key[side ^ 1],
-                                                                        g.idx[side ^ 1], g.dhist + pass * GS_RADIX, ch,
-                                                                        &g.hdr->tickets[pass], P, pass * GS_RADIX_BITS,
-                                                                        pass == 0);
+        depth_pass_kernel<<<chunks, SORT_THREADS, SORT_SMEM, f.stream>>>(g.key[0], g.idx[0], g.key[1], g.idx[1],
+                                                                        g.dhist + pass * GS_RADIX, ch,
+                                                                        &g.hdr->tickets[pass], g.hdr, P, pass);
         gs_note_launch();
         GS_TRY(cudaGetLastError());
-        side ^= 1;
     }
-    return cudaSuccess;  // four passes: the sorted order is back in key[0] / idx[0]
+    return cudaSuccess;  // the sorted order is in key[s] / idx[s], s = hdr->sort_side[3]
 }
 
 #define PART_SMEM(NB) ((8 * PART_ROUNDS * ((NB) + 4) + 8 * (NB)) * 4)
@@ -818,13 +832,14 @@ cudaError_t gs_launch_tile_lists(const GsFrame& f, const GsGeom& g, const GsBinn
     const unsigned long long rowcap = RowCap;
 #define LAUNCH_PART(NB, PASS, GRID)                                                                               \
     range_partition_kernel<NB, PASS><<<GRID, 256, PART_SMEM(NB), f.stream>>>(                                     \
-        g.idx[0], g.rect, P, b.items, im.rdiff, f.gx, f.gy, im.tile_start, rowcap, (PASS == 1) ? g.ragg : b.cagg, \
+        g.idx[0], g.idx[1], g.rect, P, b.items, im.rdiff, f.gx, f.gy, im.tile_start, rowcap,                       \
+        (PASS == 1) ? g.ragg : b.cagg,                                                                            \
         &g.hdr->tickets[3 + PASS], g.hdr, b.items, b.list)
     // row counts per chunk -> output positions; row pass: Gaussians in depth order -> row items grouped by tile row
     if (f.gy <= 128)
-        row_count_kernel<128><<<(unsigned)g.row_chunks, 256, 0, f.stream>>>(g.idx[0], g.rect, P, f.gy, g.ragg);
+        row_count_kernel<128><<<(unsigned)g.row_chunks, 256, 0, f.stream>>>(g.idx[0], g.idx[1], g.hdr, g.rect, P, f.gy, g.ragg);
     else
-        row_count_kernel<256><<<(unsigned)g.row_chunks, 256, 0, f.stream>>>(g.idx[0], g.rect, P, f.gy, g.ragg);
+        row_count_kernel<256><<<(unsigned)g.row_chunks, 256, 0, f.stream>>>(g.idx[0], g.idx[1], g.hdr, g.rect, P, f.gy, g.ragg);
     gs_note_launch();
     GS_TRY(cudaGetLastError());
     row_scan_kernel<<<(unsigned)f.gy, 32, 0, f.stream>>>(im.rdiff, f.gy, (uint32_t)g.row_chunks, g.ragg);

@@ -55,7 +55,9 @@ struct GsHeader {  // lives at offset 0 of the geometry buffer
     unsigned int tickets[16];    // 0-3 depth-sort passes, 4 row pass, 5 column pass, 6 blend work queue,
                                  // 7 parked blend units (count), 8 parked units taken by teams, 9 fresh CTAs done,
                                  // 10 blend-backward work queue, 11 CTA arrival order of the blend kernel
-    unsigned int pad[40];
+    unsigned int sort_side[4];   // depth sort: side (0 / 1) of the key / idx ping-pong that holds the output of pass p
+                                 // (an identity pass -- all keys share the digit -- moves nothing and keeps the side)
+    unsigned int pad[36];
 };
 static_assert(sizeof(GsHeader) == 256, "header is one aligned slot");
 
@@ -229,7 +231,7 @@ struct GsFrame {  // host-side derived quantities handed to every launcher
 cudaError_t gs_launch_preprocess(const GsFrame& f, const GsGeom& g, const GsImage& im, int32_t* radii);
 cudaError_t gs_launch_recolor(const GsFrame& f, const GsGeom& g);  // colour-only pass (gs_forward_recolor)
 cudaError_t gs_launch_pack_extra(const GsFrame& f, const GsGeom& g);  // GsScene.extra_colors -> g.xrec
-cudaError_t gs_launch_depth_sort(const GsFrame& f, const GsGeom& g);  // result in g.key[0] / g.idx[0]
+cudaError_t gs_launch_depth_sort(const GsFrame& f, const GsGeom& g);  // result in g.key[s] / g.idx[s], s = hdr->sort_side[3]
 // row pass -> column histogram -> plan (ranges, tile_start, blend queue) -> column pass
 cudaError_t gs_launch_tile_lists(const GsFrame& f, const GsGeom& g, const GsBinning& b, size_t Rcap, size_t RowCap,
                                  const GsImage& im);

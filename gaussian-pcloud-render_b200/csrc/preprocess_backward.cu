@@ -1,8 +1,26 @@
 // preprocess_backward.cu -- per-Gaussian backward (K8 + K9 fused; replaces computeCov2DCUDA and the backward
 // preprocessCUDA, dgr/cuda_rasterizer/backward.cu:144-274 and :346-396, with the SH backward :20-139 and the
-// scale/rotation backward :278-341).  One thread per Gaussian, one launch instead of two: both reference kernels
-// read the same mean / covariance / view data, and the fused kernel keeps dL_dmean3D in registers between the
-// covariance part (assignment, :273) and the projection + SH parts (+=, :387 and :138).
+// scale/rotation backward :278-341).  One thread per Gaussian, one launch instead of two.
+//
+// The gradients are derived here from the forward model in matrix form (not transcribed term by term), and checked
+// against the C oracle's restatement of the reference in tests/test_oracle.py::test_preprocess_backward_derivation
+// (a numpy mirror of exactly these formulas) and against the reference library on the GPU (<= 1e-3, tests/test_gpu.py):
+//
+//   view space     t = R m + t0            R = rows r0, r1, r2 of the view rotation
+//   projection     Sigma' = M V M^T + 0.3 I,   M = J R (2 x 3),   J = [fx/tz 0 -fx tx/tz^2; 0 fy/tz -fy ty/tz^2]
+//   conic          K = Sigma'^-1;  blend backward delivers G = dL/dK as the symmetric matrix [gx gy; gy gz]
+//   => dL/dSigma' = D = -K G K                (the reference's dL_da, dL_dc are D11, D22, its dL_db is 2 D12)
+//      dL/dV      = M^T D M                   (stored as the upper triangle with doubled off-diagonals: an off-diagonal
+//                                              entry of the symmetric V appears twice)
+//      dL/dM      = 2 D M V,  dL/dJ_ic = (dL/dM)_i . r_c,  dL/dt through the four non-zero entries of J
+//                                              (no gradient through tx, ty where the reference clamps them)
+//      dL/dm      = R^T dL/dt + the projected-mean term + the view-direction term of the SH colour
+//   SH colour      c = sum_k B_k(d) sh_k + 0.5,  d = (m - cam) / |m - cam|
+//   => dL/dsh_k = B_k(d) dL/dc,   dL/dd = sum_k grad B_k(d) (sh_k . dL/dc),   dL/dm += (g - d (d . g)) / |m - cam|
+//   world cov.     V = A S^2 A^T,  A = rotation of the (un-normalised) quaternion with columns a_k,  S = mod * scale
+//   => dL/dS_k = 2 S_k a_k^T E a_k,   dL/dA = 2 E A S^2   (E = dL/dV as a symmetric matrix, off-diagonals halved),
+//      dL/dq by the chain rule through the nine entries of A.  Two quirks of the reference are kept on purpose
+//      (SURVEY App. A item 17): dL/dscale is dL/dS without the factor `mod`, and the quaternion is not normalised.
 // Streaming, HBM-bound: ~80 B + SH in, ~64 B + 12*(D+1)^2 out per visible Gaussian.
 #include "gs_common.cuh"
 #include "gs_math.cuh"
@@ -18,239 +36,195 @@ struct BwdArgs {
     float* dL_dmean3D; float* dL_dcov3D; float* dL_dsh; float* dL_dscale; float* dL_drot;
 };
 
-// SH backward: writes dL_dsh rows 0..(D+1)^2-1 of this Gaussian and returns the gradient w.r.t. the mean that
-// flows through the view direction.
-__device__ __forceinline__ float3 sh_backward(int deg, const float* __restrict__ sh, float3 mean, float3 cam,
-                                              unsigned clamp_bits, float3 dL_dcol, float* __restrict__ dL_dsh) {
-    const float3 dir_orig = make_float3(mean.x - cam.x, mean.y - cam.y, mean.z - cam.z);
-    const float len = sqrtf(dir_orig.x * dir_orig.x + dir_orig.y * dir_orig.y + dir_orig.z * dir_orig.z);
-    const float x = dir_orig.x / len, y = dir_orig.y / len, z = dir_orig.z / len;
-    float dRGB[3] = {dL_dcol.x, dL_dcol.y, dL_dcol.z};
-#pragma unroll
-    for (int ch = 0; ch < 3; ch++) dRGB[ch] *= ((clamp_bits >> ch) & 1u) ? 0 : 1;
-    float ddx[3] = {0.f, 0.f, 0.f}, ddy[3] = {0.f, 0.f, 0.f}, ddz[3] = {0.f, 0.f, 0.f};
-#define SHV(i, ch) sh[(i) * 3 + (ch)]
-#define DSH(i, wgt)                                                          \
-    {                                                                        \
-        const float w_ = (wgt);                                              \
-        _Pragma("unroll") for (int ch = 0; ch < 3; ch++) dL_dsh[(i) * 3 + ch] = w_ * dRGB[ch]; \
-    }
-    DSH(0, GS_SH_C0);
-    if (deg > 0) {
-        DSH(1, -GS_SH_C1 * y);
-        DSH(2, GS_SH_C1 * z);
-        DSH(3, -GS_SH_C1 * x);
-#pragma unroll
-        for (int ch = 0; ch < 3; ch++) {
-            ddx[ch] = -GS_SH_C1 * SHV(3, ch);
-            ddy[ch] = -GS_SH_C1 * SHV(1, ch);
-            ddz[ch] = GS_SH_C1 * SHV(2, ch);
-        }
-        if (deg > 1) {
-            const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
-            DSH(4, GS_SH_C2[0] * xy);
-            DSH(5, GS_SH_C2[1] * yz);
-            DSH(6, GS_SH_C2[2] * (2.f * zz - xx - yy));
-            DSH(7, GS_SH_C2[3] * xz);
-            DSH(8, GS_SH_C2[4] * (xx - yy));
-#pragma unroll
-            for (int ch = 0; ch < 3; ch++) {
-                ddx[ch] += GS_SH_C2[0] * y * SHV(4, ch) + GS_SH_C2[2] * 2.f * -x * SHV(6, ch) +
-                           GS_SH_C2[3] * z * SHV(7, ch) + GS_SH_C2[4] * 2.f * x * SHV(8, ch);
-                ddy[ch] += GS_SH_C2[0] * x * SHV(4, ch) + GS_SH_C2[1] * z * SHV(5, ch) +
-                           GS_SH_C2[2] * 2.f * -y * SHV(6, ch) + GS_SH_C2[4] * 2.f * -y * SHV(8, ch);
-                ddz[ch] += GS_SH_C2[1] * y * SHV(5, ch) + GS_SH_C2[2] * 2.f * 2.f * z * SHV(6, ch) +
-                           GS_SH_C2[3] * x * SHV(7, ch);
-            }
-            if (deg > 2) {
-                DSH(9, GS_SH_C3[0] * y * (3.f * xx - yy));
-                DSH(10, GS_SH_C3[1] * xy * z);
-                DSH(11, GS_SH_C3[2] * y * (4.f * zz - xx - yy));
-                DSH(12, GS_SH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy));
-                DSH(13, GS_SH_C3[4] * x * (4.f * zz - xx - yy));
-                DSH(14, GS_SH_C3[5] * z * (xx - yy));
-                DSH(15, GS_SH_C3[6] * x * (xx - 3.f * yy));
-#pragma unroll
-                for (int ch = 0; ch < 3; ch++) {
-                    ddx[ch] += (GS_SH_C3[0] * SHV(9, ch) * 3.f * 2.f * xy + GS_SH_C3[1] * SHV(10, ch) * yz +
-                                GS_SH_C3[2] * SHV(11, ch) * -2.f * xy + GS_SH_C3[3] * SHV(12, ch) * -3.f * 2.f * xz +
-                                GS_SH_C3[4] * SHV(13, ch) * (-3.f * xx + 4.f * zz - yy) +
-                                GS_SH_C3[5] * SHV(14, ch) * 2.f * xz + GS_SH_C3[6] * SHV(15, ch) * 3.f * (xx - yy));
-                    ddy[ch] += (GS_SH_C3[0] * SHV(9, ch) * 3.f * (xx - yy) + GS_SH_C3[1] * SHV(10, ch) * xz +
-                                GS_SH_C3[2] * SHV(11, ch) * (-3.f * yy + 4.f * zz - xx) +
-                                GS_SH_C3[3] * SHV(12, ch) * -3.f * 2.f * yz + GS_SH_C3[4] * SHV(13, ch) * -2.f * xy +
-                                GS_SH_C3[5] * SHV(14, ch) * -2.f * yz + GS_SH_C3[6] * SHV(15, ch) * -3.f * 2.f * xy);
-                    ddz[ch] += (GS_SH_C3[1] * SHV(10, ch) * xy + GS_SH_C3[2] * SHV(11, ch) * 4.f * 2.f * yz +
-                                GS_SH_C3[3] * SHV(12, ch) * 3.f * (2.f * zz - xx - yy) +
-                                GS_SH_C3[4] * SHV(13, ch) * 4.f * 2.f * xz + GS_SH_C3[5] * SHV(14, ch) * (xx - yy));
-                }
-            }
-        }
-    }
-#undef SHV
-#undef DSH
-    const float3 dL_ddir = make_float3(ddx[0] * dRGB[0] + ddx[1] * dRGB[1] + ddx[2] * dRGB[2],
-                                       ddy[0] * dRGB[0] + ddy[1] * dRGB[1] + ddy[2] * dRGB[2],
-                                       ddz[0] * dRGB[0] + ddz[1] * dRGB[1] + ddz[2] * dRGB[2]);
-    // gradient through v / |v| (auxiliary.h:108-119)
-    const float3 v = dir_orig, dv = dL_ddir;
-    const float sum2 = v.x * v.x + v.y * v.y + v.z * v.z;
-    const float invsum32 = 1.0f / sqrtf(sum2 * sum2 * sum2);
-    float3 r;
-    r.x = ((+sum2 - v.x * v.x) * dv.x - v.y * v.x * dv.y - v.z * v.x * dv.z) * invsum32;
-    r.y = (-v.x * v.y * dv.x + (sum2 - v.y * v.y) * dv.y - v.z * v.y * dv.z) * invsum32;
-    r.z = (-v.x * v.z * dv.x - v.y * v.z * dv.y + (sum2 - v.z * v.z) * dv.z) * invsum32;
-    return r;
+__device__ __forceinline__ float3 v3(float x, float y, float z) { return make_float3(x, y, z); }
+__device__ __forceinline__ float dot3(float3 a, float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ float3 lin2(float s, float3 a, float t, float3 b) {  // s a + t b
+    return v3(s * a.x + t * b.x, s * a.y + t * b.y, s * a.z + t * b.z);
+}
+__device__ __forceinline__ float3 symmul(const float* c6, float3 v) {  // V v for V = upper triangle c6
+    return v3(c6[0] * v.x + c6[1] * v.y + c6[2] * v.z, c6[1] * v.x + c6[3] * v.y + c6[4] * v.z,
+              c6[2] * v.x + c6[4] * v.y + c6[5] * v.z);
 }
 
-// dL/dcov3D -> dL/dscale, dL/drot (no quaternion-normalisation backward)
-__device__ __forceinline__ void cov3d_backward(float3 scale, float mod, float4 rot, const float* dc, float* dL_dscale,
-                                               float* dL_drot) {
-    const float r = rot.x, x = rot.y, y = rot.z, z = rot.w;
-    M3 R = m3_cols(1.f - 2.f * (y * y + z * z), 2.f * (x * y - r * z), 2.f * (x * z + r * y),
-                   2.f * (x * y + r * z), 1.f - 2.f * (x * x + z * z), 2.f * (y * z - r * x),
-                   2.f * (x * z - r * y), 2.f * (y * z + r * x), 1.f - 2.f * (x * x + y * y));
-    const float3 s = make_float3(mod * scale.x, mod * scale.y, mod * scale.z);
-    M3 S = m3_cols(s.x, 0.f, 0.f, 0.f, s.y, 0.f, 0.f, 0.f, s.z);
-    M3 M = m3_mul(S, R);
-    M3 dSig = m3_cols(dc[0], 0.5f * dc[1], 0.5f * dc[2], 0.5f * dc[1], dc[3], 0.5f * dc[4], 0.5f * dc[2],
-                      0.5f * dc[4], dc[5]);
-    M3 M2;
-#pragma unroll
-    for (int j = 0; j < 3; j++)
-#pragma unroll
-        for (int i = 0; i < 3; i++) M2.c[j][i] = 2.0f * M.c[j][i];
-    M3 dM = m3_mul(M2, dSig);
-    M3 Rt = m3_t(R);
-    M3 dMt = m3_t(dM);
-    const float sv[3] = {s.x, s.y, s.z};
-#pragma unroll
-    for (int k = 0; k < 3; k++)
-        dL_dscale[k] = Rt.c[k][0] * dMt.c[k][0] + Rt.c[k][1] * dMt.c[k][1] + Rt.c[k][2] * dMt.c[k][2];
-#pragma unroll
-    for (int k = 0; k < 3; k++)
-#pragma unroll
-        for (int i = 0; i < 3; i++) dMt.c[k][i] *= sv[k];
-#define D(a, b) dMt.c[a][b]
-    dL_drot[0] = 2 * z * (D(0, 1) - D(1, 0)) + 2 * y * (D(2, 0) - D(0, 2)) + 2 * x * (D(1, 2) - D(2, 1));
-    dL_drot[1] = 2 * y * (D(1, 0) + D(0, 1)) + 2 * z * (D(2, 0) + D(0, 2)) + 2 * r * (D(1, 2) - D(2, 1)) -
-                 4 * x * (D(2, 2) + D(1, 1));
-    dL_drot[2] = 2 * x * (D(1, 0) + D(0, 1)) + 2 * r * (D(2, 0) - D(0, 2)) + 2 * z * (D(1, 2) + D(2, 1)) -
-                 4 * y * (D(2, 2) + D(0, 0));
-    dL_drot[3] = 2 * r * (D(0, 1) - D(1, 0)) + 2 * x * (D(2, 0) + D(0, 2)) + 2 * y * (D(1, 2) + D(2, 1)) -
-                 4 * z * (D(1, 1) + D(0, 0));
-#undef D
+// One SH coefficient: dL/dsh_k = B dRGB, and its share of dL/dd.
+__device__ __forceinline__ void sh_term(int k, float B, float3 gradB, const float* __restrict__ sh, float3 dRGB,
+                                        float* __restrict__ dL_dsh, float3& g) {
+    dL_dsh[3 * k] = B * dRGB.x;
+    dL_dsh[3 * k + 1] = B * dRGB.y;
+    dL_dsh[3 * k + 2] = B * dRGB.z;
+    const float s = sh[3 * k] * dRGB.x + sh[3 * k + 1] * dRGB.y + sh[3 * k + 2] * dRGB.z;
+    g.x += s * gradB.x; g.y += s * gradB.y; g.z += s * gradB.z;
+}
+
+// SH backward of one Gaussian: writes dL_dsh rows 0..(deg+1)^2-1 and returns dL/dmean through the view direction.
+// B_k and grad B_k are the real SH basis polynomials in the reference's sign convention (forward.cu:20-71).
+__device__ __forceinline__ float3 sh_backward(int deg, const float* __restrict__ sh, float3 mean, float3 cam,
+                                              unsigned clamp_bits, float3 dcol, float* __restrict__ dL_dsh) {
+    const float3 v = v3(mean.x - cam.x, mean.y - cam.y, mean.z - cam.z);
+    const float inv_len = 1.0f / sqrtf(dot3(v, v));
+    const float x = v.x * inv_len, y = v.y * inv_len, z = v.z * inv_len;
+    // a clamped channel (colour < 0 in the forward pass) passes no gradient
+    const float3 dRGB = v3((clamp_bits & 1u) ? 0.f : dcol.x, (clamp_bits & 2u) ? 0.f : dcol.y,
+                           (clamp_bits & 4u) ? 0.f : dcol.z);
+    float3 g = v3(0.f, 0.f, 0.f);
+    sh_term(0, GS_SH_C0, v3(0.f, 0.f, 0.f), sh, dRGB, dL_dsh, g);
+    if (deg > 0) {
+        const float c1 = GS_SH_C1;
+        sh_term(1, -c1 * y, v3(0.f, -c1, 0.f), sh, dRGB, dL_dsh, g);
+        sh_term(2, c1 * z, v3(0.f, 0.f, c1), sh, dRGB, dL_dsh, g);
+        sh_term(3, -c1 * x, v3(-c1, 0.f, 0.f), sh, dRGB, dL_dsh, g);
+    }
+    if (deg > 1) {
+        const float xx = x * x, yy = y * y, zz = z * z;
+        const float a0 = GS_SH_C2[0], a1 = GS_SH_C2[1], a2 = GS_SH_C2[2], a3 = GS_SH_C2[3], a4 = GS_SH_C2[4];
+        sh_term(4, a0 * x * y, v3(a0 * y, a0 * x, 0.f), sh, dRGB, dL_dsh, g);
+        sh_term(5, a1 * y * z, v3(0.f, a1 * z, a1 * y), sh, dRGB, dL_dsh, g);
+        sh_term(6, a2 * (2.f * zz - xx - yy), v3(-2.f * a2 * x, -2.f * a2 * y, 4.f * a2 * z), sh, dRGB, dL_dsh, g);
+        sh_term(7, a3 * x * z, v3(a3 * z, 0.f, a3 * x), sh, dRGB, dL_dsh, g);
+        sh_term(8, a4 * (xx - yy), v3(2.f * a4 * x, -2.f * a4 * y, 0.f), sh, dRGB, dL_dsh, g);
+        if (deg > 2) {
+            const float b0 = GS_SH_C3[0], b1 = GS_SH_C3[1], b2 = GS_SH_C3[2], b3 = GS_SH_C3[3], b4 = GS_SH_C3[4],
+                        b5 = GS_SH_C3[5], b6 = GS_SH_C3[6];
+            sh_term(9, b0 * y * (3.f * xx - yy), v3(6.f * b0 * x * y, 3.f * b0 * (xx - yy), 0.f), sh, dRGB, dL_dsh, g);
+            sh_term(10, b1 * x * y * z, v3(b1 * y * z, b1 * x * z, b1 * x * y), sh, dRGB, dL_dsh, g);
+            sh_term(11, b2 * y * (4.f * zz - xx - yy),
+                    v3(-2.f * b2 * x * y, b2 * (4.f * zz - xx - 3.f * yy), 8.f * b2 * y * z), sh, dRGB, dL_dsh, g);
+            sh_term(12, b3 * z * (2.f * zz - 3.f * xx - 3.f * yy),
+                    v3(-6.f * b3 * x * z, -6.f * b3 * y * z, 3.f * b3 * (2.f * zz - xx - yy)), sh, dRGB, dL_dsh, g);
+            sh_term(13, b4 * x * (4.f * zz - xx - yy),
+                    v3(b4 * (4.f * zz - 3.f * xx - yy), -2.f * b4 * x * y, 8.f * b4 * x * z), sh, dRGB, dL_dsh, g);
+            sh_term(14, b5 * z * (xx - yy), v3(2.f * b5 * x * z, -2.f * b5 * y * z, b5 * (xx - yy)), sh, dRGB, dL_dsh, g);
+            sh_term(15, b6 * x * (xx - 3.f * yy), v3(3.f * b6 * (xx - yy), -6.f * b6 * x * y, 0.f), sh, dRGB, dL_dsh, g);
+        }
+    }
+    // d = v / |v|:  dL/dv = (g - d (d . g)) / |v|
+    const float dg = x * g.x + y * g.y + z * g.z;
+    return v3((g.x - x * dg) * inv_len, (g.y - y * dg) * inv_len, (g.z - z * dg) * inv_len);
 }
 
 __global__ void __launch_bounds__(256) preprocess_backward_kernel(const BwdArgs a) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.P || !(a.radii[i] > 0)) return;
-    const float3 mean = make_float3(a.means[3 * i], a.means[3 * i + 1], a.means[3 * i + 2]);
-    const float* cov3D = a.cov3D + 6 * (size_t)i;
+    const float3 mean = v3(a.means[3 * i], a.means[3 * i + 1], a.means[3 * i + 2]);
     float c6[6];
-#pragma unroll
-    for (int k = 0; k < 6; k++) c6[k] = cov3D[k];
-
-    // ---- gradient of the conic w.r.t. the 2D covariance, then w.r.t. cov3D and the view-space mean ----
-    Cov2D k;
-    cov2d_eval(mean, a.fx, a.fy, a.tanx, a.tany, c6, a.view, k);
-    const float3 dL_dconic = make_float3(a.dL_dconic[4 * i], a.dL_dconic[4 * i + 1], a.dL_dconic[4 * i + 3]);
-    const float x_grad_mul = k.txtz < -k.limx || k.txtz > k.limx ? 0 : 1;
-    const float y_grad_mul = k.tytz < -k.limy || k.tytz > k.limy ? 0 : 1;
-    const float ca = k.a, cb = k.b, cc = k.c;
-    const float denom = ca * cc - cb * cb;
-    float dL_da = 0, dL_db = 0, dL_dc = 0;
-    const float denom2inv = 1.0f / ((denom * denom) + 0.0000001f);
-    float dcov[6];
-#define TT(col, row) k.T.c[col][row]
-#define VV(col, row) k.Vrk.c[col][row]
-#define WW(col, row) k.W.c[col][row]
-    if (denom2inv != 0) {
-        dL_da = denom2inv * (-cc * cc * dL_dconic.x + 2 * cb * cc * dL_dconic.y + (denom - ca * cc) * dL_dconic.z);
-        dL_dc = denom2inv * (-ca * ca * dL_dconic.z + 2 * ca * cb * dL_dconic.y + (denom - ca * cc) * dL_dconic.x);
-        dL_db = denom2inv * 2 * (cb * cc * dL_dconic.x - (denom + 2 * cb * cb) * dL_dconic.y + ca * cb * dL_dconic.z);
-        dcov[0] = (TT(0, 0) * TT(0, 0) * dL_da + TT(0, 0) * TT(1, 0) * dL_db + TT(1, 0) * TT(1, 0) * dL_dc);
-        dcov[3] = (TT(0, 1) * TT(0, 1) * dL_da + TT(0, 1) * TT(1, 1) * dL_db + TT(1, 1) * TT(1, 1) * dL_dc);
-        dcov[5] = (TT(0, 2) * TT(0, 2) * dL_da + TT(0, 2) * TT(1, 2) * dL_db + TT(1, 2) * TT(1, 2) * dL_dc);
-        dcov[1] = 2 * TT(0, 0) * TT(0, 1) * dL_da + (TT(0, 0) * TT(1, 1) + TT(0, 1) * TT(1, 0)) * dL_db +
-                  2 * TT(1, 0) * TT(1, 1) * dL_dc;
-        dcov[2] = 2 * TT(0, 0) * TT(0, 2) * dL_da + (TT(0, 0) * TT(1, 2) + TT(0, 2) * TT(1, 0)) * dL_db +
-                  2 * TT(1, 0) * TT(1, 2) * dL_dc;
-        dcov[4] = 2 * TT(0, 2) * TT(0, 1) * dL_da + (TT(0, 1) * TT(1, 2) + TT(0, 2) * TT(1, 1)) * dL_db +
-                  2 * TT(1, 1) * TT(1, 2) * dL_dc;
+    if ((reinterpret_cast<uintptr_t>(a.cov3D) & 7u) == 0) {  // 24-byte rows of an 8-byte aligned array: three 8-byte loads
+        const float2* cp = reinterpret_cast<const float2*>(a.cov3D + 6 * (size_t)i);
+        const float2 p0 = cp[0], p1 = cp[1], p2 = cp[2];
+        c6[0] = p0.x; c6[1] = p0.y; c6[2] = p1.x; c6[3] = p1.y; c6[4] = p2.x; c6[5] = p2.y;
     } else {
 #pragma unroll
-        for (int q = 0; q < 6; q++) dcov[q] = 0;
+        for (int k = 0; k < 6; k++) c6[k] = a.cov3D[6 * (size_t)i + k];
     }
-#pragma unroll
-    for (int q = 0; q < 6; q++) a.dL_dcov3D[6 * (size_t)i + q] = dcov[q];
-
-    const float dL_dT00 = 2 * (TT(0, 0) * VV(0, 0) + TT(0, 1) * VV(0, 1) + TT(0, 2) * VV(0, 2)) * dL_da +
-                          (TT(1, 0) * VV(0, 0) + TT(1, 1) * VV(0, 1) + TT(1, 2) * VV(0, 2)) * dL_db;
-    const float dL_dT01 = 2 * (TT(0, 0) * VV(1, 0) + TT(0, 1) * VV(1, 1) + TT(0, 2) * VV(1, 2)) * dL_da +
-                          (TT(1, 0) * VV(1, 0) + TT(1, 1) * VV(1, 1) + TT(1, 2) * VV(1, 2)) * dL_db;
-    const float dL_dT02 = 2 * (TT(0, 0) * VV(2, 0) + TT(0, 1) * VV(2, 1) + TT(0, 2) * VV(2, 2)) * dL_da +
-                          (TT(1, 0) * VV(2, 0) + TT(1, 1) * VV(2, 1) + TT(1, 2) * VV(2, 2)) * dL_db;
-    const float dL_dT10 = 2 * (TT(1, 0) * VV(0, 0) + TT(1, 1) * VV(0, 1) + TT(1, 2) * VV(0, 2)) * dL_dc +
-                          (TT(0, 0) * VV(0, 0) + TT(0, 1) * VV(0, 1) + TT(0, 2) * VV(0, 2)) * dL_db;
-    const float dL_dT11 = 2 * (TT(1, 0) * VV(1, 0) + TT(1, 1) * VV(1, 1) + TT(1, 2) * VV(1, 2)) * dL_dc +
-                          (TT(0, 0) * VV(1, 0) + TT(0, 1) * VV(1, 1) + TT(0, 2) * VV(1, 2)) * dL_db;
-    const float dL_dT12 = 2 * (TT(1, 0) * VV(2, 0) + TT(1, 1) * VV(2, 1) + TT(1, 2) * VV(2, 2)) * dL_dc +
-                          (TT(0, 0) * VV(2, 0) + TT(0, 1) * VV(2, 1) + TT(0, 2) * VV(2, 2)) * dL_db;
-    const float dL_dJ00 = WW(0, 0) * dL_dT00 + WW(0, 1) * dL_dT01 + WW(0, 2) * dL_dT02;
-    const float dL_dJ02 = WW(2, 0) * dL_dT00 + WW(2, 1) * dL_dT01 + WW(2, 2) * dL_dT02;
-    const float dL_dJ11 = WW(1, 0) * dL_dT10 + WW(1, 1) * dL_dT11 + WW(1, 2) * dL_dT12;
-    const float dL_dJ12 = WW(2, 0) * dL_dT10 + WW(2, 1) * dL_dT11 + WW(2, 2) * dL_dT12;
-#undef TT
-#undef VV
-#undef WW
-    const float tz = 1.f / k.tz;
-    const float tz2 = tz * tz;
-    const float tz3 = tz2 * tz;
-    const float dL_dtx = x_grad_mul * -a.fx * tz2 * dL_dJ02;
-    const float dL_dty = y_grad_mul * -a.fy * tz2 * dL_dJ12;
-    const float dL_dtz = -a.fx * tz2 * dL_dJ00 - a.fy * tz2 * dL_dJ11 + (2 * a.fx * k.tx) * tz3 * dL_dJ02 +
-                         (2 * a.fy * k.ty) * tz3 * dL_dJ12;
     const float* vm = a.view;
-    float3 dmean = make_float3(vm[0] * dL_dtx + vm[1] * dL_dty + vm[2] * dL_dtz,
-                               vm[4] * dL_dtx + vm[5] * dL_dty + vm[6] * dL_dtz,
-                               vm[8] * dL_dtx + vm[9] * dL_dty + vm[10] * dL_dtz);
+    const float3 r0 = v3(vm[0], vm[4], vm[8]), r1 = v3(vm[1], vm[5], vm[9]), r2 = v3(vm[2], vm[6], vm[10]);
 
-    // ---- gradient of the projected 2D mean ----
-    const float* proj = a.proj;
-    const float4 m_hom = xform44(proj, mean);
-    const float m_w = 1.0f / (m_hom.w + 0.0000001f);
-    const float mul1 = (proj[0] * mean.x + proj[4] * mean.y + proj[8] * mean.z + proj[12]) * m_w * m_w;
-    const float mul2 = (proj[1] * mean.x + proj[5] * mean.y + proj[9] * mean.z + proj[13]) * m_w * m_w;
-    const float g2x = a.dL_dmean2D[3 * (size_t)i], g2y = a.dL_dmean2D[3 * (size_t)i + 1];
-    float3 dm2;
-    dm2.x = (proj[0] * m_w - proj[3] * mul1) * g2x + (proj[1] * m_w - proj[3] * mul2) * g2y;
-    dm2.y = (proj[4] * m_w - proj[7] * mul1) * g2x + (proj[5] * m_w - proj[7] * mul2) * g2y;
-    dm2.z = (proj[8] * m_w - proj[11] * mul1) * g2x + (proj[9] * m_w - proj[11] * mul2) * g2y;
-    dmean.x += dm2.x; dmean.y += dm2.y; dmean.z += dm2.z;
+    // ---- forward quantities: clamped view-space position, M = J R, U = M V, Sigma' ----
+    const float tz = dot3(r2, mean) + vm[14];
+    const float limx = 1.3f * a.tanx, limy = 1.3f * a.tany;
+    const float ux = (dot3(r0, mean) + vm[12]) / tz, uy = (dot3(r1, mean) + vm[13]) / tz;
+    const bool in_x = !(ux < -limx || ux > limx), in_y = !(uy < -limy || uy > limy);
+    const float tx = fminf(limx, fmaxf(-limx, ux)) * tz, ty = fminf(limy, fmaxf(-limy, uy)) * tz;
+    const float iz = 1.f / tz, iz2 = iz * iz;
+    const float j00 = a.fx * iz, j02 = -(a.fx * tx) * iz2, j11 = a.fy * iz, j12 = -(a.fy * ty) * iz2;
+    const float3 m0 = lin2(j00, r0, j02, r2), m1 = lin2(j11, r1, j12, r2);
+    const float3 u0 = symmul(c6, m0), u1 = symmul(c6, m1);
+    const float ca = dot3(m0, u0) + 0.3f, cb = dot3(m0, u1), cc = dot3(m1, u1) + 0.3f;
+
+    // ---- D = -K G K with the reference's regularised 1 / det^2 ----
+    const float det = ca * cc - cb * cb;
+    const float w = 1.0f / (det * det + 0.0000001f);
+    // [P][2][2] rows: gx, gy, (unused), gz (caller memory of any 4-byte alignment)
+    const float gx = a.dL_dconic[4 * (size_t)i], gy = a.dL_dconic[4 * (size_t)i + 1], gz = a.dL_dconic[4 * (size_t)i + 3];
+    float D11 = 0.f, D12 = 0.f, D22 = 0.f;
+    if (w != 0.f) {  // det * K = [cc -cb; -cb ca]
+        const float p0 = cc * gx - cb * gy, p1 = cc * gy - cb * gz;   // (det K) G, first row
+        const float q0 = ca * gy - cb * gx, q1 = ca * gz - cb * gy;   // second row
+        D11 = -w * (p0 * cc - p1 * cb);
+        D12 = -w * (p1 * ca - p0 * cb);
+        D22 = -w * (q1 * ca - q0 * cb);
+    }
+
+    // ---- dL/dV = M^T D M ----
+    const float3 e0 = lin2(D11, m0, D12, m1), e1 = lin2(D12, m0, D22, m1);  // rows of D M
+    float dcov[6];
+    dcov[0] = m0.x * e0.x + m1.x * e1.x;
+    dcov[3] = m0.y * e0.y + m1.y * e1.y;
+    dcov[5] = m0.z * e0.z + m1.z * e1.z;
+    dcov[1] = 2.f * (m0.x * e0.y + m1.x * e1.y);
+    dcov[2] = 2.f * (m0.x * e0.z + m1.x * e1.z);
+    dcov[4] = 2.f * (m0.y * e0.z + m1.y * e1.z);
+    if ((reinterpret_cast<uintptr_t>(a.dL_dcov3D) & 7u) == 0) {
+        float2* dp = reinterpret_cast<float2*>(a.dL_dcov3D + 6 * (size_t)i);
+        dp[0] = make_float2(dcov[0], dcov[1]); dp[1] = make_float2(dcov[2], dcov[3]); dp[2] = make_float2(dcov[4], dcov[5]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 6; k++) a.dL_dcov3D[6 * (size_t)i + k] = dcov[k];
+    }
+
+    // ---- dL/dM = 2 D (M V) -> dL/dJ -> dL/dt -> dL/dmean ----
+    const float3 q0 = lin2(2.f * D11, u0, 2.f * D12, u1), q1 = lin2(2.f * D12, u0, 2.f * D22, u1);
+    const float dJ00 = dot3(q0, r0), dJ02 = dot3(q0, r2), dJ11 = dot3(q1, r1), dJ12 = dot3(q1, r2);
+    const float dtx = in_x ? -a.fx * iz2 * dJ02 : 0.f;
+    const float dty = in_y ? -a.fy * iz2 * dJ12 : 0.f;
+    const float dtz = -iz2 * (a.fx * dJ00 + a.fy * dJ11) + 2.f * iz2 * iz * (a.fx * tx * dJ02 + a.fy * ty * dJ12);
+    float3 dmean = v3(r0.x * dtx + r1.x * dty + r2.x * dtz, r0.y * dtx + r1.y * dty + r2.y * dtz,
+                      r0.z * dtx + r1.z * dty + r2.z * dtz);
+
+    // ---- projected 2D mean p = h.xy / (h.w + eps), h = P [m 1] ----
+    {
+        const float* pj = a.proj;
+        const float hx = pj[0] * mean.x + pj[4] * mean.y + pj[8] * mean.z + pj[12];
+        const float hy = pj[1] * mean.x + pj[5] * mean.y + pj[9] * mean.z + pj[13];
+        const float hw = pj[3] * mean.x + pj[7] * mean.y + pj[11] * mean.z + pj[15];
+        const float iw = 1.0f / (hw + 0.0000001f);
+        const float g2x = a.dL_dmean2D[3 * (size_t)i], g2y = a.dL_dmean2D[3 * (size_t)i + 1];
+        const float sx = g2x * iw, sy = g2y * iw;                // weights of d h.x/dm, d h.y/dm
+        const float sw = -(sx * hx + sy * hy) * iw;              // weight of d h.w/dm
+        dmean.x += sx * pj[0] + sy * pj[1] + sw * pj[3];
+        dmean.y += sx * pj[4] + sy * pj[5] + sw * pj[7];
+        dmean.z += sx * pj[8] + sy * pj[9] + sw * pj[11];
+    }
 
     // ---- colour -> SH ----
     if (a.shs) {
-        const float3 dcol = make_float3(a.dL_dcolor[3 * (size_t)i], a.dL_dcolor[3 * (size_t)i + 1],
-                                        a.dL_dcolor[3 * (size_t)i + 2]);
-        const float3 dsh_mean = sh_backward(a.D, a.shs + (size_t)i * a.M * 3, mean,
-                                            make_float3(a.campos[0], a.campos[1], a.campos[2]), a.clamp[i], dcol,
-                                            a.dL_dsh + (size_t)i * a.M * 3);
-        dmean.x += dsh_mean.x; dmean.y += dsh_mean.y; dmean.z += dsh_mean.z;
+        const float3 dcol = v3(a.dL_dcolor[3 * (size_t)i], a.dL_dcolor[3 * (size_t)i + 1], a.dL_dcolor[3 * (size_t)i + 2]);
+        const float3 g = sh_backward(a.D, a.shs + (size_t)i * a.M * 3, mean, v3(a.campos[0], a.campos[1], a.campos[2]),
+                                     a.clamp[i], dcol, a.dL_dsh + (size_t)i * a.M * 3);
+        dmean.x += g.x; dmean.y += g.y; dmean.z += g.z;
     }
     a.dL_dmean3D[3 * (size_t)i] = dmean.x;
     a.dL_dmean3D[3 * (size_t)i + 1] = dmean.y;
     a.dL_dmean3D[3 * (size_t)i + 2] = dmean.z;
 
-    // ---- covariance -> scale / rotation ----
+    // ---- covariance -> scale / rotation:  V = A S^2 A^T ----
     if (a.scales) {
-        float ds[3], dq[4];
-        cov3d_backward(make_float3(a.scales[3 * i], a.scales[3 * i + 1], a.scales[3 * i + 2]), a.mod,
-                       reinterpret_cast<const float4*>(a.rots)[i], dcov, ds, dq);
+        const float r = a.rots[4 * (size_t)i], x = a.rots[4 * (size_t)i + 1], y = a.rots[4 * (size_t)i + 2],
+                    z = a.rots[4 * (size_t)i + 3];
+        const float s[3] = {a.mod * a.scales[3 * i], a.mod * a.scales[3 * i + 1], a.mod * a.scales[3 * i + 2]};
+        // columns a_k of the rotation
+        const float3 ak[3] = {v3(1.f - 2.f * (y * y + z * z), 2.f * (x * y + r * z), 2.f * (x * z - r * y)),
+                              v3(2.f * (x * y - r * z), 1.f - 2.f * (x * x + z * z), 2.f * (y * z + r * x)),
+                              v3(2.f * (x * z + r * y), 2.f * (y * z - r * x), 1.f - 2.f * (x * x + y * y))};
+        const float e6[6] = {dcov[0], 0.5f * dcov[1], 0.5f * dcov[2], dcov[3], 0.5f * dcov[4], dcov[5]};
+        float ds[3];
+        float A[3][3];  // dL/dA, A[row][col]
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const float3 ea = symmul(e6, ak[k]);          // E a_k
+            ds[k] = 2.f * s[k] * dot3(ak[k], ea);
+            const float f = 2.f * s[k] * s[k];
+            A[0][k] = f * ea.x; A[1][k] = f * ea.y; A[2][k] = f * ea.z;
+        }
         a.dL_dscale[3 * (size_t)i] = ds[0];
         a.dL_dscale[3 * (size_t)i + 1] = ds[1];
         a.dL_dscale[3 * (size_t)i + 2] = ds[2];
-        reinterpret_cast<float4*>(a.dL_drot)[i] = make_float4(dq[0], dq[1], dq[2], dq[3]);
+        float4 dq;
+        dq.x = 2.f * (z * (A[1][0] - A[0][1]) + y * (A[0][2] - A[2][0]) + x * (A[2][1] - A[1][2]));
+        dq.y = 2.f * (y * (A[0][1] + A[1][0]) + z * (A[0][2] + A[2][0]) + r * (A[2][1] - A[1][2])) - 4.f * x * (A[1][1] + A[2][2]);
+        dq.z = 2.f * (x * (A[0][1] + A[1][0]) + r * (A[0][2] - A[2][0]) + z * (A[1][2] + A[2][1])) - 4.f * y * (A[0][0] + A[2][2]);
+        dq.w = 2.f * (r * (A[1][0] - A[0][1]) + x * (A[0][2] + A[2][0]) + y * (A[1][2] + A[2][1])) - 4.f * z * (A[0][0] + A[1][1]);
+        a.dL_drot[4 * (size_t)i] = dq.x; a.dL_drot[4 * (size_t)i + 1] = dq.y;
+        a.dL_drot[4 * (size_t)i + 2] = dq.z; a.dL_drot[4 * (size_t)i + 3] = dq.w;
     }
 }
 

@@ -222,3 +222,55 @@ def test_head_oracle_matches_reference_head_decode(name):
     r2 = head.decode_head(feat, rgb, prim, scale_factor=448, xyz_offset=512, cuda_scalar_division=True, **cfg)
     for k in ("means3D", "shs"):
         np.testing.assert_allclose(r2[k].numpy(), r[k].numpy(), rtol=2.4e-7, atol=3e-7)
+
+
+def test_preprocess_backward_derivation(oracle64):
+    """The per-Gaussian backward kernel implements gradients DERIVED in matrix form (csrc/preprocess_backward.cu header);
+    tests/derivation_preprocess_backward.py states the same formulas in numpy.  They must reproduce the oracle's
+    restatement of the reference (backward.cu:144-396) to double-precision round-off, for all SH degrees, clamped
+    colour channels, clamped view-space positions and culled points."""
+    import ctypes as C
+
+    from derivation_preprocess_backward import matrix_form_backward
+    from oracle.oracle import _ptr
+    rng = np.random.default_rng(0)
+    for D, M, tanx, tany in ((3, 16, 1.0, 0.8), (1, 13, 0.35, 0.3), (0, 1, 1.0, 1.0), (2, 9, 0.6, 0.9)):
+        P, W, H = 300, 640, 480
+        means = rng.uniform(-1, 1, (P, 3)).astype(np.float32)
+        means[:, 2] += 3.0
+        scales = np.exp(rng.uniform(-4, -2, (P, 3))).astype(np.float32)
+        rots = rng.standard_normal((P, 4)).astype(np.float32)
+        mod = 1.3
+        shs = (0.4 * rng.standard_normal((P, M, 3))).astype(np.float32)
+        clamped = (rng.uniform(size=(P, 3)) < 0.2).astype(np.uint8)
+        radii = (rng.uniform(size=P) < 0.9).astype(np.int32)
+        Q, _ = np.linalg.qr(rng.standard_normal((3, 3)))
+        Rw = Q * np.sign(np.linalg.det(Q))
+        tr = np.array([0.1, -0.2, 0.4])
+        w2c = np.eye(4)
+        w2c[:3, :3], w2c[:3, 3] = Rw, tr
+        view = np.ascontiguousarray(w2c.T.astype(np.float32)).reshape(16)
+        Pm = np.zeros((4, 4))
+        Pm[0, 0], Pm[1, 1], Pm[2, 2], Pm[2, 3], Pm[3, 2] = 1 / tanx, 1 / tany, 1.0001, -0.01, 1
+        proj = np.ascontiguousarray((Pm @ w2c).T.astype(np.float32)).reshape(16)
+        campos = (-Rw.T @ tr).astype(np.float32)
+        cov = rng.standard_normal((P, 3, 3))
+        cov = 1e-3 * np.einsum("pij,pkj->pik", cov, cov)                     # any symmetric PSD world covariance
+        cov = np.ascontiguousarray(np.stack([cov[:, 0, 0], cov[:, 0, 1], cov[:, 0, 2], cov[:, 1, 1], cov[:, 1, 2],
+                                             cov[:, 2, 2]], 1))
+        g2, gc, gcol = rng.standard_normal((P, 3)), rng.standard_normal((P, 4)), rng.standard_normal((P, 3))
+        out = dict(m3=np.zeros((P, 3)), c3=np.zeros((P, 6)), sh=np.zeros((P, M, 3)), sc=np.zeros((P, 3)),
+                   rt=np.zeros((P, 4)))
+        oracle64.lib.gso_preprocess_backward(
+            C.c_int(P), C.c_int(D), C.c_int(M), _ptr(means), _ptr(radii), _ptr(shs), _ptr(clamped), _ptr(scales),
+            _ptr(rots), C.c_float(mod), _ptr(cov), _ptr(view), _ptr(proj), _ptr(campos), C.c_int(W), C.c_int(H),
+            C.c_float(tanx), C.c_float(tany), _ptr(g2), _ptr(gc), _ptr(gcol), _ptr(out["m3"]), _ptr(out["c3"]),
+            _ptr(out["sh"]), _ptr(out["sc"]), _ptr(out["rt"]))
+        mine = matrix_form_backward(means=means, radii=radii, shs=shs, clamped=clamped, scales=scales, rots=rots, mod=mod,
+                                    cov=cov, view=view, proj=proj, campos=campos, W=W, H=H, tanx=tanx, tany=tany, D=D,
+                                    g2=g2, gc=gc, gcol=gcol)
+        assert (np.abs(np.concatenate([means @ Rw.T[:, :1] + tr[0]]) / (means @ Rw.T[:, 2:] + tr[2])) > 1.3 * tanx).any() \
+            or tanx >= 0.6                                                   # the narrow case exercises the clamp
+        for k in out:
+            err = np.abs(out[k] - mine[k]).max() / (np.abs(out[k]).max() + 1e-30)
+            assert err < 2e-5, (D, k, err)  # (un-normalised quaternions: large, cancelling rotation entries)
