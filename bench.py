@@ -333,11 +333,11 @@ def tiles_leg(args, rank, world, fr, vdev, parts, W, H, dev, steps):
         if peer is not None:
             img, ptrs, peer_barrier = peer.next()
             if r1 > r0:
-                fr.enqueue(v, tile_rows=(r0, r1), slot=i, peer_out=ptrs)
+                fr.enqueue(v, tile_rows=(r0, r1), slot=i, peer_out=ptrs, shard_cull=True)
             peer_barrier()
             return img
         if r1 > r0:
-            fr.enqueue(v, tile_rows=(r0, r1), slot=i)
+            fr.enqueue(v, tile_rows=(r0, r1), slot=i, shard_cull=True)
         sharding.exchange_image(fr.color, rows, rank)
         return fr.color
 

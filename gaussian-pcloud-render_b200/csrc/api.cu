@@ -96,6 +96,7 @@ int make_frame(const GsScene* s, void* stream, GsFrame& f, bool forward = true) 
     } else if (s->tile_row_begin != 0 || s->tile_row_end != 0) {
         f.row0 = f.row1 = 0;  // empty shard: every tile rectangle is clipped away, nothing is binned or blended
     }
+    f.cull = s->shard_cull != 0 && s->P > 0 && f.row1 > f.row0 && (f.row0 > 0 || f.row1 < f.gy);  // a proper shard only
     if (f.gx > GS_MAX_GRID || f.gy > GS_MAX_GRID) return GS_ERR_UNSUPPORTED;  // at most 4096 x 4096 pixels
     if ((unsigned long long)s->P >= (1ull << 30)) return GS_ERR_UNSUPPORTED;  // instance counters stay well inside 32 bits
     f.focal_y = s->height / (2.0f * s->tan_fovy);  // rasterizer_impl.cu:222-223
@@ -170,6 +171,7 @@ int64_t gs_forward(const GsScene* scene, GsBuffer geometry, GsBuffer binning, Gs
     GS_CU(cudaMemsetAsync(gptr, 0, g.zero_bytes, f.stream));
     GS_CU(cudaMemsetAsync(iptr, 0, im.zero_bytes, f.stream));
     t_prof.mark(0, f.stream);
+    GS_STAGE(gs_launch_shard_cull(f, g));
     GS_STAGE(gs_launch_preprocess(f, g, im, radii));
     t_prof.mark(1, f.stream);
     if (f.row1 == f.row0) return 0;  // empty tile-row shard: radii are done, there is nothing to bin or blend
@@ -211,6 +213,7 @@ int32_t gs_forward_nosync(const GsScene* scene, char* geometry, char* binning, i
     GS_CU(cudaMemsetAsync(geometry, 0, g.zero_bytes, f.stream));
     GS_CU(cudaMemsetAsync(image, 0, im.zero_bytes, f.stream));
     t_prof.mark(0, f.stream);
+    GS_STAGE(gs_launch_shard_cull(f, g));
     GS_STAGE(gs_launch_preprocess(f, g, im, radii));
     t_prof.mark(1, f.stream);
     if (f.row1 == f.row0) return GS_OK;  // empty tile-row shard

@@ -182,9 +182,11 @@ __device__ __forceinline__ int chunk_row(const uint32_t* s_cf, int gy, uint32_t 
 
 // ---------------------------------------------------------------------------------------------------
 // Depth sort.  Histograms of all four digits in one pass over the keys.
+// `pn` (shard cull): the number of keys is hdr->num_cand, known only on the device; nullptr = P.
 __global__ void __launch_bounds__(1024) depth_hist_kernel(const uint32_t* __restrict__ key, uint32_t P,
-                                                          uint32_t* __restrict__ hist) {
+                                                          const unsigned* __restrict__ pn, uint32_t* __restrict__ hist) {
     __shared__ uint32_t s[4][GS_RADIX];
+    if (pn) P = *pn;
     const int tid = threadIdx.x, lane = tid & 31;
     (&s[0][0])[tid] = 0;
     __syncthreads();
@@ -247,7 +249,9 @@ __global__ void __launch_bounds__(SORT_THREADS, SORT_MIN_BLOCKS) depth_pass_kern
                                                                   uint32_t* __restrict__ idx1,
                                                                   const uint32_t* __restrict__ hist,  // 256 totals
                                                                   const GsChain chain, unsigned* __restrict__ ticket,
-                                                                  GsHeader* __restrict__ hdr, uint32_t P, int pass) {
+                                                                  GsHeader* __restrict__ hdr, uint32_t P, int pass,
+                                                                  const uint32_t* __restrict__ cand) {
+    if (cand) P = hdr->num_cand;  // shard cull: keys of the candidates only; position t holds Gaussian cand[t]
     // input side of the ping-pong = where the previous pass left its output (preprocess writes the keys to side 0)
     const int shift = pass * GS_RADIX_BITS, first_pass = pass == 0;
     const unsigned side = first_pass ? 0u : hdr->sort_side[pass - 1];
@@ -272,6 +276,7 @@ __global__ void __launch_bounds__(SORT_THREADS, SORT_MIN_BLOCKS) depth_pass_kern
     for (int i = tid; i < SORT_WARPS * GS_RADIX; i += SORT_THREADS) s_cnt[i] = 0;
     __syncthreads();
     const uint32_t chunk = s_chunk;
+    if (chunk * GS_SORT_CHUNK >= P && !(chunk == 0)) return;  // past the keys (the grid is sized for the upper bound)
     const uint32_t base = chunk * GS_SORT_CHUNK + warp * (GS_SORT_CHUNK / SORT_WARPS);
     const uint32_t tl_slot = (uint32_t)(shift / 8) * 1024u + chunk;
     BIN_MARK(tl_slot, 0);
@@ -281,10 +286,10 @@ __global__ void __launch_bounds__(SORT_THREADS, SORT_MIN_BLOCKS) depth_pass_kern
     // before this kernel starts, so every CTA takes the same branch.
     if (hist[(key_in[0] >> shift) & 255u] == P) {
         if (first_pass) {
-            const uint32_t beg = chunk * GS_SORT_CHUNK, n = min((uint32_t)GS_SORT_CHUNK, P - beg);
+            const uint32_t beg = chunk * GS_SORT_CHUNK, n = beg < P ? min((uint32_t)GS_SORT_CHUNK, P - beg) : 0u;
             for (uint32_t t = tid; t < n; t += SORT_THREADS) {
                 key_out[beg + t] = key_in[beg + t];
-                idx_out[beg + t] = beg + t;
+                idx_out[beg + t] = cand ? cand[beg + t] : beg + t;
             }
         }
         if (chunk == 0 && tid == 0) hdr->sort_side[pass] = first_pass ? 1u : side;
@@ -299,7 +304,7 @@ __global__ void __launch_bounds__(SORT_THREADS, SORT_MIN_BLOCKS) depth_pass_kern
     for (int r = 0; r < SORT_ROUNDS; r++) {
         const uint32_t i = base + r * 32 + lane;
         k[r] = (i < P) ? key_in[i] : 0xFFFFFFFFu;
-        v[r] = (first_pass || i >= P) ? i : idx_in[i];
+        v[r] = i >= P ? i : (first_pass ? (cand ? cand[i] : i) : idx_in[i]);
     }
 #pragma unroll
     for (int r = 0; r < SORT_ROUNDS; r++) {
@@ -360,7 +365,7 @@ __global__ void __launch_bounds__(SORT_THREADS, SORT_MIN_BLOCKS) depth_pass_kern
     }
     __syncthreads();
     BIN_MARK(tl_slot, 4);
-    const uint32_t n = min((uint32_t)GS_SORT_CHUNK, P - chunk * GS_SORT_CHUNK);
+    const uint32_t n = chunk * GS_SORT_CHUNK < P ? min((uint32_t)GS_SORT_CHUNK, P - chunk * GS_SORT_CHUNK) : 0u;
 #pragma unroll 4
     for (uint32_t t = tid; t < n; t += SORT_THREADS) {
         const uint32_t kk = s_key[t];
@@ -382,16 +387,17 @@ template <int NB>
 __global__ void __launch_bounds__(256) row_count_kernel(const uint32_t* __restrict__ idx0,
                                                         const uint32_t* __restrict__ idx1,
                                                         const GsHeader* __restrict__ hdr,
-                                                        const ushort4* __restrict__ rect, uint32_t P, int gy,
-                                                        uint32_t* __restrict__ chunk_cnt /*[gy][nchunks]*/) {
+                                                        const ushort4* __restrict__ rect, uint32_t P, int use_cand,
+                                                        int gy, uint32_t* __restrict__ chunk_cnt /*[gy][nchunks]*/) {
     constexpr int G = NB / 32;
     const uint32_t* __restrict__ sorted_idx = hdr->sort_side[3] ? idx1 : idx0;  // output side of the depth sort
+    if (use_cand) P = hdr->num_cand;
     __shared__ int s_d[NB + 1];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t chunk = blockIdx.x, nchunks = gridDim.x;
     for (int i = tid; i <= NB; i += 256) s_d[i] = 0;
     __syncthreads();
-    const uint32_t ibeg = chunk * GS_PART_CHUNK, iend = min(P, ibeg + (uint32_t)GS_PART_CHUNK);
+    const uint32_t ibeg = min(P, chunk * GS_PART_CHUNK), iend = min(P, ibeg + (uint32_t)GS_PART_CHUNK);
     for (uint32_t i = ibeg + tid; i < iend; i += 256) {
         const ushort4 rc = rect[sorted_idx[i]];
         if (rc.w > rc.y) {
@@ -601,7 +607,7 @@ __global__ void __launch_bounds__(1024) plan_kernel(const uint32_t* __restrict__
 template <int NB, int PASS>
 __global__ void __launch_bounds__(256, (NB == 128) ? PART_MIN_BLOCKS : 2) range_partition_kernel(
     const uint32_t* __restrict__ idx0, const uint32_t* __restrict__ idx1,  // PASS 1 input: the depth order (either side)
-    const ushort4* __restrict__ rect, uint32_t P,
+    const ushort4* __restrict__ rect, uint32_t P, int use_cand,
     const uint2* __restrict__ items_in,                                                      // PASS 2 input
     const int* __restrict__ rdiff, int gx, int gy, const uint32_t* __restrict__ tile_start,
     unsigned long long RowCap, const uint32_t* __restrict__ chunk_base /*[chunks][GS_MAX_GRID]*/,
@@ -617,6 +623,7 @@ __global__ void __launch_bounds__(256, (NB == 128) ? PART_MIN_BLOCKS : 2) range_
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (PASS == 2 && hdr->skip) return;
     const uint32_t* __restrict__ sorted_idx = (PASS == 1 && hdr->sort_side[3]) ? idx1 : idx0;
+    const uint32_t Pn = (PASS == 1 && use_cand) ? hdr->num_cand : P;  // row pass input: the depth-sorted candidates
     if (warp == 0) row_tables(rdiff, gy, s_rs, s_cf, lane);
     __syncthreads();
     if ((unsigned long long)s_rs[gy] > RowCap) {  // no-sync mode: row-item buffer too small -> frame is skipped
@@ -645,8 +652,8 @@ __global__ void __launch_bounds__(256, (NB == 128) ? PART_MIN_BLOCKS : 2) range_
         uint32_t ibeg, iend;
         int first = 0, row = 0;
         if (PASS == 1) {
-            ibeg = chunk * GS_PART_CHUNK;
-            iend = min(P, ibeg + (uint32_t)GS_PART_CHUNK);
+            ibeg = min(Pn, chunk * GS_PART_CHUNK);
+            iend = min(Pn, ibeg + (uint32_t)GS_PART_CHUNK);
         } else {
             row = chunk_row(s_cf, gy, chunk);
             first = (int)s_cf[row];
@@ -793,7 +800,9 @@ cudaError_t gs_launch_depth_sort(const GsFrame& f, const GsGeom& g) {
         return cudaFuncSetAttribute(depth_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_SMEM);
     }));
     const unsigned chunks = (unsigned)g.sort_chunks;
-    depth_hist_kernel<<<(unsigned)min((size_t)HIST_CTAS, gs_div_up(P, 4096)), 1024, 0, f.stream>>>(g.key[0], P, g.dhist);
+    const uint32_t* cand = f.cull ? g.cand : nullptr;
+    depth_hist_kernel<<<(unsigned)min((size_t)HIST_CTAS, gs_div_up(P, 4096)), 1024, 0, f.stream>>>(
+        g.key[0], P, f.cull ? &g.hdr->num_cand : nullptr, g.dhist);
     gs_note_launch();
     GS_TRY(cudaGetLastError());
     for (int pass = 0; pass < 4; pass++) {
@@ -801,7 +810,7 @@ cudaError_t gs_launch_depth_sort(const GsFrame& f, const GsGeom& g) {
                             g.dinc + (size_t)pass * chunks * GS_RADIX};
         depth_pass_kernel<<<chunks, SORT_THREADS, SORT_SMEM, f.stream>>>(g.key[0], g.idx[0], g.key[1], g.idx[1],
                                                                         g.dhist + pass * GS_RADIX, ch,
-                                                                        &g.hdr->tickets[pass], g.hdr, P, pass);
+                                                                        &g.hdr->tickets[pass], g.hdr, P, pass, cand);
         gs_note_launch();
         GS_TRY(cudaGetLastError());
     }
@@ -832,14 +841,14 @@ cudaError_t gs_launch_tile_lists(const GsFrame& f, const GsGeom& g, const GsBinn
     const unsigned long long rowcap = RowCap;
 #define LAUNCH_PART(NB, PASS, GRID)                                                                               \
     range_partition_kernel<NB, PASS><<<GRID, 256, PART_SMEM(NB), f.stream>>>(                                     \
-        g.idx[0], g.idx[1], g.rect, P, b.items, im.rdiff, f.gx, f.gy, im.tile_start, rowcap,                       \
+        g.idx[0], g.idx[1], g.rect, P, f.cull ? 1 : 0, b.items, im.rdiff, f.gx, f.gy, im.tile_start, rowcap,       \
         (PASS == 1) ? g.ragg : b.cagg,                                                                            \
         &g.hdr->tickets[3 + PASS], g.hdr, b.items, b.list)
     // row counts per chunk -> output positions; row pass: Gaussians in depth order -> row items grouped by tile row
     if (f.gy <= 128)
-        row_count_kernel<128><<<(unsigned)g.row_chunks, 256, 0, f.stream>>>(g.idx[0], g.idx[1], g.hdr, g.rect, P, f.gy, g.ragg);
+        row_count_kernel<128><<<(unsigned)g.row_chunks, 256, 0, f.stream>>>(g.idx[0], g.idx[1], g.hdr, g.rect, P, f.cull ? 1 : 0, f.gy, g.ragg);
     else
-        row_count_kernel<256><<<(unsigned)g.row_chunks, 256, 0, f.stream>>>(g.idx[0], g.idx[1], g.hdr, g.rect, P, f.gy, g.ragg);
+        row_count_kernel<256><<<(unsigned)g.row_chunks, 256, 0, f.stream>>>(g.idx[0], g.idx[1], g.hdr, g.rect, P, f.cull ? 1 : 0, f.gy, g.ragg);
     gs_note_launch();
     GS_TRY(cudaGetLastError());
     row_scan_kernel<<<(unsigned)f.gy, 32, 0, f.stream>>>(im.rdiff, f.gy, (uint32_t)g.row_chunks, g.ragg);

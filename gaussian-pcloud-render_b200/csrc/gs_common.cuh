@@ -15,6 +15,8 @@
 //     cov3D [P][6] f32    world covariance (only when computed from scale/rotation)
 //     clamp [P] u8        bit c set = SH colour channel c was clamped at 0
 //     xrec  [P][3] float4 colours of up to three extra passes blended in the same list walk (GsScene.extra_colors)
+//     cand  [P] u32       GsScene.shard_cull: ascending indices of the Gaussians that may reach the shard's tile rows;
+//     cmask [P/32] u32, ccount [P/4096 + 1] u32: their bit mask and per-block counts (compaction scratch)
 //   binning buffer (per instance, R entries)
 //     list  [R] u32       final per-tile, depth-ordered Gaussian index list ("point_list"); FIRST, so that backward
 //                         finds it from num_rendered alone
@@ -57,7 +59,8 @@ struct GsHeader {  // lives at offset 0 of the geometry buffer
                                  // 10 blend-backward work queue, 11 CTA arrival order of the blend kernel
     unsigned int sort_side[4];   // depth sort: side (0 / 1) of the key / idx ping-pong that holds the output of pass p
                                  // (an identity pass -- all keys share the digit -- moves nothing and keeps the side)
-    unsigned int pad[36];
+    unsigned int num_cand;       // GsScene.shard_cull: Gaussians that may reach the shard's tile rows (= entries of cand[])
+    unsigned int pad[35];
 };
 static_assert(sizeof(GsHeader) == 256, "header is one aligned slot");
 
@@ -82,6 +85,7 @@ struct GsCarver {
 #define GS_SORT_CHUNK 8192   // depth keys per CTA and pass
 #endif
 #define GS_PART_CHUNK 2048   // items per CTA of the row / column partition passes
+#define GS_CULL_CHUNK 4096   // Gaussians per CTA of the shard-cull kernels
 #define GS_MAX_GRID 256      // at most 256 x 256 tiles (4096 x 4096 pixels)
 #define GS_PARK_CAP 2048     // pixel blocks per frame that can be handed to the blend team kernel
 #define GS_PARK_WORDS 384    // saved state of one pixel block: 12 words x 32 lanes
@@ -110,7 +114,8 @@ struct GsGeom {
     float* cov3D;
     uint8_t* clamp;
     float4* xrec;      // [P][3] colours of up to three extra passes (rgb + pad), gathered like rec by the blend
-    size_t sort_chunks, row_chunks, zero_bytes, bytes;
+    uint32_t* cand; uint32_t* cmask; uint32_t* ccount;  // shard cull (see above)
+    size_t sort_chunks, row_chunks, cull_chunks, zero_bytes, bytes;
     __host__ __device__ GsGeom(char* base, size_t P) {
         GsCarver c(base);
         hdr = c.take<GsHeader>(1);
@@ -130,6 +135,10 @@ struct GsGeom {
         cov3D = c.take<float>(6 * P);
         clamp = c.take<uint8_t>(P);
         xrec = c.take<float4>(3 * P);
+        cull_chunks = gs_div_up(P, GS_CULL_CHUNK);
+        cand = c.take<uint32_t>(P);
+        cmask = c.take<uint32_t>(cull_chunks * (GS_CULL_CHUNK / 32));
+        ccount = c.take<uint32_t>(cull_chunks + 1);
         bytes = c.off + GS_ALIGN;
     }
 };
@@ -223,11 +232,14 @@ struct GsFrame {  // host-side derived quantities handed to every launcher
     GsScene s;
     int gx, gy, Tn;        // tile grid
     int row0, row1;        // tile-row shard
+    bool cull;             // GsScene.shard_cull on a proper shard: per-Gaussian work runs on the compacted candidates
     float focal_x, focal_y;
     cudaStream_t stream;
 };
 
 // stage launchers (each in its own translation unit)
+// f.cull: candidates of the tile-row shard -> g.cand / hdr->num_cand (before gs_launch_preprocess)
+cudaError_t gs_launch_shard_cull(const GsFrame& f, const GsGeom& g);
 cudaError_t gs_launch_preprocess(const GsFrame& f, const GsGeom& g, const GsImage& im, int32_t* radii);
 cudaError_t gs_launch_recolor(const GsFrame& f, const GsGeom& g);  // colour-only pass (gs_forward_recolor)
 cudaError_t gs_launch_pack_extra(const GsFrame& f, const GsGeom& g);  // GsScene.extra_colors -> g.xrec

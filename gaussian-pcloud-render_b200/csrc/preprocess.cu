@@ -23,6 +23,7 @@ struct PreArgs {
     GsRec* rec; uint32_t* key; ushort4* rect; uint32_t* ntile; float* cov3D; uint8_t* clamp;
     int* rdiff;
     GsHeader* hdr;
+    const uint32_t* cand;  // shard cull: thread t handles Gaussian cand[t], t < hdr->num_cand (nullptr: Gaussian t, t < P)
 };
 
 // SH -> RGB for one Gaussian; coefficient stride is M (may exceed (D+1)^2), SURVEY App. A item 9.
@@ -89,7 +90,10 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 // banks (conflict-free for the benchmark's M = 13) instead of fetching partial sectors through L1.
 template <bool STAGED>
 __global__ void __launch_bounds__(256) preprocess_kernel(const PreArgs a) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int pos = blockIdx.x * blockDim.x + threadIdx.x;  // position in the depth-sort input
+    const int n = a.cand ? (int)a.hdr->num_cand : a.P;
+    if (a.cand && blockIdx.x * blockDim.x >= n) return;  // (whole block past the candidates)
+    const int i = (a.cand && pos < n) ? (int)a.cand[pos] : pos;  // the Gaussian
     extern __shared__ __align__(128) unsigned char s_stage[];
     const float* mp = a.means + 3 * (size_t)i;
     const float* sp = a.scales ? a.scales + 3 * (size_t)i : nullptr;
@@ -127,7 +131,7 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreArgs a) {
     __shared__ int s_rd[GS_MAX_GRID + 1];  // this block's share of the row difference array
     for (int y = threadIdx.x; y <= a.gy; y += 256) s_rd[y] = 0;
     __syncthreads();
-    if (i < a.P) {
+    if (pos < n) {
         int radius_out = 0;
         uint32_t key = 0xFFFFFFFFu;  // culled Gaussians sort to the end of the depth order
         ushort4 rect = make_ushort4(0, 0, 0, 0);
@@ -210,7 +214,7 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreArgs a) {
             my_vis = 1;
         } while (false);
         if (a.radii) a.radii[i] = radius_out;
-        a.key[i] = key;
+        a.key[pos] = key;
         a.rect[i] = rect;
         a.ntile[i] = my_tiles;
     }
@@ -239,6 +243,140 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreArgs a) {
     for (int y = threadIdx.x; y <= a.gy; y += 256) {  // the __syncthreads_or above ordered the shared atomics
         const int d = s_rd[y];
         if (d) atomicAdd(&a.rdiff[y], d);
+    }
+}
+
+
+// ---- Shard cull (GsScene.shard_cull): which Gaussians can reach tile rows [row0, row1)? ---------------------------------
+// A Gaussian is kept unless its splat provably misses the shard: same near-plane test and the same pixel y as the
+// per-Gaussian stage (identical expressions), and an upper bound R on its screen radius ceil(3 sqrt(lambda_max)):
+//   lambda_max(Sigma') <= trace(Sigma') = a + c,   a <= |j0|^2 |W|_F^2 trace(V) + 0.3,   c likewise with j1,
+// (j0, j1 the rows of the projection Jacobian, W the view rotation, V the world covariance, trace(V) = sum_k S_k^2 |a_k|^2
+// for V = A S^2 A^T), plus a relative allowance for rounding and the reference's max(0.1, .) under the square root.
+// Reads 40 B per Gaussian instead of the 92 - 236 B of the full stage.  The three kernels (flags + counts per
+// 4096-block, scan of the block counts, ordered scatter) give the ascending candidate list: the depth sort's stable
+// tie order is the Gaussian index, so the compaction must keep it.
+__device__ __forceinline__ bool shard_candidate(const PreArgs& a, int i) {
+    const float3 mean = make_float3(a.means[3 * (size_t)i], a.means[3 * (size_t)i + 1], a.means[3 * (size_t)i + 2]);
+    const float3 p_view = xform43(a.view, mean);
+    if (p_view.z <= 0.2f) return false;
+    const float4 p_hom = xform44(a.proj, mean);
+    const float p_w = 1.0f / (p_hom.w + 0.0000001f);
+    const float py = ndc_to_pix(p_hom.y * p_w, a.H);
+    float tr;  // trace of the world covariance
+    if (a.cov3D_pre != nullptr) {
+        tr = a.cov3D_pre[6 * (size_t)i] + a.cov3D_pre[6 * (size_t)i + 3] + a.cov3D_pre[6 * (size_t)i + 5];
+    } else {
+        const float r = a.rots[4 * (size_t)i], x = a.rots[4 * (size_t)i + 1], y = a.rots[4 * (size_t)i + 2],
+                    z = a.rots[4 * (size_t)i + 3];
+        const float s0 = a.mod * a.scales[3 * (size_t)i], s1 = a.mod * a.scales[3 * (size_t)i + 1],
+                    s2 = a.mod * a.scales[3 * (size_t)i + 2];
+        // squared column norms of the (un-normalised) quaternion's rotation matrix
+        const float a00 = 1.f - 2.f * (y * y + z * z), a10 = 2.f * (x * y + r * z), a20 = 2.f * (x * z - r * y);
+        const float a01 = 2.f * (x * y - r * z), a11 = 1.f - 2.f * (x * x + z * z), a21 = 2.f * (y * z + r * x);
+        const float a02 = 2.f * (x * z + r * y), a12 = 2.f * (y * z - r * x), a22 = 1.f - 2.f * (x * x + y * y);
+        tr = s0 * s0 * (a00 * a00 + a10 * a10 + a20 * a20) + s1 * s1 * (a01 * a01 + a11 * a11 + a21 * a21) +
+             s2 * s2 * (a02 * a02 + a12 * a12 + a22 * a22);
+    }
+    const float* vm = a.view;
+    const float wn = vm[0] * vm[0] + vm[1] * vm[1] + vm[2] * vm[2] + vm[4] * vm[4] + vm[5] * vm[5] + vm[6] * vm[6] +
+                     vm[8] * vm[8] + vm[9] * vm[9] + vm[10] * vm[10];
+    const float iz = 1.0f / p_view.z;
+    const float ux = fminf(1.3f * a.tanx, fabsf(p_view.x * iz)), uy = fminf(1.3f * a.tany, fabsf(p_view.y * iz));
+    const float j0 = (a.fx * iz) * (a.fx * iz) * (1.f + ux * ux), j1 = (a.fy * iz) * (a.fy * iz) * (1.f + uy * uy);
+    const float lam = (j0 + j1) * wn * tr * 1.01f + 1.0f;  // >= a + c + 0.32 with room for rounding
+    if (!(lam < 1.0e12f)) return true;                     // overflow / NaN: let the full stage decide
+    const float R = ceilf(3.f * sqrtf(lam)) + 1.f;
+    const int y0 = min(a.gy, max(0, (int)((py - R) / GS_TILE)));
+    const int y1 = min(a.gy, max(0, (int)((py + R + GS_TILE - 1) / GS_TILE)));
+    return max(y0, a.row0) < min(y1, a.row1);
+}
+
+__global__ void __launch_bounds__(256) shard_flag_kernel(const PreArgs a, uint32_t* __restrict__ cmask,
+                                                         uint32_t* __restrict__ ccount) {
+    __shared__ unsigned s_cnt[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t base = (size_t)blockIdx.x * GS_CULL_CHUNK;
+    unsigned mine = 0;
+#pragma unroll 4
+    for (int r = 0; r < GS_CULL_CHUNK / 256; r++) {
+        const size_t i = base + (size_t)r * 256 + threadIdx.x;
+        const bool keep = i < (size_t)a.P && shard_candidate(a, (int)i);
+        const unsigned m = __ballot_sync(GS_FULL, keep);
+        if (lane == 0) {
+            cmask[(base >> 5) + (size_t)r * 8 + warp] = m;
+            mine += __popc(m);
+        }
+    }
+    if (lane == 0) s_cnt[warp] = mine;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned tot = 0;
+        for (int k = 0; k < 8; k++) tot += s_cnt[k];
+        ccount[blockIdx.x] = tot;
+    }
+}
+
+// One CTA: exclusive scan of the block counts (in place), total -> hdr->num_cand.
+__global__ void __launch_bounds__(1024) shard_scan_kernel(uint32_t* __restrict__ ccount, int nblocks,
+                                                          GsHeader* __restrict__ hdr) {
+    __shared__ unsigned s_w[32];
+    __shared__ unsigned s_run;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_run = 0;
+    __syncthreads();
+    for (int b0 = 0; b0 < nblocks; b0 += 1024) {
+        const int b = b0 + threadIdx.x;
+        const unsigned v = b < nblocks ? ccount[b] : 0u;
+        unsigned incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned u = __shfl_up_sync(GS_FULL, incl, o);
+            if (lane >= o) incl += u;
+        }
+        if (lane == 31) s_w[warp] = incl;
+        __syncthreads();
+        unsigned pre = s_run;
+        for (int w = 0; w < warp; w++) pre += s_w[w];
+        if (b < nblocks) ccount[b] = pre + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_run = pre + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) hdr->num_cand = s_run;
+}
+
+__global__ void __launch_bounds__(256) shard_scatter_kernel(const uint32_t* __restrict__ cmask,
+                                                            const uint32_t* __restrict__ ccount, int P,
+                                                            uint32_t* __restrict__ cand) {
+    __shared__ unsigned s_pre[GS_CULL_CHUNK / 32];  // exclusive prefix of the 128 mask words of this block
+    __shared__ unsigned s_w[4];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t wbase = (size_t)blockIdx.x * (GS_CULL_CHUNK / 32);
+    unsigned word = 0, incl = 0;
+    if (threadIdx.x < GS_CULL_CHUNK / 32) {
+        word = cmask[wbase + threadIdx.x];
+        incl = __popc(word);
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned u = __shfl_up_sync(GS_FULL, incl, o);
+            if (lane >= o) incl += u;
+        }
+        if (lane == 31) s_w[warp] = incl;
+    }
+    __syncthreads();
+    if (threadIdx.x < GS_CULL_CHUNK / 32) {
+        unsigned pre = ccount[blockIdx.x];
+        for (int w = 0; w < warp; w++) pre += s_w[w];
+        s_pre[threadIdx.x] = pre + incl - __popc(word);
+    }
+    __syncthreads();
+    for (int k = warp; k < GS_CULL_CHUNK / 32; k += 8) {  // warp k-th word: lane l <-> Gaussian 32 (wbase + k) + l
+        const unsigned m = cmask[wbase + k];
+        if ((m >> lane) & 1u) {
+            const size_t i = ((wbase + k) << 5) + lane;
+            if (i < (size_t)P) cand[s_pre[k] + __popc(m & ((1u << lane) - 1u))] = (uint32_t)i;
+        }
     }
 }
 
@@ -380,7 +518,7 @@ __global__ void __launch_bounds__(HEAD_PTS) decode_head_kernel(const float* __re
 
 }  // namespace
 
-cudaError_t gs_launch_preprocess(const GsFrame& f, const GsGeom& g, const GsImage& im, int32_t* radii) {
+static PreArgs make_pre_args(const GsFrame& f, const GsGeom& g, const int* rdiff, int32_t* radii) {
     const GsScene& s = f.s;
     PreArgs a;
     a.P = s.P; a.D = s.sh_degree; a.M = s.sh_stride; a.W = s.width; a.H = s.height; a.gx = f.gx; a.gy = f.gy;
@@ -392,17 +530,41 @@ cudaError_t gs_launch_preprocess(const GsFrame& f, const GsGeom& g, const GsImag
     a.campos = s.campos;
     a.radii = radii;
     a.rec = g.rec; a.key = g.key[0]; a.rect = g.rect; a.ntile = g.ntile; a.cov3D = g.cov3D;
-    a.clamp = g.clamp; a.rdiff = im.rdiff; a.hdr = g.hdr;
+    a.clamp = g.clamp; a.rdiff = const_cast<int*>(rdiff); a.hdr = g.hdr;
+    a.cand = f.cull ? g.cand : nullptr;
+    return a;
+}
+
+cudaError_t gs_launch_shard_cull(const GsFrame& f, const GsGeom& g) {
+    if (!f.cull) return cudaSuccess;
+    const PreArgs a = make_pre_args(f, g, nullptr, nullptr);
+    const unsigned nblocks = (unsigned)g.cull_chunks;
+    // ntile of a Gaussian outside the shard must read 0 (gs_forward_recolor, gs_fetch): the full stage will not visit it
+    cudaError_t e = cudaMemsetAsync(g.ntile, 0, sizeof(uint32_t) * (size_t)f.s.P, f.stream);
+    if (e != cudaSuccess) return e;
+    shard_flag_kernel<<<nblocks, 256, 0, f.stream>>>(a, g.cmask, g.ccount);
+    gs_note_launch();
+    shard_scan_kernel<<<1, 1024, 0, f.stream>>>(g.ccount, (int)nblocks, g.hdr);
+    gs_note_launch();
+    shard_scatter_kernel<<<nblocks, 256, 0, f.stream>>>(g.cmask, g.ccount, f.s.P, g.cand);
+    gs_note_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t gs_launch_preprocess(const GsFrame& f, const GsGeom& g, const GsImage& im, int32_t* radii) {
+    const GsScene& s = f.s;
+    const PreArgs a = make_pre_args(f, g, im.rdiff, radii);
     // TMA-staged variant: scale/rotation + SH inputs, every slab 16-B aligned, and the staging buffer fits
     const size_t stage_bytes = (size_t)(3 + 3 + 4 + 1) * 256 * 4 + (size_t)256 * s.sh_stride * 12;
     auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
     // ... and at least half of every SH row is actually read (bulk copies fetch whole rows; the pcrender shape reads 4
     // of its 13 coefficients, there the direct path moves fewer bytes).  Measured on B200: neutral at C2 and C4 --
     // the kernel is bound by its scattered 48-B record stores and per-thread latency, not by the input reads.
+    // (Not with shard cull: the candidates of a block are not contiguous.)
     const bool sh_dense = 2 * (s.sh_degree + 1) * (s.sh_degree + 1) > s.sh_stride;
-    const bool staged = sh_dense && s.P >= 256 && s.scales && s.rotations && s.shs && !s.cov3D_precomp && !s.colors_precomp &&
-                        stage_bytes <= 100 * 1024 && al16(s.means3D) && al16(s.scales) && al16(s.rotations) &&
-                        al16(s.opacities) && al16(s.shs);
+    const bool staged = !f.cull && sh_dense && s.P >= 256 && s.scales && s.rotations && s.shs && !s.cov3D_precomp &&
+                        !s.colors_precomp && stage_bytes <= 100 * 1024 && al16(s.means3D) && al16(s.scales) &&
+                        al16(s.rotations) && al16(s.opacities) && al16(s.shs);
     if (staged) {
         static GsPerDevice per_dev;
         const int* dv = nullptr;

@@ -64,7 +64,7 @@ class FrameRenderer:
             self.binning = torch.empty(self.L.gs_binning_bytes(self.capacity, self.P, self.W, self.H),
                                        dtype=torch.uint8, device=self.dev)
 
-    def _scene(self, view_dev, tile_rows, peer_out=None, extra_passes=None):
+    def _scene(self, view_dev, tile_rows, peer_out=None, extra_passes=None, shard_cull=False):
         viewmatrix, projmatrix, campos, tanx, tany = view_dev
         return _C.make_scene(P=self.P, sh_degree=self.sh_degree, sh_stride=int(self.shs.shape[1]), width=self.W,
                              height=self.H, tan_fovx=float(tanx), tan_fovy=float(tany), scale_modifier=1.0,
@@ -72,7 +72,8 @@ class FrameRenderer:
                              colors_precomp=None, opacities=self.opacities, scales=self.scales,
                              rotations=self.rotations, cov3D_precomp=None, viewmatrix=viewmatrix,
                              projmatrix=projmatrix, campos=campos, tile_rows=tile_rows, peer_out=peer_out,
-                             extra_passes=extra_passes, downsample=self.downsample, team_after=self.team_after)
+                             extra_passes=extra_passes, downsample=self.downsample, team_after=self.team_after,
+                             shard_cull=shard_cull)
 
     def upload_view(self, view):
         """host View (scenes.make_view) -> device tensors; done once per camera, outside the frame loop."""
@@ -80,14 +81,18 @@ class FrameRenderer:
         return (t(view.viewmatrix), t(view.projmatrix), t(view.campos), view.tanfovx, view.tanfovy)
 
     def enqueue(self, view_dev, out_color: Optional[torch.Tensor] = None, tile_rows=None, slot: int = 0,
-                peer_out=None, extra_passes=None) -> torch.Tensor:
+                peer_out=None, extra_passes=None, shard_cull: bool = False) -> torch.Tensor:
         """Queues one frame on the current stream; no host synchronisation.  Returns the (3,H,W) colour tensor.
         peer_out: device pointers of the (3,H,W) images of all ranks (sharding.PeerFrame): the blend epilogue then
         writes this rank's tile rows into every one of them instead of into out_color.
         extra_passes: up to three (colors (P,3), out (3,H,W)) pairs of contiguous fp32 CUDA tensors blended in the same
-        list walk as the frame; each `out` equals a separate forward with colors_precomp = colors."""
+        list walk as the frame; each `out` equals a separate forward with colors_precomp = colors.
+        shard_cull (with tile_rows): Gaussians that cannot reach the shard's rows are dropped before the per-Gaussian
+        stage, which then runs -- like the depth sort and the list passes -- on the survivors only (pixels unchanged;
+        `self.radii` is only updated for the survivors)."""
         out = self.color if out_color is None else out_color
-        scene = self._scene(view_dev, tile_rows if tile_rows is not None else self.tile_rows, peer_out, extra_passes)
+        scene = self._scene(view_dev, tile_rows if tile_rows is not None else self.tile_rows, peer_out, extra_passes,
+                            shard_cull)
         with torch.cuda.device(self.dev):
             st = torch.cuda.current_stream(self.dev).cuda_stream
             _C._check(self.L.gs_forward_nosync(C.byref(scene), self.geom.data_ptr(), self.binning.data_ptr(),

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define GS_ABI_VERSION 4
+#define GS_ABI_VERSION 5
 
 enum {
     GS_OK = 0,
@@ -90,6 +90,14 @@ typedef struct GsScene {
     int32_t team_after;
     const float* extra_colors[3];  /* each [P][3] */
     float* extra_out[3];           /* each [3][H][W] */
+    /* Tile-row shards only (multi-GPU): != 0 lets the rank skip, BEFORE the per-Gaussian stage, every Gaussian whose
+     * splat cannot reach its tile rows (a conservative bound on the screen radius from the trace of the world
+     * covariance; one pass over means / scales / rotations, 40 of the 92-236 input bytes per point), and run the
+     * per-Gaussian stage, the depth sort and the list passes on the compacted survivors.  Pixels are unchanged;
+     * `radii` is then only written for the survivors (0 = "not in this shard" for a caller-zeroed array), so leave it
+     * 0 when a backward pass needs the radii of the whole frame. */
+    int32_t shard_cull;
+    int32_t reserved3;
 } GsScene;
 
 /* Growable scratch buffer: fn(user, bytes) must return a DEVICE pointer to at least `bytes` bytes that stays

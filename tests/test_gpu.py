@@ -941,3 +941,71 @@ print('TEAM OK' if ok else 'TEAM MISMATCH')
 """ % (ROOT, ROOT)
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=240)
     assert "TEAM OK" in out.stdout, out.stdout[-1500:] + out.stderr[-1500:]
+
+
+def test_two_devices_in_one_process():
+    """The library keeps its launcher state (dynamic shared-memory opt-ins, grid sizes) per device: one process renders
+    the same frame, forward and backward, on cuda:0 and then on cuda:1.  Needs two GPUs."""
+    _dev()
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    cl = scenes.human_cloud(60000, scale_factor=300.0, seed=5, opacity="uniform")
+    v = scenes.make_view(scenes.orbit_c2w(9)[2], 800, 600)
+    kw = dict(means3D=cl["means3D"], opacities=cl["opacities"], W=800, H=600, viewmatrix=v.viewmatrix,
+              projmatrix=v.projmatrix, campos=v.campos, bg=np.ones(3, np.float32), tanfovx=v.tanfovx, tanfovy=v.tanfovy,
+              sh_degree=1, shs=cl["shs"], scales=cl["scales"], rotations=cl["rotations"])
+    wgt = torch.from_numpy(loss_weights((3, 600, 800)))
+    res = []
+    for d in (0, 1, 0):
+        dev = torch.device("cuda", d)
+        color, radii, leaves, _ = _render(kw, dev, requires_grad=True)
+        color.backward(wgt.to(dev))
+        torch.cuda.synchronize(dev)
+        res.append((color.detach().cpu(), radii.cpu(), leaves["means3D"].grad.cpu()))
+    for c, r, g in res[1:]:
+        assert torch.equal(c, res[0][0]) and torch.equal(r, res[0][1])
+        assert float((g - res[0][2]).abs().max()) <= GRAD_RTOL * float(res[0][2].abs().max())
+
+
+@pytest.mark.parametrize("kind", ["human", "random_sh3"])
+def test_shard_cull_reassembles_the_frame_bitwise(kind):
+    """GsScene.shard_cull: a tile-row shard whose per-Gaussian stage, depth sort and list passes run only on the
+    Gaussians that can reach its rows (conservative radius bound + ordered compaction) renders exactly the pixels,
+    transmittances and contributor counts of the full frame in its rows; its candidate set contains every Gaussian
+    that has an instance in the shard and is much smaller than the cloud."""
+    dev = _dev()
+    from diff_gaussian_rasterization import _C
+    from renderer import FrameRenderer
+    if kind == "human":
+        cl, W, H, bg = scenes.human_cloud(150000, scale_factor=320.0, seed=3, opacity="uniform"), 1000, 600, [1, 1, 1]
+    else:
+        cl, W, H, bg = scenes.random_cloud(400000, seed=4, sh_degree=3), 1024, 768, [0, 0, 0]
+    gy = (H + 15) // 16
+    fr = FrameRenderer(cl, W, H, bg, dev, capacity=30_000_000)
+    for k in (1, 4):
+        vd = fr.upload_view(scenes.make_view(scenes.orbit_c2w(9)[k], W, H))
+        full = fr.render(vd).clone()
+        sc = fr._scene(vd, None)
+        T_full = _C.fetch("final_T", sc, fr.geom, fr.binning, fr.img, fr.capacity).view(H, W)
+        n_full = _C.fetch("n_contrib", sc, fr.geom, fr.binning, fr.img, fr.capacity).view(H, W)
+        touched_full = _C.fetch("tiles_touched", sc, fr.geom, fr.binning, fr.img, fr.capacity)
+        acc = torch.zeros_like(full)
+        cuts = [0, 3, 4, gy // 2, gy - 5, gy]
+        for r0, r1 in zip(cuts[:-1], cuts[1:]):
+            part = torch.zeros_like(full)
+            fr.enqueue(vd, out_color=part, tile_rows=(r0, r1), shard_cull=True)
+            torch.cuda.synchronize()
+            nr, nvis, code = fr.status()
+            assert code == 0
+            y0, y1 = r0 * 16, min(H, r1 * 16)
+            assert torch.equal(part[:, y0:y1], full[:, y0:y1])
+            assert float(part[:, :y0].abs().max() if y0 else 0) == 0 and float(part[:, y1:].abs().max() if y1 < H else 0) == 0
+            sc = fr._scene(vd, (r0, r1), shard_cull=True)
+            assert torch.equal(_C.fetch("final_T", sc, fr.geom, fr.binning, fr.img, fr.capacity).view(H, W)[y0:y1], T_full[y0:y1])
+            assert torch.equal(_C.fetch("n_contrib", sc, fr.geom, fr.binning, fr.img, fr.capacity).view(H, W)[y0:y1], n_full[y0:y1])
+            touched = _C.fetch("tiles_touched", sc, fr.geom, fr.binning, fr.img, fr.capacity)
+            assert int(touched.sum()) == nr and bool((touched <= touched_full).all())
+            assert 0 < nvis <= int((touched_full > 0).sum())          # visible Gaussians among the candidates
+            acc += part
+        assert torch.equal(acc, full)
+        assert torch.equal(fr.render(vd), full)                       # and the plain path afterwards is unaffected

@@ -33,7 +33,7 @@ for i, v in enumerate(views):
     img, ptrs, barrier = peer.next()
     r0, r1 = rows[rank]
     if r1 > r0:
-        fr.enqueue(vd, tile_rows=(r0, r1), peer_out=ptrs)
+        fr.enqueue(vd, tile_rows=(r0, r1), peer_out=ptrs, shard_cull=bool(i % 2))  # with and without the shard cull
     barrier()
     torch.cuda.synchronize()
     same = bool(torch.equal(img, full))
