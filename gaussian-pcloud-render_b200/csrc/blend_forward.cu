@@ -595,6 +595,343 @@ __device__ __forceinline__ void team_serve(TmShared& S, GsHeader* __restrict__ h
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Split walks (latency mode 2, GsScene.blend_split; NOT bit-identical, pixels within ~1e-6 of the exact walk): what no
+// exact restructuring shortens is the serial walk of ONE long list (a silhouette block: 19 K entries, 3000 surviving
+// instances, 0.45 ms in one warp while the rest of the GPU is idle).  Front-to-back compositing is associative --
+// (C, T) of a list = (C_a + T_a C_b, T_a T_b) for any cut -- so a parked block's remaining list is cut into rounds of
+// eight segments, one per warp of a CTA: every warp walks its segment with the ordinary loop from the neutral state
+// (T = 1, C = 0), the eight partial results are merged in list order, and only a pixel whose early stop
+// (T (1 - alpha) < 1e-4, forward.cu:353-358) falls inside the round is walked again from the merged state with the
+// exact recurrence (by warp 0, cull box = just those pixels), so the stop position, n_contrib and final_T follow the
+// reference's rule on the merged transmittance.  Only the association of the sums differs from the reference.
+struct BfPix2 {  // compositing state of the two pixels of a lane
+    f2 T2;
+    float c0A, c0B, c1A, c1B, c2A, c2B;
+    uint32_t lastA, lastB;
+    bool doneA, doneB;
+};
+
+// The warp-per-block loop of the kernel below over list entries [beg, end) (beg a multiple of 32), state in / out.
+__device__ __forceinline__ void bf_walk(BfStage<0>* __restrict__ ring, const uint32_t* __restrict__ lst,
+                                        const GsRec* __restrict__ rec, uint32_t beg, uint32_t end, int bx0, int by0,
+                                        float pfx, f2 pfy2, BfPix2& s, int lane) {
+    float fx0 = 0.f, fx1 = 0.f, fy0 = 0.f, fy1 = 0.f;
+    auto live_box = [&]() -> bool {
+        const unsigned aliveA = __ballot_sync(GS_FULL, !s.doneA), aliveB = __ballot_sync(GS_FULL, !s.doneB);
+        const unsigned both = aliveA | aliveB;
+        if (both == 0u) return false;
+        const unsigned cols = (both | (both >> 8) | (both >> 16) | (both >> 24)) & 0xffu;
+        unsigned rows = 0;
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            rows |= ((aliveA >> (8 * r)) & 0xffu) ? (1u << r) : 0u;
+            rows |= ((aliveB >> (8 * r)) & 0xffu) ? (16u << r) : 0u;
+        }
+        fx0 = (float)(bx0 + __ffs(cols) - 1); fx1 = (float)(bx0 + 31 - __clz(cols));
+        fy0 = (float)(by0 + __ffs(rows) - 1); fy1 = (float)(by0 + 31 - __clz(rows));
+        return true;
+    };
+    if (beg >= end || !live_box()) return;
+    __syncwarp();
+#pragma unroll
+    for (int p = 0; p < 2; p++) {
+        if (beg + p * 32 + lane < end) {
+            const GsRec* r = rec + lst[beg + p * 32 + lane];
+            cp_async16(&ring[p].a[lane], &r->a);
+            cp_async16(&ring[p].b[lane], &r->b);
+            cp_async16(&ring[p].c[lane], &r->c);
+        }
+        cp_async_commit();
+    }
+    uint32_t id_next = (beg + 64 + lane < end) ? lst[beg + 64 + lane] : 0u;
+    int stage = 0;
+    uint32_t next_check = beg + BF_CHECK * 32;
+    for (uint32_t base = beg; base < end; base += 32) {
+        if (base == next_check) {
+            next_check += BF_CHECK * 32;
+            if (!live_box()) break;
+        }
+        cp_async_wait<1>();
+        __syncwarp();
+        {
+            int nst = stage + 2; if (nst >= BF_STAGES) nst -= BF_STAGES;
+            if (base + 64 + lane < end) {
+                const GsRec* r = rec + id_next;
+                cp_async16(&ring[nst].a[lane], &r->a);
+                cp_async16(&ring[nst].b[lane], &r->b);
+                cp_async16(&ring[nst].c[lane], &r->c);
+            }
+            cp_async_commit();
+            if (base + 96 + lane < end) id_next = lst[base + 96 + lane];
+        }
+        const BfStage<0>& st = ring[stage];
+        stage = (stage + 1 == BF_STAGES) ? 0 : stage + 1;
+        bool hit = false;
+        if (base + lane < end) {
+            const float4 a = st.a[lane], b = st.b[lane];
+            const float nBA = st.c[lane].w;
+            const float bound = box_max_power(a.z, a.w, b.x, nBA, b.w, a.x - fx1, a.x - fx0, a.y - fy1, a.y - fy0);
+            hit = !(bound < b.z);
+        }
+        unsigned mask = __ballot_sync(GS_FULL, hit);
+        while (mask) {
+            const int j = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const float4 ga = st.a[j], gb = st.b[j];
+            const float dx = ga.x - pfx;
+            const f2 dy2 = sub2(bc(ga.y), pfy2);
+            f2 t1 = mul2(bc(gb.x), dy2);
+            t1 = mul2(dy2, t1);
+            const float t2 = ga.z * dx, t3n = (-ga.w) * dx;
+            const f2 t3 = mul2(dy2, bc(t3n));
+            const f2 sm = fma2(bc(dx), bc(t2), t1);
+            const f2 p2 = fma2(sm, bc(-0.5f), t3);
+            const float pA = lo(p2), pB = hi(p2);
+            float alphaA = fminf(0.99f, gb.y * expf(pA)), alphaB = fminf(0.99f, gb.y * expf(pB));
+            const bool okA = !s.doneA && !(pA > 0.0f) && !(alphaA < 1.0f / 255.0f);
+            const bool okB = !s.doneB && !(pB > 0.0f) && !(alphaB < 1.0f / 255.0f);
+            if (!__any_sync(GS_FULL, okA || okB)) continue;
+            alphaA = okA ? alphaA : 0.0f;
+            alphaB = okB ? alphaB : 0.0f;
+            const f2 tt2 = mul2(s.T2, sub2(bc(1.0f), pk(alphaA, alphaB)));
+            const bool stopA = okA && lo(tt2) < 0.0001f, stopB = okB && hi(tt2) < 0.0001f;
+            s.doneA = s.doneA || stopA;
+            s.doneB = s.doneB || stopB;
+            alphaA = stopA ? 0.0f : alphaA;
+            alphaB = stopB ? 0.0f : alphaB;
+            const f2 a2 = pk(alphaA, alphaB);
+            const float4 gc = st.c[j];
+            const float TA = lo(s.T2), TB = hi(s.T2);
+            const f2 w0 = mul2(bc(gc.x), a2), w1 = mul2(bc(gc.y), a2), w2 = mul2(bc(gc.z), a2);
+            s.c0A = __fmaf_rn(lo(w0), TA, s.c0A); s.c0B = __fmaf_rn(hi(w0), TB, s.c0B);
+            s.c1A = __fmaf_rn(lo(w1), TA, s.c1A); s.c1B = __fmaf_rn(hi(w1), TB, s.c1B);
+            s.c2A = __fmaf_rn(lo(w2), TA, s.c2A); s.c2B = __fmaf_rn(hi(w2), TB, s.c2B);
+            s.T2 = pk(stopA ? TA : lo(tt2), stopB ? TB : hi(tt2));
+            if (okA && !stopA) s.lastA = base + (uint32_t)j + 1u;
+            if (okB && !stopB) s.lastB = base + (uint32_t)j + 1u;
+        }
+        if (__all_sync(GS_FULL, s.doneA && s.doneB)) break;
+    }
+    cp_async_wait<0>();
+    __syncwarp();
+}
+
+#ifndef SP_GMIN
+#define SP_GMIN 4    // batches per segment: at least / at most
+#define SP_GMAX 32
+#endif
+struct SpShared {  // behind the record rings of the eight warps
+    float T[BF_WARPS][64], c0[BF_WARPS][64], c1[BF_WARPS][64], c2[BF_WARPS][64];  // pixel A of lane l at l, pixel B at 32 + l
+    unsigned last[BF_WARPS][64];
+    unsigned stopped[BF_WARPS][32];  // bit 0 / 1: pixel A / B stopped inside the segment
+    float pT[64], p0[64], p1[64], p2[64];  // state after the exact second walk (published by warp 0)
+    unsigned plast[64], pdone[32];
+    unsigned slot;
+};
+
+// One parked block, all eight warps of the CTA.  Called between two __syncthreads of the caller.
+__device__ __forceinline__ void split_block(BfStage<0>* __restrict__ ring, SpShared& S, unsigned slot,
+                                            const uint2* __restrict__ ranges, const uint32_t* __restrict__ order,
+                                            const uint32_t* __restrict__ list, const GsRec* __restrict__ rec, int W, int H,
+                                            int gx, const float* __restrict__ bg, float* __restrict__ final_T,
+                                            uint32_t* __restrict__ n_contrib, const BfTargets& tg,
+                                            const uint2* __restrict__ park_units, const float* __restrict__ park_state) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lx = lane & 7, ly = lane >> 3;
+    const uint2 pu = __ldcg(park_units + slot);
+    const uint32_t unit = pu.x;
+    const uint32_t tile = order[unit >> 2];
+    const int sub = unit & 3;
+    const int tile_x = tile % gx, tile_y = tile / gx;
+    const int bx0 = tile_x * GS_TILE + (sub & 1) * 8, by0 = tile_y * GS_TILE + (sub >> 1) * 8;
+    const uint2 range = ranges[tile];
+    const uint32_t total = range.y - range.x;
+    const uint32_t* __restrict__ lst = list + range.x;
+    const int px = bx0 + lx, pyA = by0 + ly, pyB = by0 + ly + 4;
+    const float pfx = (float)px;
+    const f2 pfy2 = pk((float)pyA, (float)pyB);
+    // every warp keeps the merged state of the 64 pixels (identical in all eight: the merge is deterministic)
+    BfPix2 s;
+    {
+        const float* stp = park_state + (size_t)slot * GS_PARK_WORDS + lane;
+        s.T2 = pk(__ldcg(stp), __ldcg(stp + 32));
+        s.c0A = __ldcg(stp + 64); s.c0B = __ldcg(stp + 96); s.c1A = __ldcg(stp + 128); s.c1B = __ldcg(stp + 160);
+        s.c2A = __ldcg(stp + 192); s.c2B = __ldcg(stp + 224);
+        s.lastA = __float_as_uint(__ldcg(stp + 256)); s.lastB = __float_as_uint(__ldcg(stp + 288));
+        const unsigned fl = __float_as_uint(__ldcg(stp + 320));
+        s.doneA = fl & 1u; s.doneB = (fl >> 1) & 1u;
+    }
+#ifdef GS_TIMELINE
+    const unsigned long long tl_t0 = gtime();
+    unsigned tl_rounds = 0, tl_second = 0;
+#endif
+    uint32_t pos = pu.y;
+    while (pos < total && __any_sync(GS_FULL, !s.doneA || !s.doneB)) {
+        const uint32_t nb_rem = (total - pos + 31u) >> 5;
+        uint32_t G = (nb_rem + BF_WARPS - 1) / BF_WARPS;
+        G = G < SP_GMIN ? SP_GMIN : (G > SP_GMAX ? SP_GMAX : G);
+        const uint32_t seg = G * 32u;
+        {   // ---- this warp's segment from the neutral state
+            BfPix2 l;
+            l.T2 = bc(1.0f);
+            l.c0A = l.c0B = l.c1A = l.c1B = l.c2A = l.c2B = 0.0f;
+            l.lastA = l.lastB = 0u;
+            l.doneA = s.doneA; l.doneB = s.doneB;
+            const uint32_t sb = pos + (uint32_t)warp * seg;
+            if (sb < total) bf_walk(ring, lst, rec, sb, min(total, sb + seg), bx0, by0, pfx, pfy2, l, lane);
+            S.T[warp][lane] = lo(l.T2); S.T[warp][32 + lane] = hi(l.T2);
+            S.c0[warp][lane] = l.c0A; S.c0[warp][32 + lane] = l.c0B;
+            S.c1[warp][lane] = l.c1A; S.c1[warp][32 + lane] = l.c1B;
+            S.c2[warp][lane] = l.c2A; S.c2[warp][32 + lane] = l.c2B;
+            S.last[warp][lane] = l.lastA; S.last[warp][32 + lane] = l.lastB;
+            S.stopped[warp][lane] = ((l.doneA && !s.doneA) ? 1u : 0u) | ((l.doneB && !s.doneB) ? 2u : 0u);
+        }
+        __syncthreads();
+        // ---- merge in list order; a pixel whose stop may lie in segment k keeps its state of the start of k
+        float TA = lo(s.T2), TB = hi(s.T2);
+        int kA = BF_WARPS, kB = BF_WARPS;
+#pragma unroll
+        for (int k = 0; k < BF_WARPS; k++) {
+            const unsigned sf = S.stopped[k][lane];
+            if (!s.doneA && kA == BF_WARPS) {
+                const float tt = __fmul_rn(TA, S.T[k][lane]);
+                if ((sf & 1u) || tt < 0.0001f) kA = k;
+                else {
+                    s.c0A = __fmaf_rn(TA, S.c0[k][lane], s.c0A); s.c1A = __fmaf_rn(TA, S.c1[k][lane], s.c1A);
+                    s.c2A = __fmaf_rn(TA, S.c2[k][lane], s.c2A);
+                    const unsigned la = S.last[k][lane];
+                    if (la) s.lastA = la;
+                    TA = tt;
+                }
+            }
+            if (!s.doneB && kB == BF_WARPS) {
+                const float tt = __fmul_rn(TB, S.T[k][32 + lane]);
+                if ((sf & 2u) || tt < 0.0001f) kB = k;
+                else {
+                    s.c0B = __fmaf_rn(TB, S.c0[k][32 + lane], s.c0B); s.c1B = __fmaf_rn(TB, S.c1[k][32 + lane], s.c1B);
+                    s.c2B = __fmaf_rn(TB, S.c2[k][32 + lane], s.c2B);
+                    const unsigned lb = S.last[k][32 + lane];
+                    if (lb) s.lastB = lb;
+                    TB = tt;
+                }
+            }
+        }
+        s.T2 = pk(TA, TB);
+        const int kmin = (int)__reduce_min_sync(GS_FULL, (unsigned)min(kA, kB));
+#ifdef GS_TIMELINE
+        tl_rounds++;
+#endif
+        if (kmin < BF_WARPS) {  // (the same in all eight warps)
+#ifdef GS_TIMELINE
+            tl_second++;
+#endif
+            if (warp == 0) {  // exact second walk of the flagged pixels, each from the start of its segment
+                BfPix2 r = s;
+                r.doneA = true; r.doneB = true;
+                for (int k = kmin; k < BF_WARPS; k++) {
+                    if (kA == k) r.doneA = false;
+                    if (kB == k) r.doneB = false;
+                    const uint32_t sb = pos + (uint32_t)k * seg;
+                    if (sb >= total) break;
+                    bf_walk(ring, lst, rec, sb, min(total, sb + seg), bx0, by0, pfx, pfy2, r, lane);
+                }
+                if (kA < BF_WARPS) { S.pT[lane] = lo(r.T2); S.p0[lane] = r.c0A; S.p1[lane] = r.c1A; S.p2[lane] = r.c2A; S.plast[lane] = r.lastA; }
+                if (kB < BF_WARPS) { S.pT[32 + lane] = hi(r.T2); S.p0[32 + lane] = r.c0B; S.p1[32 + lane] = r.c1B; S.p2[32 + lane] = r.c2B; S.plast[32 + lane] = r.lastB; }
+                S.pdone[lane] = (r.doneA ? 1u : 0u) | (r.doneB ? 2u : 0u);
+            }
+            __syncthreads();
+            const unsigned pd = S.pdone[lane];
+            if (kA < BF_WARPS) {
+                TA = S.pT[lane]; s.c0A = S.p0[lane]; s.c1A = S.p1[lane]; s.c2A = S.p2[lane]; s.lastA = S.plast[lane];
+                s.doneA = pd & 1u;
+            }
+            if (kB < BF_WARPS) {
+                TB = S.pT[32 + lane]; s.c0B = S.p0[32 + lane]; s.c1B = S.p1[32 + lane]; s.c2B = S.p2[32 + lane];
+                s.lastB = S.plast[32 + lane];
+                s.doneB = (pd >> 1) & 1u;
+            }
+            s.T2 = pk(TA, TB);
+        }
+        __syncthreads();  // everybody has read this round's partial results
+        pos += BF_WARPS * seg;
+    }
+    if (warp == 0) {  // ---- epilogue (the stores of the warp-per-block path)
+        const float bg0 = bg[0], bg1 = bg[1], bg2 = bg[2];
+        const bool insA = px < W && pyA < H, insB = px < W && pyB < H;
+        const float TA = lo(s.T2), TB = hi(s.T2);
+        const size_t pidA = (size_t)W * pyA + px, pidB = (size_t)W * pyB + px;
+        if (insA) { final_T[pidA] = TA; n_contrib[pidA] = s.lastA; }
+        if (insB) { final_T[pidB] = TB; n_contrib[pidB] = s.lastB; }
+        float oA[3], oB[3];
+        oA[0] = s.c0A + TA * bg0; oA[1] = s.c1A + TA * bg1; oA[2] = s.c2A + TA * bg2;
+        oB[0] = s.c0B + TB * bg0; oB[1] = s.c1B + TB * bg1; oB[2] = s.c2B + TB * bg2;
+        size_t oplane = (size_t)H * W, opA = pidA, opB = pidB;
+        bool wA = insA, wB = insB;
+        if (tg.ds) {
+#pragma unroll
+            for (int c = 0; c < 3; c++) { oA[c] = box4(oA[c]); oB[c] = box4(oB[c]); }
+            const int W2 = W >> 1;
+            oplane = (size_t)W2 * (H >> 1);
+            opA = (size_t)W2 * (pyA >> 1) + (px >> 1);
+            opB = (size_t)W2 * (pyB >> 1) + (px >> 1);
+            const bool writer = (lane & 9) == 0;
+            wA = insA && writer; wB = insB && writer;
+        }
+        _Pragma("unroll") for (int k = 0; k < 8; k++) if (k < tg.n) {
+            float* oc = tg.img[k];
+            if (wA) { oc[opA] = oA[0]; oc[oplane + opA] = oA[1]; oc[2 * oplane + opA] = oA[2]; }
+            if (wB) { oc[opB] = oB[0]; oc[oplane + opB] = oB[1]; oc[2 * oplane + opB] = oB[2]; }
+        }
+#ifdef GS_TIMELINE
+        if (g_timeline && lane == 0) {
+            unsigned long long* tl = g_timeline + 12ull * unit;
+            tl[6] = tl_t0; tl[7] = gtime(); tl[8] = ((unsigned long long)tl_rounds << 32) | tl_second;
+        }
+#endif
+    }
+}
+
+// Serves parked blocks (split walks) until every fresh CTA is done and the parked queue is empty.
+__device__ __forceinline__ void split_serve(BfStage<0>* __restrict__ ring, SpShared& S, GsHeader* __restrict__ hdr,
+                                            unsigned n_fresh, const unsigned* __restrict__ park_ready,
+                                            const uint2* __restrict__ ranges, const uint32_t* __restrict__ order,
+                                            const uint32_t* __restrict__ list, const GsRec* __restrict__ rec, int W, int H,
+                                            int gx, const float* __restrict__ bg, float* __restrict__ final_T,
+                                            uint32_t* __restrict__ n_contrib, const BfTargets& tg,
+                                            const uint2* __restrict__ park_units, const float* __restrict__ park_state) {
+    while (true) {
+        __syncthreads();  // the previous block is finished by everybody
+        if (threadIdx.x == 0) {
+            unsigned slot = 0xFFFFFFFFu;
+            while (true) {
+                const unsigned taken = ldv(&hdr->tickets[8]);
+                unsigned avail = min(ldv(&hdr->tickets[7]), (unsigned)GS_PARK_CAP);
+                if (taken < avail) {
+                    if (atomicCAS(&hdr->tickets[8], taken, taken + 1u) == taken) { slot = taken; break; }
+                    continue;
+                }
+                if (ldv(&hdr->tickets[9]) >= n_fresh) {  // nobody parks any more: is the count we compared with final?
+                    avail = min(ldv(&hdr->tickets[7]), (unsigned)GS_PARK_CAP);
+                    if (ldv(&hdr->tickets[8]) >= avail) break;
+                    continue;
+                }
+                __nanosleep(200);
+            }
+            if (slot != 0xFFFFFFFFu) {
+                while (ldv(park_ready + slot) == 0u) __nanosleep(100);  // the parking warp is still writing the state
+                __threadfence();
+            }
+            S.slot = slot;
+        }
+        __syncthreads();
+        const unsigned slot = S.slot;
+        if (slot == 0xFFFFFFFFu) break;
+        split_block(ring, S, slot, ranges, order, list, rec, W, H, gx, bg, final_T, n_contrib, tg, park_units, park_state);
+    }
+}
+
 #ifndef BF_THR_TEST
 #define BF_THR_TEST 0
 #endif
@@ -608,7 +945,7 @@ __device__ __forceinline__ void team_serve(TmShared& S, GsHeader* __restrict__ h
 #ifndef BF_PX2_OCC
 #define BF_PX2_OCC 3
 #endif
-template <int K, bool TEAM>
+template <int K, int TEAM>  // TEAM: 0 = off, 1 = exact teams, 2 = split walks (associative merge)
 __global__ void __launch_bounds__(BF_WARPS * 32, (K == 0) ? BF_PX2_OCC : 2) blend_forward_px2_kernel(
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ order, const uint32_t* __restrict__ list,
     const GsRec* __restrict__ rec, int W, int H, int gx, uint32_t num_tiles, GsHeader* __restrict__ hdr,
@@ -975,24 +1312,31 @@ __global__ void __launch_bounds__(BF_WARPS * 32, (K == 0) ? BF_PX2_OCC : 2) blen
             __threadfence();
             atomicAdd(&hdr->tickets[9], 1u);  // this CTA parks nothing any more
         }
-        TmShared& S = *reinterpret_cast<TmShared*>(s_ring_raw);
-        team_serve(S, hdr, n_fresh, park_ready, ranges, order, list, rec, W, H, gx, bg, final_T, n_contrib, tg, park_units,
-                   park_state);
+        if (TEAM == 2) {
+            SpShared& S = *reinterpret_cast<SpShared*>(s_ring_raw + sizeof(BfStage<0>) * BF_STAGES * BF_WARPS);
+            split_serve(reinterpret_cast<BfStage<0>(*)[BF_STAGES]>(s_ring_raw)[warp], S, hdr, n_fresh, park_ready, ranges,
+                        order, list, rec, W, H, gx, bg, final_T, n_contrib, tg, park_units, park_state);
+        } else {
+            TmShared& S = *reinterpret_cast<TmShared*>(s_ring_raw);
+            team_serve(S, hdr, n_fresh, park_ready, ranges, order, list, rec, W, H, gx, bg, final_T, n_contrib, tg,
+                       park_units, park_state);
+        }
     }
 }
 
-// per extra-pass count K (index 4: the K = 0 kernel with teams): value[0] = resident CTAs of the kernel on this
+// per extra-pass count K (index 4 / 5: the K = 0 kernel with teams / split walks): value[0] = resident CTAs of the kernel on this
 // device, value[1] = default hand-over threshold
-GsPerDevice g_blend_dev[5];
+GsPerDevice g_blend_dev[6];
 
-template <int K, bool TEAM>
+template <int K, int TEAM>
 cudaError_t launch_blend(const GsFrame& f, const GsGeom& g, const GsBinning& b, const GsImage& im, float* out_color,
                          uint32_t num_tiles, int team_after) {
     const size_t ring_bytes = sizeof(BfStage<K>) * BF_STAGES * BF_WARPS;
-    const size_t smem = TEAM && sizeof(TmShared) > ring_bytes ? sizeof(TmShared) : ring_bytes;  // teams alias the rings
+    const size_t smem = TEAM == 2 ? ring_bytes + sizeof(SpShared)  // split walks keep the rings
+                                  : (TEAM == 1 && sizeof(TmShared) > ring_bytes ? sizeof(TmShared) : ring_bytes);  // teams alias them
     const int* dv = nullptr;
     {
-        cudaError_t e = g_blend_dev[TEAM ? 4 : K].get(&dv, [smem](int dev, int* v) {
+        cudaError_t e = g_blend_dev[TEAM ? 3 + TEAM : K].get(&dv, [smem](int dev, int* v) {
             int sms = 0, per_sm = 0;
             cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
             if (e != cudaSuccess) return e;
@@ -1061,12 +1405,13 @@ cudaError_t gs_launch_blend_forward(const GsFrame& f, const GsGeom& g, const GsB
         after = env_after;
     }
     switch (f.s.num_extra) {
-        case 1: return launch_blend<1, false>(f, g, b, im, out_color, num_tiles, 0);
-        case 2: return launch_blend<2, false>(f, g, b, im, out_color, num_tiles, 0);
-        case 3: return launch_blend<3, false>(f, g, b, im, out_color, num_tiles, 0);
+        case 1: return launch_blend<1, 0>(f, g, b, im, out_color, num_tiles, 0);
+        case 2: return launch_blend<2, 0>(f, g, b, im, out_color, num_tiles, 0);
+        case 3: return launch_blend<3, 0>(f, g, b, im, out_color, num_tiles, 0);
         default:
-            if (after > 0) return launch_blend<0, true>(f, g, b, im, out_color, num_tiles, after);
-            return launch_blend<0, false>(f, g, b, im, out_color, num_tiles, 0);
+            if (f.s.blend_split > 0) return launch_blend<0, 2>(f, g, b, im, out_color, num_tiles, f.s.blend_split);
+            if (after > 0) return launch_blend<0, 1>(f, g, b, im, out_color, num_tiles, after);
+            return launch_blend<0, 0>(f, g, b, im, out_color, num_tiles, 0);
     }
 }
 

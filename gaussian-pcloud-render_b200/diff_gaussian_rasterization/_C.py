@@ -41,7 +41,7 @@ class GsScene(C.Structure):
                 ("projmatrix", C.c_void_p), ("campos", C.c_void_p),
                 ("num_peers", C.c_int32), ("downsample", C.c_int32), ("peer_out_color", C.c_void_p * 8),
                 ("num_extra", C.c_int32), ("team_after", C.c_int32), ("extra_colors", C.c_void_p * 3),
-                ("extra_out", C.c_void_p * 3), ("shard_cull", C.c_int32), ("reserved3", C.c_int32)]
+                ("extra_out", C.c_void_p * 3), ("shard_cull", C.c_int32), ("blend_split", C.c_int32)]
 
 
 class GsHeadLayout(C.Structure):
@@ -181,8 +181,10 @@ def _pooled_workspaces(dev):
 def make_scene(*, P, sh_degree, sh_stride, width, height, tan_fovx, tan_fovy, scale_modifier, prefiltered, debug,
                background, means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, viewmatrix,
                projmatrix, campos, tile_rows: Optional[Tuple[int, int]] = None, peer_out=None,
-               extra_passes=None, downsample: int = 1, team_after: int = 0, shard_cull: bool = False) -> GsScene:
-    """shard_cull: tile-row shards only -- Gaussians that cannot reach the shard's rows are dropped before the
+               extra_passes=None, downsample: int = 1, team_after: int = 0, shard_cull: bool = False, blend_split: int = 0) -> GsScene:
+    """blend_split: > 0 = latency mode of the blend (GsScene.blend_split): list walks longer than that many batches are
+    finished by a CTA as parallel segments merged associatively (pixels within ~1e-6, NOT bit-identical); 0 = off.
+    shard_cull: tile-row shards only -- Gaussians that cannot reach the shard's rows are dropped before the
     per-Gaussian stage (GsScene.shard_cull; pixels unchanged, radii only written for the survivors).
     team_after: blend scheduling hint (GsScene.team_after): > 0 = hand-over threshold in batches (long list walks are
     finished by CTA teams; never changes a result), 0 = library default (off), < 0 = off.
@@ -205,7 +207,7 @@ def make_scene(*, P, sh_degree, sh_stride, width, height, tan_fovx, tan_fovy, sc
                    int(team_after),
                    (C.c_void_p * 3)(*([_ptr(c) for c, _ in extras] + [None] * (3 - len(extras)))),
                    (C.c_void_p * 3)(*([_ptr(o) for _, o in extras] + [None] * (3 - len(extras)))),
-                   int(bool(shard_cull)), 0)
+                   int(bool(shard_cull)), int(blend_split))
 
 
 def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp,

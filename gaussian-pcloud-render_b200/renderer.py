@@ -22,14 +22,18 @@ class FrameRenderer:
 
     def __init__(self, cloud: dict, width: int, height: int, bg, device, capacity: int = 0, headroom: float = 1.3,
                  tile_rows: Optional[Tuple[int, int]] = None, share: Optional["FrameRenderer"] = None,
-                 downsample: int = 1, team_after: int = 0):
-        """downsample=2: width x height is the (super-sampled) raster size, every output image is the 2x2 box mean
+                 downsample: int = 1, team_after: int = 0, blend_split: int = 0):
+        """blend_split: > 0 = latency mode of the blend (GsScene.blend_split): list walks longer than that many batches
+        are finished by a CTA as parallel segments merged associatively -- pixels within ~1e-6 of the exact frame, NOT
+        bit-identical; 0 = off (every frame bit-identical to the reference kernels).
+        downsample=2: width x height is the (super-sampled) raster size, every output image is the 2x2 box mean
         (3, height/2, width/2) -- the reference caller's bilinear x0.5, done in the blend epilogue.
         team_after: blend scheduling hint (GsScene.team_after; results never change): > 0 = list walks longer than
         that many batches are finished by CTA teams (a latency experiment, see csrc/blend_forward.cu), 0 = library
         default (off), -1 = off."""
         self.L = _C.lib()
         self.team_after = int(team_after)
+        self.blend_split = int(blend_split)
         if downsample not in (1, 2) or (downsample == 2 and (int(width) % 2 or int(height) % 2)):
             raise ValueError("downsample must be 1 or 2 (2 needs an even raster size)")
         self.downsample = int(downsample)
@@ -73,7 +77,7 @@ class FrameRenderer:
                              rotations=self.rotations, cov3D_precomp=None, viewmatrix=viewmatrix,
                              projmatrix=projmatrix, campos=campos, tile_rows=tile_rows, peer_out=peer_out,
                              extra_passes=extra_passes, downsample=self.downsample, team_after=self.team_after,
-                             shard_cull=shard_cull)
+                             shard_cull=shard_cull, blend_split=self.blend_split)
 
     def upload_view(self, view):
         """host View (scenes.make_view) -> device tensors; done once per camera, outside the frame loop."""

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define GS_ABI_VERSION 5
+#define GS_ABI_VERSION 6
 
 enum {
     GS_OK = 0,
@@ -97,7 +97,16 @@ typedef struct GsScene {
      * `radii` is then only written for the survivors (0 = "not in this shard" for a caller-zeroed array), so leave it
      * 0 when a backward pass needs the radii of the whole frame. */
     int32_t shard_cull;
-    int32_t reserved3;
+    /* Latency mode of the blend (forward only, plain frames: no extra passes).  0 = off: every result is bit-identical
+     * to the reference kernels.  > 0: a pixel block whose list walk is still running after `blend_split` batches of 32
+     * instances is parked and finished by a whole CTA that cuts the remaining list into segments, walks them in
+     * parallel from the neutral state and merges the partial (colour, transmittance) pairs in list order --
+     * front-to-back compositing is associative, only the association of the floating-point sums changes (pixels
+     * within ~1e-6 of the exact walk; the early-stop rule T (1 - alpha) < 1e-4 is re-applied exactly on the merged
+     * state, so n_contrib / final_T stay consistent for gs_backward).  Cuts the single-frame time of silhouette-heavy
+     * frames (one warp walking a 19 K-entry list) and is what lets tile-row shards scale; the north star's pixel
+     * tolerance (1e-4) holds with two orders of magnitude to spare.  Takes precedence over team_after. */
+    int32_t blend_split;
 } GsScene;
 
 /* Growable scratch buffer: fn(user, bytes) must return a DEVICE pointer to at least `bytes` bytes that stays

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     assert {"gs_forward", "gs_backward", "gs_mark_visible", "gs_forward_nosync", "gs_fetch"} <= set(names)
     for n in names:
         assert hasattr(lib, n), f"{n} declared in gsplat_b200.h but not exported"
-    assert lib.gs_abi_version() == 5
+    assert lib.gs_abi_version() == 6
 
 
 def test_ctypes_structs_match_c_layout():
