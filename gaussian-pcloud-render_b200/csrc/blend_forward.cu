@@ -110,6 +110,25 @@ __device__ __forceinline__ float box_max_power(float A, float B, float C, float 
     return best;
 }
 
+// The same bound without branches (both edge maxima are always evaluated and selected afterwards): for a warp that has
+// its scheduler to itself a predicate-to-branch round trip costs more than the arithmetic it skips.
+__device__ __forceinline__ float box_max_power_sel(float A, float B, float C, float nBA, float nBC, float xlo, float xhi,
+                                                   float ylo, float yhi) {
+    const bool in_x = (xlo <= 0.f) && (xhi >= 0.f);
+    const bool in_y = (ylo <= 0.f) && (yhi >= 0.f);
+    const float xe = (xlo > 0.f) ? xlo : xhi;
+    const float ye = (ylo > 0.f) ? ylo : yhi;
+    const float y = fminf(yhi, fmaxf(ylo, nBC * xe));
+    const float a1 = 0.5f * A * xe * xe, a2 = 0.5f * C * y * y, a3 = B * xe * y;
+    const float v1 = -(a1 + a2) - a3 + (4.0e-6f * (a1 + a2 + fabsf(a3)) + 0.01f);
+    const float x = fminf(xhi, fmaxf(xlo, nBA * ye));
+    const float b1 = 0.5f * A * x * x, b2 = 0.5f * C * ye * ye, b3 = B * x * ye;
+    const float v2 = -(b1 + b2) - b3 + (4.0e-6f * (b1 + b2 + fabsf(b3)) + 0.01f);
+    const float e1 = in_x ? -3.0e38f : v1;
+    const float best = in_y ? e1 : fmaxf(e1, v2);
+    return (in_x && in_y) ? 0.f : best;
+}
+
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src) : "memory");
@@ -1324,6 +1343,327 @@ __global__ void __launch_bounds__(BF_WARPS * 32, (K == 0) ? BF_PX2_OCC : 2) blen
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Grouped hit loop (the K = 0 kernel of plain frames).  The hit loop above is one dependent chain per instance --
+// ffs -> record -> exponent -> expf -> tests -> vote -> blend, ~30 dependent steps, ~280 cycles for a warp that has its
+// scheduler to itself -- although only FOUR of those steps depend on the compositing state: alpha of an instance at a
+// pixel is a function of the record alone.  Here the instances that survive the block cull are taken BI_G at a time:
+// phase A evaluates the BI_G alphas (independent chains the scheduler interleaves, no votes, no branches), phase B
+// applies them in list order with the reference's recurrence arranged so that the loop-carried chain is
+// multiply -> compare -> select: test_T = T (1 - alpha) with alpha = 0 for a pixel that is done or fails the
+// reference's skip tests (the factor is then exactly 1), stop test, C = fma(c alpha, T, C).  Same operations on the same
+// operands in the same order as the loop above, so every result stays bit-identical.  The survivors of a batch are
+// compacted into a small per-warp FIFO (every surviving lane stores ITS record at its rank among the survivors: no
+// serial find-first-set chain, and a group reads BI_G consecutive FIFO entries at compile-time offsets); survivors that
+// do not fill a group simply stay in the FIFO for the next batch, so a group is always full except at the end of a list
+// (padded with null records: opacity 0 -> alpha 0).
+#ifndef BI_G
+#define BI_G 4
+#endif
+#define BI_FIFO 48  // FIFO entries: a multiple of BI_G (a group never wraps) >= 32 + BI_G - 1 (one batch + left-overs)
+static_assert(BI_FIFO % BI_G == 0 && BI_FIFO >= 32 + 2 * BI_G - 1, "FIFO size");
+struct BiRing {  // one per warp
+    float4 a[BF_STAGES][32];  // x, y, conic.x, conic.y                      } the record ring (cp.async), as BfStage
+    float4 b[BF_STAGES][32];  // conic.z, opacity, thr, -B/C                 }
+    float4 c[BF_STAGES][32];  // r, g, b, -B/A                               }
+    float4 fa[BI_FIFO + 2];   // FIFO of survivors: x, y, conic.x, conic.y   (entry BI_FIFO: scratch, takes the stores
+    float4 fc[BI_FIFO + 2];   //                    r, g, b, list position + 1  of the lanes that have no survivor)
+    float2 fb[BI_FIFO + 2];   //                    conic.z, opacity
+};
+
+__device__ __forceinline__ void bf_fill_empty_tile(uint32_t tile, int gx, int W, int H, int lane, float bg0, float bg1,
+                                                   float bg2, float* __restrict__ final_T,
+                                                   uint32_t* __restrict__ n_contrib, const BfTargets& tg) {
+    const size_t plane = (size_t)H * W;
+    const int x0 = (int)(tile % gx) * GS_TILE, y0 = (int)(tile / gx) * GS_TILE;
+    if (tg.ds) {  // half-resolution colour (8x8 per tile), full-resolution T / contributor count
+        const int W2 = W >> 1, H2 = H >> 1;
+        const size_t plane2 = (size_t)W2 * H2;
+        const int qx = (x0 >> 1) + (lane & 7);
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            const int qy = (y0 >> 1) + r * 4 + (lane >> 3);
+            if (qx < W2 && qy < H2) {
+                const size_t pid = (size_t)W2 * qy + qx;
+                _Pragma("unroll") for (int k = 0; k < 8; k++) if (k < tg.n) {
+                    float* oc = tg.img[k];
+                    oc[pid] = bg0; oc[plane2 + pid] = bg1; oc[2 * plane2 + pid] = bg2;
+                }
+            }
+        }
+        for (int r = 0; r < 8; r++) {
+            const int px = x0 + (lane & 15), py = y0 + r * 2 + (lane >> 4);
+            if (px < W && py < H) {
+                const size_t pid = (size_t)W * py + px;
+                final_T[pid] = 1.f; n_contrib[pid] = 0u;
+            }
+        }
+    } else if ((W & 3) == 0 && x0 + GS_TILE <= W) {
+        const int px = x0 + (lane & 3) * 4;
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            const int py = y0 + r * 8 + (lane >> 2);
+            if (py < H) {
+                const size_t pid = (size_t)W * py + px;
+                _Pragma("unroll") for (int k = 0; k < 8; k++) if (k < tg.n) {
+                    float* oc = tg.img[k];
+                    *reinterpret_cast<float4*>(oc + pid) = make_float4(bg0, bg0, bg0, bg0);
+                    *reinterpret_cast<float4*>(oc + plane + pid) = make_float4(bg1, bg1, bg1, bg1);
+                    *reinterpret_cast<float4*>(oc + 2 * plane + pid) = make_float4(bg2, bg2, bg2, bg2);
+                }
+                *reinterpret_cast<float4*>(final_T + pid) = make_float4(1.f, 1.f, 1.f, 1.f);
+                *reinterpret_cast<uint4*>(n_contrib + pid) = make_uint4(0u, 0u, 0u, 0u);
+            }
+        }
+    } else {
+        for (int r = 0; r < 8; r++) {
+            const int px = x0 + (lane & 15), py = y0 + r * 2 + (lane >> 4);
+            if (px < W && py < H) {
+                const size_t pid = (size_t)W * py + px;
+                _Pragma("unroll") for (int k = 0; k < 8; k++) if (k < tg.n) {
+                    float* oc = tg.img[k];
+                    oc[pid] = bg0; oc[plane + pid] = bg1; oc[2 * plane + pid] = bg2;
+                }
+                final_T[pid] = 1.f; n_contrib[pid] = 0u;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(BF_WARPS * 32, BF_PX2_OCC) blend_forward_grouped_kernel(
+    const uint2* __restrict__ ranges, const uint32_t* __restrict__ order, const uint32_t* __restrict__ list,
+    const GsRec* __restrict__ rec, int W, int H, int gx, uint32_t num_tiles, GsHeader* __restrict__ hdr,
+    const float* __restrict__ bg, float* __restrict__ final_T, uint32_t* __restrict__ n_contrib, const BfTargets tg,
+    int quota) {
+    extern __shared__ __align__(16) unsigned char s_ring_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lx = lane & 7, ly = lane >> 3;
+    const float bg0 = bg[0], bg1 = bg[1], bg2 = bg[2];
+    BiRing& R = reinterpret_cast<BiRing*>(s_ring_raw)[warp];
+    unsigned* const q_fresh = &hdr->tickets[6];
+    const uint32_t nonempty = hdr->nonempty_tiles;
+    const uint32_t blend_units = nonempty * 4u;
+    const uint32_t num_units = blend_units + (num_tiles - nonempty);
+
+    for (int served = 0; served < quota; served++) {
+        uint32_t unit = 0;
+        if (lane == 0) unit = atomicAdd(q_fresh, 1u);
+        unit = __shfl_sync(GS_FULL, unit, 0);
+        if (unit >= num_units) break;
+        if (unit >= blend_units) {  // ---- empty tile: colour = background, T = 1, no contributor
+            bf_fill_empty_tile(order[nonempty + (unit - blend_units)], gx, W, H, lane, bg0, bg1, bg2, final_T, n_contrib, tg);
+            continue;
+        }
+        const uint32_t tile = order[unit >> 2];
+        const int sub = unit & 3;
+        const int tile_x = tile % gx, tile_y = tile / gx;
+        const int bx0 = tile_x * GS_TILE + (sub & 1) * 8, by0 = tile_y * GS_TILE + (sub >> 1) * 8;
+        if (bx0 >= W || by0 >= H) continue;  // block entirely outside the image
+        const int px = bx0 + lx, pyA = by0 + ly, pyB = by0 + ly + 4;
+        const bool insA = px < W && pyA < H, insB = px < W && pyB < H;
+        const float pfx = (float)px;
+        const f2 pfy2 = pk((float)pyA, (float)pyB);
+        float fx0 = (float)bx0, fx1 = (float)(bx0 + 7), fy0 = (float)by0, fy1 = (float)(by0 + 7);
+
+        const uint2 range = ranges[tile];
+        const uint32_t total = range.y - range.x;
+        const uint32_t* __restrict__ lst = list + range.x;
+#ifdef GS_TIMELINE
+        const unsigned long long tl_t0 = gtime();
+        unsigned tl_batches = 0, tl_hits = 0;
+        long long tl_wait = 0, tl_loop = 0, tl_issue = 0, tl_cull = 0;
+#endif
+        bool doneA = !insA, doneB = !insB;
+        f2 T2 = bc(1.0f);
+        float c0A = 0.f, c0B = 0.f, c1A = 0.f, c1B = 0.f, c2A = 0.f, c2B = 0.f;
+        uint32_t lastA = 0, lastB = 0;
+
+        __syncwarp();
+#pragma unroll
+        for (int p = 0; p < 2; p++) {
+            if (p * 32 + lane < total) {
+                const GsRec* r = rec + lst[p * 32 + lane];
+                cp_async16(&R.a[p][lane], &r->a);
+                cp_async16(&R.b[p][lane], &r->b);
+                cp_async16(&R.c[p][lane], &r->c);
+            }
+            cp_async_commit();
+        }
+        // list indices run two batches ahead of the record prefetch (a dependent load chain: index -> record)
+        uint32_t id_next = (64 + lane < total) ? lst[64 + lane] : 0u;
+        uint32_t id_next2 = (96 + lane < total) ? lst[96 + lane] : 0u;
+
+        int stage = 0;
+        uint32_t next_check = BF_CHECK * 32;
+        unsigned head = 0, avail = 0;  // FIFO: first unconsumed entry (a multiple of BI_G, < BI_FIFO), entries waiting
+        for (uint32_t base = 0; base < total; base += 32) {
+            if (base == next_check) {  // shrink the cull box to the pixels that are still live
+                next_check += BF_CHECK * 32;
+                const unsigned aliveA = __ballot_sync(GS_FULL, !doneA), aliveB = __ballot_sync(GS_FULL, !doneB);
+                const unsigned both = aliveA | aliveB;
+                const unsigned cols = (both | (both >> 8) | (both >> 16) | (both >> 24)) & 0xffu;
+                unsigned rows = 0;
+#pragma unroll
+                for (int r = 0; r < 4; r++) {
+                    rows |= ((aliveA >> (8 * r)) & 0xffu) ? (1u << r) : 0u;
+                    rows |= ((aliveB >> (8 * r)) & 0xffu) ? (16u << r) : 0u;
+                }
+                fx0 = (float)(bx0 + __ffs(cols) - 1); fx1 = (float)(bx0 + 31 - __clz(cols));
+                fy0 = (float)(by0 + __ffs(rows) - 1); fy1 = (float)(by0 + 31 - __clz(rows));
+            }
+#ifdef GS_TIMELINE
+            tl_batches++;
+            const long long tl_c0 = clock64();
+#endif
+            cp_async_wait<1>();
+            __syncwarp();
+#ifdef GS_TIMELINE
+            tl_wait += clock64() - tl_c0;
+            const long long tl_c2 = clock64();
+#endif
+            {
+                int nst = stage + 2; if (nst >= BF_STAGES) nst -= BF_STAGES;
+                if (base + 64 + lane < total) {
+                    const GsRec* r = rec + id_next;
+                    cp_async16(&R.a[nst][lane], &r->a);
+                    cp_async16(&R.b[nst][lane], &r->b);
+                    cp_async16(&R.c[nst][lane], &r->c);
+                }
+                cp_async_commit();
+                id_next = id_next2;
+                if (base + 128 + lane < total) id_next2 = lst[base + 128 + lane];
+            }
+#ifdef GS_TIMELINE
+            const long long tl_c3 = clock64();
+            tl_issue += tl_c3 - tl_c2;
+#endif
+            const int sb = stage;
+            stage = (stage + 1 == BF_STAGES) ? 0 : stage + 1;
+
+            // cull, without branches: lanes behind the end of the list read stale ring slots and are masked out
+            const float4 ra = R.a[sb][lane], rb = R.b[sb][lane], rc = R.c[sb][lane];
+            const float bound = box_max_power_sel(ra.z, ra.w, rb.x, rc.w, rb.w, ra.x - fx1, ra.x - fx0, ra.y - fy1, ra.y - fy0);
+            const bool hit = (base + lane < total) && !(bound < rb.z);
+            const unsigned mask = __ballot_sync(GS_FULL, hit);
+            const bool final_batch = base + 32 >= total;
+#ifdef GS_TIMELINE
+            tl_hits += __popc(mask);
+            const long long tl_c1 = clock64();
+            tl_cull += tl_c1 - tl_c3;
+#endif
+            {   // compaction: the survivor of lane l goes to FIFO entry head + avail + (survivors in lower lanes)
+                unsigned pos = head + avail + (unsigned)__popc(mask & ((1u << lane) - 1u));
+                if (pos >= (unsigned)BI_FIFO) pos -= (unsigned)BI_FIFO;
+                pos = hit ? pos : (unsigned)BI_FIFO;  // (scratch entry)
+                R.fa[pos] = ra;
+                R.fb[pos] = make_float2(rb.x, rb.y);
+                R.fc[pos] = make_float4(rc.x, rc.y, rc.z, __uint_as_float(base + (uint32_t)lane + 1u));
+                avail += (unsigned)__popc(mask);
+                // the last batch pads the last group with null records (opacity 0 -> alpha 0)
+                const unsigned pad = final_batch ? ((unsigned)BI_G - avail % BI_G) % BI_G : 0u;
+                unsigned pp = head + avail + (unsigned)lane;
+                if (pp >= (unsigned)BI_FIFO) pp -= (unsigned)BI_FIFO;
+                pp = (unsigned)lane < pad ? pp : (unsigned)BI_FIFO + 1u;
+                R.fa[pp] = make_float4(0.f, 0.f, 0.f, 0.f);
+                R.fb[pp] = make_float2(0.f, 0.f);
+                R.fc[pp] = make_float4(0.f, 0.f, 0.f, 0.f);
+                avail += pad;
+                __syncwarp();
+            }
+            while (avail >= (unsigned)BI_G) {
+                const float4* __restrict__ Fa = R.fa + head;
+                const float2* __restrict__ Fb = R.fb + head;
+                const float4* __restrict__ Fc = R.fc + head;
+                head = (head + BI_G == (unsigned)BI_FIFO) ? 0u : head + BI_G;
+                avail -= BI_G;
+                // ---- phase A: alpha of each instance at the two pixels of this lane (0 = the reference skips it);
+                // operation for operation the loop above (forward.cu:336-338 as compiled, libdevice expf)
+                f2 al[BI_G];
+#pragma unroll
+                for (int u = 0; u < BI_G; u++) {
+                    const float4 ga = Fa[u];
+                    const float2 gb = Fb[u];
+                    const float dx = ga.x - pfx;
+                    const f2 dy2 = sub2(bc(ga.y), pfy2);
+                    f2 t1 = mul2(bc(gb.x), dy2);
+                    t1 = mul2(dy2, t1);
+                    const float t2 = ga.z * dx, t3n = (-ga.w) * dx;
+                    const f2 t3 = mul2(dy2, bc(t3n));
+                    const f2 sm = fma2(bc(dx), bc(t2), t1);
+                    const f2 p2 = fma2(sm, bc(-0.5f), t3);
+                    const float pA = lo(p2), pB = hi(p2);
+                    const float alphaA = fminf(0.99f, gb.y * expf(pA)), alphaB = fminf(0.99f, gb.y * expf(pB));
+                    const bool okA = !(pA > 0.0f) && !(alphaA < 1.0f / 255.0f);
+                    const bool okB = !(pB > 0.0f) && !(alphaB < 1.0f / 255.0f);
+                    al[u] = pk(okA ? alphaA : 0.0f, okB ? alphaB : 0.0f);
+                }
+                // ---- phase B: the recurrence, in list order
+#pragma unroll
+                for (int u = 0; u < BI_G; u++) {
+                    const float aA = lo(al[u]), aB = hi(al[u]);
+                    const f2 om = sub2(bc(1.0f), al[u]);
+                    const f2 tt2 = mul2(T2, pk(doneA ? 1.0f : lo(om), doneB ? 1.0f : hi(om)));
+                    // T never is below the stop threshold itself, so a pixel that is done or skipped cannot stop here
+                    const bool dA = doneA || lo(tt2) < 0.0001f, dB = doneB || hi(tt2) < 0.0001f;
+                    const f2 eff = pk(dA ? 0.0f : aA, dB ? 0.0f : aB);
+                    const float4 gc = Fc[u];
+                    const float TA = lo(T2), TB = hi(T2);
+                    const f2 w0 = mul2(bc(gc.x), eff), w1 = mul2(bc(gc.y), eff), w2 = mul2(bc(gc.z), eff);
+                    c0A = __fmaf_rn(lo(w0), TA, c0A); c0B = __fmaf_rn(hi(w0), TB, c0B);
+                    c1A = __fmaf_rn(lo(w1), TA, c1A); c1B = __fmaf_rn(hi(w1), TB, c1B);
+                    c2A = __fmaf_rn(lo(w2), TA, c2A); c2B = __fmaf_rn(hi(w2), TB, c2B);
+                    T2 = pk(dA ? TA : lo(tt2), dB ? TB : hi(tt2));
+                    if (!dA && aA != 0.0f) lastA = __float_as_uint(gc.w);
+                    if (!dB && aB != 0.0f) lastB = __float_as_uint(gc.w);
+                    doneA = dA; doneB = dB;
+                }
+            }
+            __syncwarp();  // the groups' reads are over before the next batch appends
+#ifdef GS_TIMELINE
+            tl_loop += clock64() - tl_c1;
+#endif
+            if (__all_sync(GS_FULL, doneA && doneB)) break;  // (pending survivors would change nothing)
+        }
+        cp_async_wait<0>();
+#ifdef GS_TIMELINE
+        if (g_timeline && lane == 0) {
+            unsigned long long* tl = g_timeline + 12ull * unit;
+            tl[0] = tl_t0; tl[1] = gtime();
+            tl[2] = ((unsigned long long)smid() << 32) | total;
+            tl[3] = ((unsigned long long)tl_batches << 32) | tl_hits;
+            tl[4] = (unsigned long long)tl_wait; tl[5] = (unsigned long long)tl_loop;
+            tl[9] = (unsigned long long)tl_issue; tl[10] = (unsigned long long)tl_cull;
+        }
+#endif
+        // ---- epilogue
+        const float TA = lo(T2), TB = hi(T2);
+        const size_t pidA = (size_t)W * pyA + px, pidB = (size_t)W * pyB + px;
+        if (insA) { final_T[pidA] = TA; n_contrib[pidA] = lastA; }
+        if (insB) { final_T[pidB] = TB; n_contrib[pidB] = lastB; }
+        float oA[3], oB[3];
+        oA[0] = c0A + TA * bg0; oA[1] = c1A + TA * bg1; oA[2] = c2A + TA * bg2;
+        oB[0] = c0B + TB * bg0; oB[1] = c1B + TB * bg1; oB[2] = c2B + TB * bg2;
+        size_t oplane = (size_t)H * W, opA = pidA, opB = pidB;
+        bool wA = insA, wB = insB;
+        if (tg.ds) {  // W, H even and blocks start on even pixels: a 2x2 group is inside or outside as a whole
+#pragma unroll
+            for (int c = 0; c < 3; c++) { oA[c] = box4(oA[c]); oB[c] = box4(oB[c]); }
+            const int W2 = W >> 1;
+            oplane = (size_t)W2 * (H >> 1);
+            opA = (size_t)W2 * (pyA >> 1) + (px >> 1);
+            opB = (size_t)W2 * (pyB >> 1) + (px >> 1);
+            const bool writer = (lane & 9) == 0;  // even lx, even ly
+            wA = insA && writer; wB = insB && writer;
+        }
+        _Pragma("unroll") for (int k = 0; k < 8; k++) if (k < tg.n) {
+            float* oc = tg.img[k];
+            if (wA) { oc[opA] = oA[0]; oc[oplane + opA] = oA[1]; oc[2 * oplane + opA] = oA[2]; }
+            if (wB) { oc[opB] = oB[0]; oc[oplane + opB] = oB[1]; oc[2 * oplane + opB] = oB[2]; }
+        }
+    }
+}
+
 // per extra-pass count K (index 4 / 5: the K = 0 kernel with teams / split walks): value[0] = resident CTAs of the kernel on this
 // device, value[1] = default hand-over threshold
 GsPerDevice g_blend_dev[6];
@@ -1388,6 +1728,47 @@ cudaError_t launch_blend(const GsFrame& f, const GsGeom& g, const GsBinning& b, 
     return cudaGetLastError();
 }
 
+GsPerDevice g_grouped_dev;
+
+cudaError_t launch_blend_grouped(const GsFrame& f, const GsGeom& g, const GsBinning& b, const GsImage& im,
+                                 float* out_color, uint32_t num_tiles) {
+    const size_t smem = sizeof(BiRing) * BF_WARPS;
+    const int* dv = nullptr;
+    {
+        cudaError_t e = g_grouped_dev.get(&dv, [smem](int dev, int* v) {
+            int sms = 0, per_sm = 0;
+            cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            if (e != cudaSuccess) return e;
+            e = cudaFuncSetAttribute(blend_forward_grouped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, blend_forward_grouped_kernel, BF_WARPS * 32, smem);
+            if (e != cudaSuccess) return e;
+            v[0] = sms * (per_sm > 0 ? per_sm : 1);
+            v[1] = sms;
+            return cudaSuccess;
+        });
+        if (e != cudaSuccess) return e;
+    }
+    BfTargets tg;
+    tg.n = f.s.num_peers > 0 ? f.s.num_peers : 1;
+    tg.ds = f.s.downsample == 2 ? 1 : 0;
+    for (int k = 0; k < 8; k++) tg.img[k] = f.s.num_peers > 0 ? f.s.peer_out_color[k] : out_color;
+    const uint32_t units_max = num_tiles * 4u;
+    // One CTA per SM (two warps per scheduler) and a per-warp unit quota that covers the upper bound of units: measured
+    // best for a single frame (long walks share their scheduler with one other warp instead of three) AND with
+    // frames in flight (the binning kernels of the next frames find room next to it); profiles/r02e_blend_grid_c2.txt
+    // (the quota is twice the even share, so that warps held up by long walks do not leave work behind in a dense frame)
+    const uint32_t slots = (uint32_t)dv[1];
+    const uint32_t share = (units_max + BF_WARPS * slots - 1) / (BF_WARPS * slots);
+    const uint32_t quota = 2u * (share < 1u ? 1u : share);
+    const unsigned grid = units_max < BF_WARPS * slots ? (units_max + BF_WARPS - 1) / BF_WARPS : slots;
+    blend_forward_grouped_kernel<<<grid, BF_WARPS * 32, smem, f.stream>>>(
+        im.ranges, im.order, b.list, g.rec, f.s.width, f.s.height, f.gx, num_tiles, g.hdr, f.s.background, im.final_T,
+        im.n_contrib, tg, (int)quota);
+    gs_note_launch();
+    return cudaGetLastError();
+}
+
 }  // namespace
 
 cudaError_t gs_launch_blend_forward(const GsFrame& f, const GsGeom& g, const GsBinning& b, const GsImage& im,
@@ -1411,7 +1792,11 @@ cudaError_t gs_launch_blend_forward(const GsFrame& f, const GsGeom& g, const GsB
         default:
             if (f.s.blend_split > 0) return launch_blend<0, 2>(f, g, b, im, out_color, num_tiles, f.s.blend_split);
             if (after > 0) return launch_blend<0, 1>(f, g, b, im, out_color, num_tiles, after);
-            return launch_blend<0, 0>(f, g, b, im, out_color, num_tiles, 0);
+            {   // developer switch: GSPLAT_B200_BLEND_PLAIN=1 selects the one-instance-per-iteration loop (A/B runs)
+                static const int plain = [] { const char* e = getenv("GSPLAT_B200_BLEND_PLAIN"); return e ? atoi(e) : 0; }();
+                if (plain) return launch_blend<0, 0>(f, g, b, im, out_color, num_tiles, 0);
+            }
+            return launch_blend_grouped(f, g, b, im, out_color, num_tiles);
     }
 }
 
