@@ -8,6 +8,7 @@
 //     gs_forward_nosync has no host synchronisation at all;
 //   * scan + 64-bit pair sort + range detection are replaced by the depth sort, the plan kernel and the row / column
 //     partition passes of binning.cu.
+#include <cstdlib>
 #include <atomic>
 #include <cstdio>
 #include <cstring>
@@ -217,10 +218,16 @@ int32_t gs_forward_nosync(const GsScene* scene, char* geometry, char* binning, i
     GS_STAGE(gs_launch_preprocess(f, g, im, radii));
     t_prof.mark(1, f.stream);
     if (f.row1 == f.row0) return GS_OK;  // empty tile-row shard
+    // developer switch (tools/frontend_cost.py): stop after the n-th stage to time the front end alone with frames in flight
+    const char* stop_env = getenv("GSPLAT_B200_STOP_AFTER");
+    const int stop_after = stop_env ? atoi(stop_env) : 0;
+    if (stop_after == 1) return GS_OK;
     GS_STAGE(gs_launch_depth_sort(f, g));
     t_prof.mark(2, f.stream);
+    if (stop_after == 2) return GS_OK;
     GS_STAGE(gs_launch_tile_lists(f, g, b, (size_t)cap, rowcap, im));
     t_prof.mark(3, f.stream);
+    if (stop_after == 3) return GS_OK;
     GS_STAGE(gs_launch_pack_extra(f, g));
     GS_STAGE(gs_launch_blend_forward(f, g, b, im, out_color));
     t_prof.mark(4, f.stream);

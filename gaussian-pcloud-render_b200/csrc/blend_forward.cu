@@ -1358,6 +1358,16 @@ __global__ void __launch_bounds__(BF_WARPS * 32, (K == 0) ? BF_PX2_OCC : 2) blen
 // serial find-first-set chain, and a group reads BI_G consecutive FIFO entries at compile-time offsets); survivors that
 // do not fill a group simply stay in the FIFO for the next batch, so a group is always full except at the end of a list
 // (padded with null records: opacity 0 -> alpha 0).
+// Measured at C2 (profiles/r02e_*): blend 0.604 -> 0.447 ms for one frame at a time (the longest walk -- 19 K entries,
+// 3121 survivors -- 0.71 -> 0.44 ms), 2340 -> 2500 frames/s with six frames in flight.  The single-warp issue model of the
+// loop (tools/sass_lonewarp.py: stall fields + scoreboards of the SASS) says 108 cycles per instance for a warp alone
+// on its scheduler against 245 for the loop above; groups of 6 / 8 gain < 10 % more.  Tried on top and not kept:
+// two batches per step (each lane culls two records, one wait / vote / loop overhead per 64 entries; 73 KB of shared
+// memory and 110 registers: blend 0.422 ms for one frame but 2390 frames/s in flight), warps 4-7 (or 0-3) take the longest
+// lists and the others the shortest (no sign of a warp-id priority in the scheduler), the first round handed out
+// warp-major, 8-32 SMs reserved for the longest lists with one warp per scheduler (list length does not predict walk
+// length: the longest lists are body tiles that saturate after ~40 batches), a long walk asking the warp that shares
+// its scheduler to leave (the queue then drains too slowly), 185-370 CTAs instead of one per SM.
 #ifndef BI_G
 #define BI_G 4
 #endif
