@@ -369,7 +369,6 @@ int64_t gs_fetch(const GsScene* scene, const char* geometry, const char* binning
     if (!strcmp(name, "records")) { src = g.rec; n = sizeof(GsRec) * P; }
     else if (!strcmp(name, "sorted_idx")) { src = g.idx[side]; n = 4 * P; }
     else if (!strcmp(name, "sorted_key")) { src = g.key[side]; n = 4 * P; }
-    else if (!strcmp(name, "cov3D")) { src = g.cov3D; n = 24 * P; }
     else if (!strcmp(name, "clamped")) { src = g.clamp; n = P; }
     else if (!strcmp(name, "tiles_touched")) { src = g.ntile; n = 4 * P; }
     else if (!strcmp(name, "point_list")) { src = b.list; n = 4 * R; }

@@ -12,7 +12,6 @@
 //     idx   [2][P] u32    depth-sort values (Gaussian index), ping/pong
 //     rect  [P] ushort4   tile rectangle [x0,x1) x [y0,y1)
 //     ntile [P] u32       tiles touched
-//     cov3D [P][6] f32    world covariance (only when computed from scale/rotation)
 //     clamp [P] u8        bit c set = SH colour channel c was clamped at 0
 //     xrec  [P][3] float4 colours of up to three extra passes blended in the same list walk (GsScene.extra_colors)
 //     cand  [P] u32       GsScene.shard_cull: ascending indices of the Gaussians that may reach the shard's tile rows;
@@ -111,7 +110,6 @@ struct GsGeom {
     uint32_t* idx[2];
     ushort4* rect;
     uint32_t* ntile;
-    float* cov3D;
     uint8_t* clamp;
     float4* xrec;      // [P][3] colours of up to three extra passes (rgb + pad), gathered like rec by the blend
     uint32_t* cand; uint32_t* cmask; uint32_t* ccount;  // shard cull (see above)
@@ -132,7 +130,6 @@ struct GsGeom {
         idx[0] = c.take<uint32_t>(P); idx[1] = c.take<uint32_t>(P);
         rect = c.take<ushort4>(P);
         ntile = c.take<uint32_t>(P);
-        cov3D = c.take<float>(6 * P);
         clamp = c.take<uint8_t>(P);
         xrec = c.take<float4>(3 * P);
         cull_chunks = gs_div_up(P, GS_CULL_CHUNK);

@@ -20,7 +20,7 @@ struct PreArgs {
     const float* means; const float* scales; const float* rots; const float* opac; const float* shs;
     const float* cov3D_pre; const float* colors_pre; const float* view; const float* proj; const float* campos;
     int32_t* radii;
-    GsRec* rec; uint32_t* key; ushort4* rect; uint32_t* ntile; float* cov3D; uint8_t* clamp;
+    GsRec* rec; uint32_t* key; ushort4* rect; uint32_t* ntile; uint8_t* clamp;
     int* rdiff;
     GsHeader* hdr;
     const uint32_t* cand;  // shard cull: thread t handles Gaussian cand[t], t < hdr->num_cand (nullptr: Gaussian t, t < P)
@@ -153,9 +153,7 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreArgs a) {
             } else {
                 const float3 sc = make_float3(sp[0], sp[1], sp[2]);
                 const float4 q = *reinterpret_cast<const float4*>(rp);
-                cov3d_from_scale_rot(sc, a.mod, q, c6);
-#pragma unroll
-                for (int k = 0; k < 6; k++) a.cov3D[6 * (size_t)i + k] = c6[k];
+                cov3d_from_scale_rot(sc, a.mod, q, c6);  // (not stored: the backward pass recomputes it)
             }
             Cov2D k2;
             cov2d_eval(mean, a.fx, a.fy, a.tanx, a.tany, c6, a.view, k2);
@@ -529,7 +527,7 @@ static PreArgs make_pre_args(const GsFrame& f, const GsGeom& g, const int* rdiff
     a.cov3D_pre = s.cov3D_precomp; a.colors_pre = s.colors_precomp; a.view = s.viewmatrix; a.proj = s.projmatrix;
     a.campos = s.campos;
     a.radii = radii;
-    a.rec = g.rec; a.key = g.key[0]; a.rect = g.rect; a.ntile = g.ntile; a.cov3D = g.cov3D;
+    a.rec = g.rec; a.key = g.key[0]; a.rect = g.rect; a.ntile = g.ntile;
     a.clamp = g.clamp; a.rdiff = const_cast<int*>(rdiff); a.hdr = g.hdr;
     a.cand = f.cull ? g.cand : nullptr;
     return a;

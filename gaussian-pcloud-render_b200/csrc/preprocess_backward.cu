@@ -106,8 +106,14 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(const BwdArgs 
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.P || !(a.radii[i] > 0)) return;
     const float3 mean = v3(a.means[3 * i], a.means[3 * i + 1], a.means[3 * i + 2]);
+    // world covariance: the caller's, or recomputed from scale / rotation with the forward pass's own function (same
+    // bits; 24 B per Gaussian that the forward pass no longer stores and this kernel no longer reads back)
     float c6[6];
-    if ((reinterpret_cast<uintptr_t>(a.cov3D) & 7u) == 0) {  // 24-byte rows of an 8-byte aligned array: three 8-byte loads
+    if (a.cov3D == nullptr) {
+        cov3d_from_scale_rot(v3(a.scales[3 * (size_t)i], a.scales[3 * (size_t)i + 1], a.scales[3 * (size_t)i + 2]), a.mod,
+                             make_float4(a.rots[4 * (size_t)i], a.rots[4 * (size_t)i + 1], a.rots[4 * (size_t)i + 2],
+                                         a.rots[4 * (size_t)i + 3]), c6);
+    } else if ((reinterpret_cast<uintptr_t>(a.cov3D) & 7u) == 0) {  // 24-byte rows of an 8-byte aligned array: three 8-byte loads
         const float2* cp = reinterpret_cast<const float2*>(a.cov3D + 6 * (size_t)i);
         const float2 p0 = cp[0], p1 = cp[1], p2 = cp[2];
         c6[0] = p0.x; c6[1] = p0.y; c6[2] = p1.x; c6[3] = p1.y; c6[4] = p2.x; c6[5] = p2.y;
@@ -239,7 +245,7 @@ cudaError_t gs_launch_preprocess_backward(const GsFrame& f, const GsGeom& g, con
     a.P = s.P; a.D = s.sh_degree; a.M = s.sh_stride;
     a.fx = f.focal_x; a.fy = f.focal_y; a.tanx = s.tan_fovx; a.tany = s.tan_fovy; a.mod = s.scale_modifier;
     a.means = s.means3D; a.radii = radii; a.shs = s.shs; a.clamp = g.clamp; a.scales = s.scales; a.rots = s.rotations;
-    a.cov3D = s.cov3D_precomp ? s.cov3D_precomp : g.cov3D;
+    a.cov3D = s.cov3D_precomp;  // nullptr: recomputed from scale / rotation
     a.view = s.viewmatrix; a.proj = s.projmatrix; a.campos = s.campos;
     a.dL_dmean2D = dL_dmean2D; a.dL_dconic = dL_dconic; a.dL_dcolor = dL_dcolor;
     a.dL_dmean3D = dL_dmean3D; a.dL_dcov3D = dL_dcov3D; a.dL_dsh = dL_dsh; a.dL_dscale = dL_dscale; a.dL_drot = dL_drot;

@@ -376,7 +376,7 @@ def decode_head(features: torch.Tensor, dc_rgb: torch.Tensor, primitives: torch.
     return out
 
 
-_FETCH_DT = {"records": torch.float32, "sorted_idx": torch.int32, "sorted_key": torch.int32, "cov3D": torch.float32,
+_FETCH_DT = {"records": torch.float32, "sorted_idx": torch.int32, "sorted_key": torch.int32,
              "clamped": torch.uint8, "tiles_touched": torch.int32, "point_list": torch.int32, "ranges": torch.int32,
              "n_contrib": torch.int32, "final_T": torch.float32}
 

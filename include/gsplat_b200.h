@@ -217,7 +217,7 @@ int32_t gs_decode_head(const float* features, const float* dc_rgb, const float* 
 
 /* Introspection for tests / profiling: copies a named internal array of the last forward into HOST memory.
  * names: "records" (P x 12 f32: x y cx cy | cz opacity thr -cy/cz | r g b -cy/cx), "point_list" (R x u32),
- * "ranges" (Tn x 2 u32), "n_contrib" (H*W u32), "final_T" (H*W f32), "sorted_idx" (P u32), "cov3D" (P x 6 f32),
+ * "ranges" (Tn x 2 u32), "n_contrib" (H*W u32), "final_T" (H*W f32), "sorted_idx" (P u32),
  * "clamped" (P u8, bit c = channel c clamped), "tiles_touched" (P u32).  Returns bytes copied or a negative code. */
 int64_t gs_fetch(const GsScene* scene, const char* geometry, const char* binning, const char* image,
                  int64_t num_rendered, const char* name, void* host_dst, int64_t max_bytes, void* stream);
