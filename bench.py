@@ -384,6 +384,31 @@ def tiles_leg(args, rank, world, fr, vdev, parts, W, H, dev, steps):
             "single_gpu_frame_ms": single_ms, "speedup_vs_single_gpu_frame": single_ms / ms}
 
 
+def tiles_c4_leg(args, rank, world, dev):
+    """Config C4 -- the workload the north star's tile-range split is for (5M random Gaussians, SH degree 3, 2048x2048):
+    the same sharded-frame measurement as `tiles_leg` (bit-exact assembly asserted, one frame at a time on one GPU
+    beside it) on this workload."""
+    from renderer import FrameRenderer
+    from diff_gaussian_rasterization import _C
+    cloud, views, w = make_workload("C4")
+    W, H = w["W"], w["H"]
+    gy = (H + 15) // 16
+    fr = FrameRenderer(cloud, W, H, [1.0, 1.0, 1.0], dev)
+    vdev = [fr.upload_view(v) for v in views]
+    parts = []
+    for v in vdev:
+        fr.render(v)  # (grows the instance buffers to this view's need)
+        scene = fr._scene(v, None)
+        ncon = _C.fetch("n_contrib", scene, fr.geom, fr.binning, fr.img, fr.capacity).view(H, W).to(dev)
+        _b, need = algorithmic_blend_bytes(ncon, W, H)
+        rng = _C.fetch("ranges", scene, fr.geom, fr.binning, fr.img, fr.capacity).view(-1, 2).to(torch.int64)
+        inst = (rng[:, 1] - rng[:, 0]).view(gy, -1)
+        parts.append(balanced_rows(sharding.row_cost(need.cpu().numpy(), inst.numpy()), world))
+    rec = tiles_leg(args, rank, world, fr, vdev, parts, W, H, dev, steps=24)
+    rec["workload"] = "C4: " + w["desc"]
+    return rec
+
+
 def run_b200(args, rank, world):
     from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer, _C
     from renderer import FramePipeline, FrameRenderer  # noqa: F401
@@ -530,6 +555,8 @@ def run_b200(args, rank, world):
     tiles = None
     if world > 1 and not tiles_mode and not args.no_tiles:
         tiles = tiles_leg(args, rank, world, fr, vdev, parts, W, H, dev, steps=max(8, min(args.steps, 120)))
+        if args.workload == "C2" and not args.no_extra:
+            tiles = dict(tiles, C4=tiles_c4_leg(args, rank, world, dev))
 
     # ---- e2e: host buffers (every step: all inputs pinned host -> device, image device -> host) ----
     host = {k: cloud[k].contiguous().pin_memory() for k in ("means3D", "opacities", "scales", "rotations", "shs")}

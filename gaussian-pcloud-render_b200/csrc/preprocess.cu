@@ -63,6 +63,25 @@ __device__ __forceinline__ float3 sh_to_rgb(int deg, const float* __restrict__ s
     return make_float3(res[0], res[1], res[2]);
 }
 
+// The same for degree <= 1 with the (at most) 12 coefficients already in registers (loaded up front by the caller, so
+// that a Gaussian costs one round trip to memory instead of one per input array).
+__device__ __forceinline__ float3 sh_to_rgb_low(int deg, const float (&sh)[12], float3 mean, float3 cam,
+                                                unsigned& clamp_bits) {
+    float3 dir = make_float3(mean.x - cam.x, mean.y - cam.y, mean.z - cam.z);
+    const float len = sqrtf(dir.x * dir.x + dir.y * dir.y + dir.z * dir.z);
+    const float x = dir.x / len, y = dir.y / len, z = dir.z / len;
+    float res[3];
+#pragma unroll
+    for (int ch = 0; ch < 3; ch++) {
+        float r = __fmul_rn(GS_SH_C0, sh[ch]);
+        if (deg > 0) r = r - GS_SH_C1 * y * sh[3 + ch] + GS_SH_C1 * z * sh[6 + ch] - GS_SH_C1 * x * sh[9 + ch];
+        r += 0.5f;
+        if (r < 0.f) clamp_bits |= 1u << ch;
+        res[ch] = (r < 0.0f) ? 0.0f : r;
+    }
+    return make_float3(res[0], res[1], res[2]);
+}
+
 // ---- TMA bulk staging (sm_90+/sm_100a): one elected thread issues 1-D bulk copies global -> shared that complete
 // on an mbarrier; the inputs of a block are five contiguous slabs of the caller's AoS arrays.
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -135,8 +154,21 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreArgs a) {
         int radius_out = 0;
         uint32_t key = 0xFFFFFFFFu;  // culled Gaussians sort to the end of the depth order
         ushort4 rect = make_ushort4(0, 0, 0, 0);
+        // every input of this Gaussian is requested before the first early-out below can hold a load back: one round
+        // trip to memory per thread instead of four (position -> scale / rotation -> SH -> opacity)
+        const float3 mean = make_float3(mp[0], mp[1], mp[2]);
+        float3 sc_in = make_float3(0.f, 0.f, 0.f);
+        float4 q_in = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a.cov3D_pre == nullptr) {
+            sc_in = make_float3(sp[0], sp[1], sp[2]);
+            q_in = *reinterpret_cast<const float4*>(rp);
+        }
+        const float op = *op_ptr;
+        const bool sh_low = !STAGED && a.colors_pre == nullptr && a.D <= 1;
+        float sh_in[12];
+#pragma unroll
+        for (int k = 0; k < 12; k++) sh_in[k] = (sh_low && (k < 3 || a.D == 1)) ? shp[k] : 0.f;
         do {
-            const float3 mean = make_float3(mp[0], mp[1], mp[2]);
             const float3 p_view = xform43(a.view, mean);
             if (p_view.z <= 0.2f) {  // near plane only (auxiliary.h:154)
                 bad = a.prefiltered != 0;
@@ -151,9 +183,7 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreArgs a) {
 #pragma unroll
                 for (int k = 0; k < 6; k++) c6[k] = a.cov3D_pre[6 * (size_t)i + k];
             } else {
-                const float3 sc = make_float3(sp[0], sp[1], sp[2]);
-                const float4 q = *reinterpret_cast<const float4*>(rp);
-                cov3d_from_scale_rot(sc, a.mod, q, c6);  // (not stored: the backward pass recomputes it)
+                cov3d_from_scale_rot(sc_in, a.mod, q_in, c6);  // (not stored: the backward pass recomputes it)
             }
             Cov2D k2;
             cov2d_eval(mean, a.fx, a.fy, a.tanx, a.tany, c6, a.view, k2);
@@ -174,12 +204,12 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreArgs a) {
             float3 rgb = make_float3(0.f, 0.f, 0.f);
             unsigned clamp_bits = 0;
             if (a.colors_pre == nullptr) {
-                rgb = sh_to_rgb(a.D, shp, mean, make_float3(a.campos[0], a.campos[1], a.campos[2]), clamp_bits);
+                const float3 cam = make_float3(a.campos[0], a.campos[1], a.campos[2]);
+                rgb = sh_low ? sh_to_rgb_low(a.D, sh_in, mean, cam, clamp_bits) : sh_to_rgb(a.D, shp, mean, cam, clamp_bits);
                 a.clamp[i] = (uint8_t)clamp_bits;
             } else {
                 rgb = make_float3(a.colors_pre[3 * i], a.colors_pre[3 * i + 1], a.colors_pre[3 * i + 2]);
             }
-            const float op = *op_ptr;
             // Conservative cut-off on `power`: below it, op*exp(power) < (1/255)(1 - 1e-3), so the blend kernels
             // may skip the exponential with no change to the result (alpha < 1/255 is skipped anyway).
             const float thr = -logf(255.0f * op) - 1.0e-3f;
@@ -256,6 +286,16 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreArgs a) {
 // tie order is the Gaussian index, so the compaction must keep it.
 __device__ __forceinline__ bool shard_candidate(const PreArgs& a, int i) {
     const float3 mean = make_float3(a.means[3 * (size_t)i], a.means[3 * (size_t)i + 1], a.means[3 * (size_t)i + 2]);
+    // (all inputs are requested before the near-plane early-out: one round trip to memory per Gaussian)
+    float tr_in[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (a.cov3D_pre != nullptr) {
+        tr_in[0] = a.cov3D_pre[6 * (size_t)i]; tr_in[1] = a.cov3D_pre[6 * (size_t)i + 3]; tr_in[2] = a.cov3D_pre[6 * (size_t)i + 5];
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; k++) tr_in[k] = a.rots[4 * (size_t)i + k];
+#pragma unroll
+        for (int k = 0; k < 3; k++) tr_in[4 + k] = a.scales[3 * (size_t)i + k];
+    }
     const float3 p_view = xform43(a.view, mean);
     if (p_view.z <= 0.2f) return false;
     const float4 p_hom = xform44(a.proj, mean);
@@ -263,12 +303,10 @@ __device__ __forceinline__ bool shard_candidate(const PreArgs& a, int i) {
     const float py = ndc_to_pix(p_hom.y * p_w, a.H);
     float tr;  // trace of the world covariance
     if (a.cov3D_pre != nullptr) {
-        tr = a.cov3D_pre[6 * (size_t)i] + a.cov3D_pre[6 * (size_t)i + 3] + a.cov3D_pre[6 * (size_t)i + 5];
+        tr = tr_in[0] + tr_in[1] + tr_in[2];
     } else {
-        const float r = a.rots[4 * (size_t)i], x = a.rots[4 * (size_t)i + 1], y = a.rots[4 * (size_t)i + 2],
-                    z = a.rots[4 * (size_t)i + 3];
-        const float s0 = a.mod * a.scales[3 * (size_t)i], s1 = a.mod * a.scales[3 * (size_t)i + 1],
-                    s2 = a.mod * a.scales[3 * (size_t)i + 2];
+        const float r = tr_in[0], x = tr_in[1], y = tr_in[2], z = tr_in[3];
+        const float s0 = a.mod * tr_in[4], s1 = a.mod * tr_in[5], s2 = a.mod * tr_in[6];
         // squared column norms of the (un-normalised) quaternion's rotation matrix
         const float a00 = 1.f - 2.f * (y * y + z * z), a10 = 2.f * (x * y + r * z), a20 = 2.f * (x * z - r * y);
         const float a01 = 2.f * (x * y - r * z), a11 = 1.f - 2.f * (x * x + z * z), a21 = 2.f * (y * z + r * x);
