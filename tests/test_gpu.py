@@ -1009,3 +1009,43 @@ def test_shard_cull_reassembles_the_frame_bitwise(kind):
             acc += part
         assert torch.equal(acc, full)
         assert torch.equal(fr.render(vd), full)                       # and the plain path afterwards is unaffected
+
+
+def test_compiled_reference_side_binding(golden):
+    """The reference's pybind module compiled against -lgsplat_b200 (integration/rasterize_points_b200.cpp: the three
+    functions of dgr/ext.cpp:15-19 with the argument order of rasterize_points.h:19-67) renders a frame: forward outputs
+    equal the ctypes binding's bit for bit and the golden vectors of the reference library, gradients agree."""
+    import sys
+    dev = _dev()
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "integration"))
+    try:
+        import build as integration_build
+        ext = integration_build.load_built()
+    except ImportError as ex:
+        pytest.skip(f"compiled binding not built ({ex})")
+    from diff_gaussian_rasterization import _C
+    name = next(n for n in GOLDEN_NAMES if golden[n][1].get("colors_precomp") is None and golden[n][1].get("scales") is not None)
+    _, kw, g = golden[name]
+    t = lambda a: torch.as_tensor(np.asarray(a, np.float32)).to(dev)
+    empty = torch.Tensor([]).to(dev)
+    opt = lambda k: t(kw[k]) if kw.get(k) is not None else empty
+    args = (t(kw["bg"]), t(kw["means3D"]), opt("colors_precomp"), t(kw["opacities"]), opt("scales"), opt("rotations"), 1.0,
+            opt("cov3D_precomp"), t(kw["viewmatrix"]).reshape(4, 4), t(kw["projmatrix"]).reshape(4, 4), float(kw["tanfovx"]),
+            float(kw["tanfovy"]), int(kw["H"]), int(kw["W"]), opt("shs"), int(kw["sh_degree"]), t(kw["campos"]).reshape(3),
+            False, False)
+    R, color, radii, gb, bb, ib = ext.rasterize_gaussians(*args)
+    assert np.array_equal(radii.cpu().numpy(), g["radii"])
+    assert np.abs(color.cpu().numpy() - g["color"]).max() <= PIX_TOL
+    color2, radii2, _, _ = _render(kw, dev, quirk_shapes=False)
+    assert torch.equal(color, color2) and torch.equal(radii, radii2)          # same library underneath: bit for bit
+    wgt = t(loss_weights(tuple(color.shape)))
+    grads = ext.rasterize_gaussians_backward(args[0], args[1], radii, args[2], args[4], args[5], 1.0, args[7], args[8],
+                                             args[9], args[10], args[11], wgt, args[14], args[15], args[16], gb, R, bb,
+                                             ib, False)
+    names = ("dL_dmeans2D", "dL_dcolors", "dL_dopacity", "dL_dmeans3D", "dL_dcov3D", "dL_dsh", "dL_dscales", "dL_drotations")
+    for nme, got in zip(names, grads):
+        if nme in g:
+            ref = np.asarray(g[nme], np.float32).reshape(got.shape)
+            assert np.abs(got.cpu().numpy() - ref).max() <= GRAD_RTOL * max(1e-12, np.abs(ref).max()), nme
+    vis = ext.mark_visible(args[1], args[8], args[9])
+    assert torch.equal(vis, _C.mark_visible(args[1], args[8], args[9]))
