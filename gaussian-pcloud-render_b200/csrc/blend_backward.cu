@@ -71,6 +71,13 @@ __device__ __forceinline__ float box_max_power_sel(float A, float B, float C, fl
     return (in_x && in_y) ? 0.f : best;
 }
 
+// Predicated shared-memory store (no branch; nothing is written when the predicate is false).
+__device__ __forceinline__ void sts_if(bool p, float4* dst, float4 v) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(dst);
+    asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %0, 0;\n@q st.shared.v4.f32 [%1], {%2, %3, %4, %5};\n}"
+                 ::"r"((unsigned)p), "r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
@@ -91,9 +98,9 @@ struct BbRing {
     float4 b[BB_STAGES][32];   // conic.z, opacity, thr, -B/C
     float4 c[BB_STAGES][32];   // r, g, b, -B/A
     uint32_t id[BB_STAGES][32];
-    float4 fa[BB_FIFO + 2];    // FIFO: x, y, conic.x, conic.y         (entries BB_FIFO, BB_FIFO + 1: scratch)
-    float4 fb[BB_FIFO + 2];    //       conic.z, opacity, thr, list position (the reference's `contributor`)
-    float4 fc[BB_FIFO + 2];    //       r, g, b, Gaussian index
+    float4 fa[BB_FIFO];        // FIFO: x, y, conic.x, conic.y
+    float4 fb[BB_FIFO];        //       conic.z, opacity, thr, list position (the reference's `contributor`)
+    float4 fc[BB_FIFO];        //       r, g, b, Gaussian index
 };
 
 #ifndef BB_OCC
@@ -212,21 +219,18 @@ __global__ void __launch_bounds__(BB_WARPS * 32, BB_OCC) blend_backward_kernel(
             {   // compaction: the survivor of lane l goes to FIFO entry head + avail + (survivors in lower lanes)
                 unsigned pos = head + avail + (unsigned)__popc(mask & ((1u << lane) - 1u));
                 if (pos >= (unsigned)BB_FIFO) pos -= (unsigned)BB_FIFO;
-                pos = hit ? pos : (unsigned)BB_FIFO;  // (scratch entry)
-                R.fa[pos] = ra;
-                R.fb[pos] = make_float4(rb.x, rb.y, rb.z, __uint_as_float(need - 1u - (base + (uint32_t)lane)));
-                R.fc[pos] = make_float4(rc.x, rc.y, rc.z, __uint_as_float(rid));
+                sts_if(hit, &R.fa[pos], ra);
+                sts_if(hit, &R.fb[pos], make_float4(rb.x, rb.y, rb.z, __uint_as_float(need - 1u - (base + (uint32_t)lane))));
+                sts_if(hit, &R.fc[pos], make_float4(rc.x, rc.y, rc.z, __uint_as_float(rid)));
                 avail += (unsigned)__popc(mask);
                 // the last batch pads the last pair with a null record (list position 2^32 - 1: no pixel takes part)
                 const unsigned pad = final_batch ? (avail & 1u) : 0u;
                 unsigned pp = head + avail;
                 if (pp >= (unsigned)BB_FIFO) pp -= (unsigned)BB_FIFO;
-                pp = pad ? pp : (unsigned)BB_FIFO + 1u;
-                if (lane == 0) {
-                    R.fa[pp] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    R.fb[pp] = make_float4(0.f, 0.f, 0.f, __uint_as_float(0xFFFFFFFFu));
-                    R.fc[pp] = make_float4(0.f, 0.f, 0.f, 0.f);
-                }
+                const bool padder = pad != 0u && lane == 0;
+                sts_if(padder, &R.fa[pp], make_float4(0.f, 0.f, 0.f, 0.f));
+                sts_if(padder, &R.fb[pp], make_float4(0.f, 0.f, 0.f, __uint_as_float(0xFFFFFFFFu)));
+                sts_if(padder, &R.fc[pp], make_float4(0.f, 0.f, 0.f, 0.f));
                 avail += pad;
                 __syncwarp();
             }

@@ -1377,10 +1377,23 @@ struct BiRing {  // one per warp
     float4 a[BF_STAGES][32];  // x, y, conic.x, conic.y                      } the record ring (cp.async), as BfStage
     float4 b[BF_STAGES][32];  // conic.z, opacity, thr, -B/C                 }
     float4 c[BF_STAGES][32];  // r, g, b, -B/A                               }
-    float4 fa[BI_FIFO + 2];   // FIFO of survivors: x, y, conic.x, conic.y   (entry BI_FIFO: scratch, takes the stores
-    float4 fc[BI_FIFO + 2];   //                    r, g, b, list position + 1  of the lanes that have no survivor)
-    float2 fb[BI_FIFO + 2];   //                    conic.z, opacity
+    float4 fa[BI_FIFO];       // FIFO of survivors: x, y, conic.x, conic.y
+    float4 fc[BI_FIFO];       //                    r, g, b, list position + 1
+    float2 fb[BI_FIFO];       //                    conic.z, opacity
 };
+
+// Predicated shared-memory stores (no branch, and nothing is written when the predicate is false -- a dummy "scratch"
+// target for the lanes without a survivor would be a write-write race in the eyes of compute-sanitizer).
+__device__ __forceinline__ void sts_if(bool p, float4* dst, float4 v) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(dst);
+    asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %0, 0;\n@q st.shared.v4.f32 [%1], {%2, %3, %4, %5};\n}"
+                 ::"r"((unsigned)p), "r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts_if(bool p, float2* dst, float2 v) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(dst);
+    asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %0, 0;\n@q st.shared.v2.f32 [%1], {%2, %3};\n}"
+                 ::"r"((unsigned)p), "r"(a), "f"(v.x), "f"(v.y) : "memory");
+}
 
 __device__ __forceinline__ void bf_fill_empty_tile(uint32_t tile, int gx, int W, int H, int lane, float bg0, float bg1,
                                                    float bg2, float* __restrict__ final_T,
@@ -1565,19 +1578,18 @@ __global__ void __launch_bounds__(BF_WARPS * 32, BF_PX2_OCC) blend_forward_group
             {   // compaction: the survivor of lane l goes to FIFO entry head + avail + (survivors in lower lanes)
                 unsigned pos = head + avail + (unsigned)__popc(mask & ((1u << lane) - 1u));
                 if (pos >= (unsigned)BI_FIFO) pos -= (unsigned)BI_FIFO;
-                pos = hit ? pos : (unsigned)BI_FIFO;  // (scratch entry)
-                R.fa[pos] = ra;
-                R.fb[pos] = make_float2(rb.x, rb.y);
-                R.fc[pos] = make_float4(rc.x, rc.y, rc.z, __uint_as_float(base + (uint32_t)lane + 1u));
+                sts_if(hit, &R.fa[pos], ra);
+                sts_if(hit, &R.fb[pos], make_float2(rb.x, rb.y));
+                sts_if(hit, &R.fc[pos], make_float4(rc.x, rc.y, rc.z, __uint_as_float(base + (uint32_t)lane + 1u)));
                 avail += (unsigned)__popc(mask);
                 // the last batch pads the last group with null records (opacity 0 -> alpha 0)
                 const unsigned pad = final_batch ? ((unsigned)BI_G - avail % BI_G) % BI_G : 0u;
                 unsigned pp = head + avail + (unsigned)lane;
                 if (pp >= (unsigned)BI_FIFO) pp -= (unsigned)BI_FIFO;
-                pp = (unsigned)lane < pad ? pp : (unsigned)BI_FIFO + 1u;
-                R.fa[pp] = make_float4(0.f, 0.f, 0.f, 0.f);
-                R.fb[pp] = make_float2(0.f, 0.f);
-                R.fc[pp] = make_float4(0.f, 0.f, 0.f, 0.f);
+                const bool padder = (unsigned)lane < pad;
+                sts_if(padder, &R.fa[pp], make_float4(0.f, 0.f, 0.f, 0.f));
+                sts_if(padder, &R.fb[pp], make_float2(0.f, 0.f));
+                sts_if(padder, &R.fc[pp], make_float4(0.f, 0.f, 0.f, 0.f));
                 avail += pad;
                 __syncwarp();
             }
