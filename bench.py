@@ -561,7 +561,8 @@ def run_b200(args, rank, world):
     # ---- e2e: host buffers (every step: all inputs pinned host -> device, image device -> host) ----
     host = {k: cloud[k].contiguous().pin_memory() for k in ("means3D", "opacities", "scales", "rotations", "shs")}
     packed = scenes.pack_cloud(cloud)
-    host_packed = dict(host, shs=packed["shs"].contiguous().pin_memory())
+    from renderer import host_block
+    host_packed = host_block(packed)  # the five attribute arrays as ONE pinned block: one host->device copy per step
     hviews = [(torch.from_numpy(v.viewmatrix).pin_memory(), torch.from_numpy(v.projmatrix).pin_memory(),
                torch.from_numpy(v.campos).pin_memory()) for v in views]
     bg = torch.ones(3, device=dev)
@@ -570,7 +571,7 @@ def run_b200(args, rank, world):
     vdev2 = [torch.empty(4, 4, device=dev), torch.empty(4, 4, device=dev), torch.empty(3, device=dev)]
     cam_bytes = (16 + 16 + 3) * 4
     h2d = sum(t.numel() * 4 for t in host.values()) + cam_bytes
-    h2d_packed = sum(t.numel() * 4 for t in host_packed.values()) + cam_bytes
+    h2d_packed = host_packed["_flat"].numel() * 4 + cam_bytes
     d2h = 3 * H * W * 4
 
     def e2e_frame(i, upload_cloud=True):
@@ -639,11 +640,16 @@ def run_b200(args, rank, world):
             if hp.lanes[used[i]].status(i)[2] != 0:
                 raise RuntimeError("pipelined e2e frame failed")
         t = max_over_ranks(e0.elapsed_time(e1), world, dev)
+        # the last frame that came back over PCIe equals the frame rendered from the resident cloud, bit for bit
+        torch.cuda.synchronize()
+        k_last = (rank + (4 + steps - 1) * world) % nv
+        if not torch.equal(outs[(hp.count - 1) % hp.depth], fr.render(vdev[k_last]).cpu()):
+            raise RuntimeError("pipelined e2e frame differs from the resident-cloud frame")
         return steps * world / (t / 1e3)
 
     e2e_steps = max(3, min(args.steps, 40))
     serial = e2e_run(e2e_steps)
-    piped_full = e2e_pipelined(e2e_steps, host, cloud)
+    piped_full = e2e_pipelined(e2e_steps, host_block(cloud), cloud)
     piped = e2e_pipelined(e2e_steps, host_packed, packed, fan_out=True)
     fan = world > 1 and piped is not None
     e2e = {"value": piped if piped is not None else serial, "unit": "frames/s",
@@ -652,9 +658,9 @@ def run_b200(args, rank, world):
            "api": (("renderer.FramePipeline.enqueue_host (3 frames in flight; C ABI gs_forward_nosync), pinned host inputs -> "
                     "device -> pinned host image every step; host cloud in the packed layout gs_decode_head emits (SH "
                     f"array without its all-zero coefficients: {h2d_packed} instead of {h2d} bytes per cloud, same frame "
-                    "bit for bit)") +
+                    "bit for bit), its five arrays in one pinned block = one host->device copy per step") +
                    (f"; the {world} ranks render {world} views of the same cloud per step, each uploads 1/{world} of it and "
-                    "one NVLink all-gather per attribute array completes it on every GPU (bytes are per rank)" if fan else ""))
+                    "one NVLink all-gather completes it on every GPU (bytes are per rank)" if fan else ""))
                   if piped is not None else
                   "diff_gaussian_rasterization.GaussianRasterizer (drop-in), pinned host inputs -> device -> host image",
            # the reference's own host layout (13 SH coefficients per point, 12 of them zero), every rank uploads all of it

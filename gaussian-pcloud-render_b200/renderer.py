@@ -253,6 +253,33 @@ def render_passes(fr, views: "ViewBatch", normals: Optional[torch.Tensor] = None
     return {n: t.permute(0, 2, 3, 1) for n, t in out.items()}
 
 
+def host_block(cloud: dict, pin: bool = True) -> dict:
+    """The Gaussian attributes of a cloud as ONE host buffer: returns the cloud dict with its five attribute arrays
+    replaced by views into a single (pinned) float32 block, arrays back to back (each start a multiple of 64 floats),
+    plus the block under "_flat" and the (name, offset, shape) layout under "_layout".
+    FramePipeline.enqueue_host then moves the whole cloud with one host->device copy instead of five (measured on the
+    B200 box: 50.1 instead of 45.6 GB/s with the image download running the other way, tools/pcie_probe.py)."""
+    names = FramePipeline._ATTRS
+    layout, off = [], 0
+    for n in names:
+        t = cloud[n]
+        layout.append((n, off, tuple(t.shape)))
+        off += -(-t.numel() // 64) * 64
+    flat = torch.empty(off, dtype=torch.float32)
+    if pin:
+        flat = flat.pin_memory()
+    out = dict(cloud)
+    for n, o, shp in layout:
+        cnt = 1
+        for d in shp:
+            cnt *= d
+        v = flat[o:o + cnt].view(shp)
+        v.copy_(cloud[n].to(torch.float32))
+        out[n] = v
+    out["_flat"], out["_layout"] = flat, layout
+    return out
+
+
 class FramePipeline:
     """Several frames in flight on separate CUDA streams, each with its own workspaces (the cloud is shared).
 
@@ -335,6 +362,22 @@ class FramePipeline:
         ln._in_rows = rows
         ln._consumed = None  # event: the lane's last frame has read its inputs
 
+    def _own_inputs_flat(self, ln, layout, numel: int, world: int) -> int:
+        """Private device block of one lane for a host_block cloud: the lane's attribute tensors become views into it
+        (same offsets as the host block).  Padded to a multiple of `world` equal slices; returns the slice length."""
+        S = -(-numel // (64 * world)) * 64
+        if getattr(ln, "_flat_key", None) != (numel, world):
+            ln._flat = torch.empty(S * world, dtype=torch.float32, device=self.dev)
+            for n, o, shp in layout:
+                cnt = 1
+                for d in shp:
+                    cnt *= d
+                setattr(ln, n, ln._flat[o:o + cnt].view(shp))
+            ln._view_dev = (torch.empty(4, 4, device=self.dev), torch.empty(4, 4, device=self.dev),
+                            torch.empty(3, device=self.dev))
+            ln._flat_key, ln._in_rows, ln._consumed = (numel, world), 0, None
+        return S
+
     def enqueue_host(self, host_cloud: dict, host_view, tanfov, out_host: torch.Tensor, slot: int = 0,
                      group=None) -> int:
         """One frame whose inputs live in (pinned) HOST memory: uploads the Gaussian attributes and the camera of
@@ -349,6 +392,38 @@ class FramePipeline:
         k = self.count % len(self.lanes)
         self.count += 1
         ln = self.lanes[k]
+        flat = host_cloud.get("_flat")
+        if flat is not None:  # the cloud as one host block (host_block): one copy (per rank: one slice + one all-gather)
+            import torch.distributed as dist
+            world = dist.get_world_size(group) if group is not None else 1
+            rank = dist.get_rank(group) if group is not None else 0
+            S = self._own_inputs_flat(ln, host_cloud["_layout"], flat.numel(), world)
+            if group is None:
+                with torch.cuda.stream(self.streams[k]):
+                    ln._flat[: flat.numel()].copy_(flat, non_blocking=True)
+                    for dst, src in zip(ln._view_dev, host_view):
+                        dst.copy_(src, non_blocking=True)
+                    out = ln.enqueue(ln._view_dev + (tanfov[0], tanfov[1]), slot=slot)
+                    out_host.copy_(out, non_blocking=True)
+                return k
+            if not hasattr(self, "_feed"):
+                self._feed = torch.cuda.Stream(self.dev)
+            a, b = min(flat.numel(), rank * S), min(flat.numel(), (rank + 1) * S)
+            with torch.cuda.stream(self._feed):
+                if ln._consumed is not None:
+                    self._feed.wait_event(ln._consumed)
+                if b > a:
+                    ln._flat[a:b].copy_(flat[a:b], non_blocking=True)
+                dist.all_gather_into_tensor(ln._flat, ln._flat[rank * S:(rank + 1) * S], group=group)
+                fed = self._feed.record_event()
+            with torch.cuda.stream(self.streams[k]):
+                self.streams[k].wait_event(fed)
+                for dst, src in zip(ln._view_dev, host_view):
+                    dst.copy_(src, non_blocking=True)
+                out = ln.enqueue(ln._view_dev + (tanfov[0], tanfov[1]), slot=slot)
+                ln._consumed = self.streams[k].record_event()
+                out_host.copy_(out, non_blocking=True)
+            return k
         if group is None:
             self._own_inputs(ln, ln.P)
             with torch.cuda.stream(self.streams[k]):

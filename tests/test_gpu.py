@@ -317,6 +317,17 @@ def test_frame_pipeline_matches_dropin_bitwise():
     torch.cuda.synchronize()
     for a, b in zip(himg, refs):
         assert torch.equal(a, b.cpu())
+    # the same cloud as ONE pinned host block (renderer.host_block): one host->device copy per frame
+    from renderer import host_block
+    blk = host_block(cl)
+    himg2 = [torch.empty((3, 320, 480)).pin_memory() for _ in views]
+    pipe.begin()
+    for i, v in enumerate(views):
+        pipe.enqueue_host(blk, hv[i], (v.tanfovx, v.tanfovy), himg2[i], slot=i)
+    pipe.end()
+    torch.cuda.synchronize()
+    for a, b in zip(himg2, refs):
+        assert torch.equal(a, b.cpu())
 
 
 
