@@ -316,7 +316,7 @@ def frames_leg_b200(name, dev, streams=4, steps=24):
             "frames_in_flight": streams, "steps": steps, "single_frame_ms": single}
 
 
-def tiles_leg(args, rank, world, fr, vdev, parts, W, H, dev, steps):
+def tiles_leg(args, rank, world, fr, vdev, parts, W, H, dev, steps, refine=2):
     """The north star's split of ONE frame: every rank bins + blends a work-balanced range of tile rows and the image
     is assembled on every GPU (peer stores from the blend epilogue + one symmetric-memory barrier, or one NCCL
     all-gather).  The assembled frame is compared bit for bit with the frame this rank renders alone before timing."""
@@ -344,6 +344,18 @@ def tiles_leg(args, rank, world, fr, vdev, parts, W, H, dev, steps):
         sharding.exchange_image(fr.color, rows, rank)
         return fr.color
 
+    # ---- profile-guided refinement of the row partitions: every rank times ITS range of a view alone, the times are
+    # all-gathered and the boundaries move towards equal time (sharding.rebalance_rows; deterministic, same on all ranks)
+    gy_rows = (H + 15) // 16
+    for _it in range(refine):
+        for k in range(nv):
+            r0, r1 = parts[k][rank]
+            mine_ms = (_median_ms(lambda i: fr.enqueue(vdev[k], tile_rows=(r0, r1), shard_cull=True), 3, warm=1)
+                       if r1 > r0 else 0.0)
+            tt = torch.tensor([mine_ms], dtype=torch.float64, device=dev)
+            allt = [torch.zeros_like(tt) for _ in range(world)]
+            dist.all_gather(allt, tt)
+            parts[k] = sharding.rebalance_rows(parts[k], [float(x.item()) for x in allt], gy_rows)
     # ---- correctness first: assembled == single-GPU frame, on every rank, for a few views
     ok = torch.ones(1, dtype=torch.int32, device=dev)
     share = None
@@ -382,6 +394,7 @@ def tiles_leg(args, rank, world, fr, vdev, parts, W, H, dev, steps):
             "exchange": ("blend epilogue stores into all ranks' images over NVLink + one symmetric-memory barrier per frame"
                          if peer is not None else "one NCCL all-gather per frame"),
             "bit_identical_to_single_gpu_frame": True, "num_rendered_share_per_rank": share,
+            "row_partition": f"prefix-sum balance of a per-row cost model, then {refine} profile-guided refinement passes per view",
             "single_gpu_frame_ms": single_ms, "speedup_vs_single_gpu_frame": single_ms / ms}
 
 

@@ -1373,12 +1373,15 @@ __global__ void __launch_bounds__(BF_WARPS * 32, (K == 0) ? BF_PX2_OCC : 2) blen
 #endif
 #define BI_FIFO 48  // FIFO entries: a multiple of BI_G (a group never wraps) >= 32 + BI_G - 1 (one batch + left-overs)
 static_assert(BI_FIFO % BI_G == 0 && BI_FIFO >= 32 + 2 * BI_G - 1, "FIFO size");
+template <int K>  // K = extra colour passes blended in the same list walk (GsScene.extra_colors)
 struct BiRing {  // one per warp
     float4 a[BF_STAGES][32];  // x, y, conic.x, conic.y                      } the record ring (cp.async), as BfStage
     float4 b[BF_STAGES][32];  // conic.z, opacity, thr, -B/C                 }
     float4 c[BF_STAGES][32];  // r, g, b, -B/A                               }
+    float4 e[K > 0 ? K : 1][BF_STAGES][32];  // colours of the extra passes  }
     float4 fa[BI_FIFO];       // FIFO of survivors: x, y, conic.x, conic.y
     float4 fc[BI_FIFO];       //                    r, g, b, list position + 1
+    float4 fe[K > 0 ? K : 1][BI_FIFO];  //          colours of the extra passes
     float2 fb[BI_FIFO];       //                    conic.z, opacity
 };
 
@@ -1395,11 +1398,18 @@ __device__ __forceinline__ void sts_if(bool p, float2* dst, float2 v) {
                  ::"r"((unsigned)p), "r"(a), "f"(v.x), "f"(v.y) : "memory");
 }
 
+template <int K>
 __device__ __forceinline__ void bf_fill_empty_tile(uint32_t tile, int gx, int W, int H, int lane, float bg0, float bg1,
                                                    float bg2, float* __restrict__ final_T,
-                                                   uint32_t* __restrict__ n_contrib, const BfTargets& tg) {
+                                                   uint32_t* __restrict__ n_contrib, const BfTargets& tg,
+                                                   const BfExtra& ex) {
     const size_t plane = (size_t)H * W;
     const int x0 = (int)(tile % gx) * GS_TILE, y0 = (int)(tile / gx) * GS_TILE;
+    // colour images: the frame's targets (this rank's image or all peers') and the images of the K extra passes
+    auto for_each_image = [&](auto&& store) {
+        _Pragma("unroll") for (int k = 0; k < 8; k++) if (k < tg.n) store(tg.img[k]);
+        _Pragma("unroll") for (int k = 0; k < K; k++) store(ex.out[k]);
+    };
     if (tg.ds) {  // half-resolution colour (8x8 per tile), full-resolution T / contributor count
         const int W2 = W >> 1, H2 = H >> 1;
         const size_t plane2 = (size_t)W2 * H2;
@@ -1409,10 +1419,7 @@ __device__ __forceinline__ void bf_fill_empty_tile(uint32_t tile, int gx, int W,
             const int qy = (y0 >> 1) + r * 4 + (lane >> 3);
             if (qx < W2 && qy < H2) {
                 const size_t pid = (size_t)W2 * qy + qx;
-                _Pragma("unroll") for (int k = 0; k < 8; k++) if (k < tg.n) {
-                    float* oc = tg.img[k];
-                    oc[pid] = bg0; oc[plane2 + pid] = bg1; oc[2 * plane2 + pid] = bg2;
-                }
+                for_each_image([&](float* oc) { oc[pid] = bg0; oc[plane2 + pid] = bg1; oc[2 * plane2 + pid] = bg2; });
             }
         }
         for (int r = 0; r < 8; r++) {
@@ -1429,12 +1436,11 @@ __device__ __forceinline__ void bf_fill_empty_tile(uint32_t tile, int gx, int W,
             const int py = y0 + r * 8 + (lane >> 2);
             if (py < H) {
                 const size_t pid = (size_t)W * py + px;
-                _Pragma("unroll") for (int k = 0; k < 8; k++) if (k < tg.n) {
-                    float* oc = tg.img[k];
+                for_each_image([&](float* oc) {
                     *reinterpret_cast<float4*>(oc + pid) = make_float4(bg0, bg0, bg0, bg0);
                     *reinterpret_cast<float4*>(oc + plane + pid) = make_float4(bg1, bg1, bg1, bg1);
                     *reinterpret_cast<float4*>(oc + 2 * plane + pid) = make_float4(bg2, bg2, bg2, bg2);
-                }
+                });
                 *reinterpret_cast<float4*>(final_T + pid) = make_float4(1.f, 1.f, 1.f, 1.f);
                 *reinterpret_cast<uint4*>(n_contrib + pid) = make_uint4(0u, 0u, 0u, 0u);
             }
@@ -1444,26 +1450,24 @@ __device__ __forceinline__ void bf_fill_empty_tile(uint32_t tile, int gx, int W,
             const int px = x0 + (lane & 15), py = y0 + r * 2 + (lane >> 4);
             if (px < W && py < H) {
                 const size_t pid = (size_t)W * py + px;
-                _Pragma("unroll") for (int k = 0; k < 8; k++) if (k < tg.n) {
-                    float* oc = tg.img[k];
-                    oc[pid] = bg0; oc[plane + pid] = bg1; oc[2 * plane + pid] = bg2;
-                }
+                for_each_image([&](float* oc) { oc[pid] = bg0; oc[plane + pid] = bg1; oc[2 * plane + pid] = bg2; });
                 final_T[pid] = 1.f; n_contrib[pid] = 0u;
             }
         }
     }
 }
 
-__global__ void __launch_bounds__(BF_WARPS * 32, BF_PX2_OCC) blend_forward_grouped_kernel(
+template <int K>
+__global__ void __launch_bounds__(BF_WARPS * 32, (K == 0) ? BF_PX2_OCC : 2) blend_forward_grouped_kernel(
     const uint2* __restrict__ ranges, const uint32_t* __restrict__ order, const uint32_t* __restrict__ list,
     const GsRec* __restrict__ rec, int W, int H, int gx, uint32_t num_tiles, GsHeader* __restrict__ hdr,
     const float* __restrict__ bg, float* __restrict__ final_T, uint32_t* __restrict__ n_contrib, const BfTargets tg,
-    int quota) {
+    const BfExtra ex, int quota) {
     extern __shared__ __align__(16) unsigned char s_ring_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int lx = lane & 7, ly = lane >> 3;
     const float bg0 = bg[0], bg1 = bg[1], bg2 = bg[2];
-    BiRing& R = reinterpret_cast<BiRing*>(s_ring_raw)[warp];
+    BiRing<K>& R = reinterpret_cast<BiRing<K>*>(s_ring_raw)[warp];
     unsigned* const q_fresh = &hdr->tickets[6];
     const uint32_t nonempty = hdr->nonempty_tiles;
     const uint32_t blend_units = nonempty * 4u;
@@ -1475,7 +1479,7 @@ __global__ void __launch_bounds__(BF_WARPS * 32, BF_PX2_OCC) blend_forward_group
         unit = __shfl_sync(GS_FULL, unit, 0);
         if (unit >= num_units) break;
         if (unit >= blend_units) {  // ---- empty tile: colour = background, T = 1, no contributor
-            bf_fill_empty_tile(order[nonempty + (unit - blend_units)], gx, W, H, lane, bg0, bg1, bg2, final_T, n_contrib, tg);
+            bf_fill_empty_tile<K>(order[nonempty + (unit - blend_units)], gx, W, H, lane, bg0, bg1, bg2, final_T, n_contrib, tg, ex);
             continue;
         }
         const uint32_t tile = order[unit >> 2];
@@ -1500,16 +1504,22 @@ __global__ void __launch_bounds__(BF_WARPS * 32, BF_PX2_OCC) blend_forward_group
         bool doneA = !insA, doneB = !insB;
         f2 T2 = bc(1.0f);
         float c0A = 0.f, c0B = 0.f, c1A = 0.f, c1B = 0.f, c2A = 0.f, c2B = 0.f;
+        f2 E[K > 0 ? K : 1][3];  // colour accumulators of the extra passes
+#pragma unroll
+        for (int k = 0; k < K; k++) { E[k][0] = bc(0.f); E[k][1] = bc(0.f); E[k][2] = bc(0.f); }
         uint32_t lastA = 0, lastB = 0;
 
         __syncwarp();
 #pragma unroll
         for (int p = 0; p < 2; p++) {
             if (p * 32 + lane < total) {
-                const GsRec* r = rec + lst[p * 32 + lane];
+                const uint32_t id = lst[p * 32 + lane];
+                const GsRec* r = rec + id;
                 cp_async16(&R.a[p][lane], &r->a);
                 cp_async16(&R.b[p][lane], &r->b);
                 cp_async16(&R.c[p][lane], &r->c);
+#pragma unroll
+                for (int k = 0; k < K; k++) cp_async16(&R.e[k][p][lane], ex.xrec + 3 * (size_t)id + k);
             }
             cp_async_commit();
         }
@@ -1552,6 +1562,8 @@ __global__ void __launch_bounds__(BF_WARPS * 32, BF_PX2_OCC) blend_forward_group
                     cp_async16(&R.a[nst][lane], &r->a);
                     cp_async16(&R.b[nst][lane], &r->b);
                     cp_async16(&R.c[nst][lane], &r->c);
+#pragma unroll
+                    for (int k = 0; k < K; k++) cp_async16(&R.e[k][nst][lane], ex.xrec + 3 * (size_t)id_next + k);
                 }
                 cp_async_commit();
                 id_next = id_next2;
@@ -1581,6 +1593,8 @@ __global__ void __launch_bounds__(BF_WARPS * 32, BF_PX2_OCC) blend_forward_group
                 sts_if(hit, &R.fa[pos], ra);
                 sts_if(hit, &R.fb[pos], make_float2(rb.x, rb.y));
                 sts_if(hit, &R.fc[pos], make_float4(rc.x, rc.y, rc.z, __uint_as_float(base + (uint32_t)lane + 1u)));
+#pragma unroll
+                for (int k = 0; k < K; k++) sts_if(hit, &R.fe[k][pos], R.e[k][sb][lane]);
                 avail += (unsigned)__popc(mask);
                 // the last batch pads the last group with null records (opacity 0 -> alpha 0)
                 const unsigned pad = final_batch ? ((unsigned)BI_G - avail % BI_G) % BI_G : 0u;
@@ -1590,6 +1604,8 @@ __global__ void __launch_bounds__(BF_WARPS * 32, BF_PX2_OCC) blend_forward_group
                 sts_if(padder, &R.fa[pp], make_float4(0.f, 0.f, 0.f, 0.f));
                 sts_if(padder, &R.fb[pp], make_float2(0.f, 0.f));
                 sts_if(padder, &R.fc[pp], make_float4(0.f, 0.f, 0.f, 0.f));
+#pragma unroll
+                for (int k = 0; k < K; k++) sts_if(padder, &R.fe[k][pp], make_float4(0.f, 0.f, 0.f, 0.f));
                 avail += pad;
                 __syncwarp();
             }
@@ -1597,6 +1613,7 @@ __global__ void __launch_bounds__(BF_WARPS * 32, BF_PX2_OCC) blend_forward_group
                 const float4* __restrict__ Fa = R.fa + head;
                 const float2* __restrict__ Fb = R.fb + head;
                 const float4* __restrict__ Fc = R.fc + head;
+                const unsigned head0 = head;
                 head = (head + BI_G == (unsigned)BI_FIFO) ? 0u : head + BI_G;
                 avail -= BI_G;
                 // ---- phase A: alpha of each instance at the two pixels of this lane (0 = the reference skips it);
@@ -1635,6 +1652,13 @@ __global__ void __launch_bounds__(BF_WARPS * 32, BF_PX2_OCC) blend_forward_group
                     c0A = __fmaf_rn(lo(w0), TA, c0A); c0B = __fmaf_rn(hi(w0), TB, c0B);
                     c1A = __fmaf_rn(lo(w1), TA, c1A); c1B = __fmaf_rn(hi(w1), TB, c1B);
                     c2A = __fmaf_rn(lo(w2), TA, c2A); c2B = __fmaf_rn(hi(w2), TB, c2B);
+#pragma unroll
+                    for (int k = 0; k < K; k++) {  // the extra passes: same alpha, same T, other colours
+                        const float4 ge = R.fe[k][head0 + u];
+                        fma2_acc(E[k][0], mul2(bc(ge.x), eff), T2);
+                        fma2_acc(E[k][1], mul2(bc(ge.y), eff), T2);
+                        fma2_acc(E[k][2], mul2(bc(ge.z), eff), T2);
+                    }
                     T2 = pk(dA ? TA : lo(tt2), dB ? TB : hi(tt2));
                     if (!dA && aA != 0.0f) lastA = __float_as_uint(gc.w);
                     if (!dB && aB != 0.0f) lastB = __float_as_uint(gc.w);
@@ -1663,14 +1687,21 @@ __global__ void __launch_bounds__(BF_WARPS * 32, BF_PX2_OCC) blend_forward_group
         const size_t pidA = (size_t)W * pyA + px, pidB = (size_t)W * pyB + px;
         if (insA) { final_T[pidA] = TA; n_contrib[pidA] = lastA; }
         if (insB) { final_T[pidB] = TB; n_contrib[pidB] = lastB; }
-        float oA[3], oB[3];
+        float oA[3 * (K + 1)], oB[3 * (K + 1)];
         oA[0] = c0A + TA * bg0; oA[1] = c1A + TA * bg1; oA[2] = c2A + TA * bg2;
         oB[0] = c0B + TB * bg0; oB[1] = c1B + TB * bg1; oB[2] = c2B + TB * bg2;
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            oA[3 * k + 3] = lo(E[k][0]) + TA * bg0; oA[3 * k + 4] = lo(E[k][1]) + TA * bg1;
+            oA[3 * k + 5] = lo(E[k][2]) + TA * bg2;
+            oB[3 * k + 3] = hi(E[k][0]) + TB * bg0; oB[3 * k + 4] = hi(E[k][1]) + TB * bg1;
+            oB[3 * k + 5] = hi(E[k][2]) + TB * bg2;
+        }
         size_t oplane = (size_t)H * W, opA = pidA, opB = pidB;
         bool wA = insA, wB = insB;
         if (tg.ds) {  // W, H even and blocks start on even pixels: a 2x2 group is inside or outside as a whole
 #pragma unroll
-            for (int c = 0; c < 3; c++) { oA[c] = box4(oA[c]); oB[c] = box4(oB[c]); }
+            for (int c = 0; c < 3 * (K + 1); c++) { oA[c] = box4(oA[c]); oB[c] = box4(oB[c]); }
             const int W2 = W >> 1;
             oplane = (size_t)W2 * (H >> 1);
             opA = (size_t)W2 * (pyA >> 1) + (px >> 1);
@@ -1682,6 +1713,12 @@ __global__ void __launch_bounds__(BF_WARPS * 32, BF_PX2_OCC) blend_forward_group
             float* oc = tg.img[k];
             if (wA) { oc[opA] = oA[0]; oc[oplane + opA] = oA[1]; oc[2 * oplane + opA] = oA[2]; }
             if (wB) { oc[opB] = oB[0]; oc[oplane + opB] = oB[1]; oc[2 * oplane + opB] = oB[2]; }
+        }
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            float* oc = ex.out[k];
+            if (wA) { oc[opA] = oA[3 * k + 3]; oc[oplane + opA] = oA[3 * k + 4]; oc[2 * oplane + opA] = oA[3 * k + 5]; }
+            if (wB) { oc[opB] = oB[3 * k + 3]; oc[oplane + opB] = oB[3 * k + 4]; oc[2 * oplane + opB] = oB[3 * k + 5]; }
         }
     }
 }
@@ -1750,20 +1787,21 @@ cudaError_t launch_blend(const GsFrame& f, const GsGeom& g, const GsBinning& b, 
     return cudaGetLastError();
 }
 
-GsPerDevice g_grouped_dev;
+GsPerDevice g_grouped_dev[4];  // per extra-pass count K: value[1] = SMs of the device
 
+template <int K>
 cudaError_t launch_blend_grouped(const GsFrame& f, const GsGeom& g, const GsBinning& b, const GsImage& im,
                                  float* out_color, uint32_t num_tiles) {
-    const size_t smem = sizeof(BiRing) * BF_WARPS;
+    const size_t smem = sizeof(BiRing<K>) * BF_WARPS;
     const int* dv = nullptr;
     {
-        cudaError_t e = g_grouped_dev.get(&dv, [smem](int dev, int* v) {
+        cudaError_t e = g_grouped_dev[K].get(&dv, [smem](int dev, int* v) {
             int sms = 0, per_sm = 0;
             cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
             if (e != cudaSuccess) return e;
-            e = cudaFuncSetAttribute(blend_forward_grouped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            e = cudaFuncSetAttribute(blend_forward_grouped_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
-            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, blend_forward_grouped_kernel, BF_WARPS * 32, smem);
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, blend_forward_grouped_kernel<K>, BF_WARPS * 32, smem);
             if (e != cudaSuccess) return e;
             v[0] = sms * (per_sm > 0 ? per_sm : 1);
             v[1] = sms;
@@ -1775,6 +1813,9 @@ cudaError_t launch_blend_grouped(const GsFrame& f, const GsGeom& g, const GsBinn
     tg.n = f.s.num_peers > 0 ? f.s.num_peers : 1;
     tg.ds = f.s.downsample == 2 ? 1 : 0;
     for (int k = 0; k < 8; k++) tg.img[k] = f.s.num_peers > 0 ? f.s.peer_out_color[k] : out_color;
+    BfExtra ex;
+    ex.xrec = g.xrec;
+    for (int k = 0; k < 3; k++) ex.out[k] = f.s.extra_out[k];
     const uint32_t units_max = num_tiles * 4u;
     // One CTA per SM (two warps per scheduler) and a per-warp unit quota that covers the upper bound of units: measured
     // best for a single frame (long walks share their scheduler with one other warp instead of three) AND with
@@ -1784,9 +1825,9 @@ cudaError_t launch_blend_grouped(const GsFrame& f, const GsGeom& g, const GsBinn
     const uint32_t share = (units_max + BF_WARPS * slots - 1) / (BF_WARPS * slots);
     const uint32_t quota = 2u * (share < 1u ? 1u : share);
     const unsigned grid = units_max < BF_WARPS * slots ? (units_max + BF_WARPS - 1) / BF_WARPS : slots;
-    blend_forward_grouped_kernel<<<grid, BF_WARPS * 32, smem, f.stream>>>(
+    blend_forward_grouped_kernel<K><<<grid, BF_WARPS * 32, smem, f.stream>>>(
         im.ranges, im.order, b.list, g.rec, f.s.width, f.s.height, f.gx, num_tiles, g.hdr, f.s.background, im.final_T,
-        im.n_contrib, tg, (int)quota);
+        im.n_contrib, tg, ex, (int)quota);
     gs_note_launch();
     return cudaGetLastError();
 }
@@ -1807,10 +1848,11 @@ cudaError_t gs_launch_blend_forward(const GsFrame& f, const GsGeom& g, const GsB
         }();
         after = env_after;
     }
+    static const int plain_k = [] { const char* e = getenv("GSPLAT_B200_BLEND_PLAIN"); return e ? atoi(e) : 0; }();
     switch (f.s.num_extra) {
-        case 1: return launch_blend<1, 0>(f, g, b, im, out_color, num_tiles, 0);
-        case 2: return launch_blend<2, 0>(f, g, b, im, out_color, num_tiles, 0);
-        case 3: return launch_blend<3, 0>(f, g, b, im, out_color, num_tiles, 0);
+        case 1: return plain_k ? launch_blend<1, 0>(f, g, b, im, out_color, num_tiles, 0) : launch_blend_grouped<1>(f, g, b, im, out_color, num_tiles);
+        case 2: return plain_k ? launch_blend<2, 0>(f, g, b, im, out_color, num_tiles, 0) : launch_blend_grouped<2>(f, g, b, im, out_color, num_tiles);
+        case 3: return plain_k ? launch_blend<3, 0>(f, g, b, im, out_color, num_tiles, 0) : launch_blend_grouped<3>(f, g, b, im, out_color, num_tiles);
         default:
             if (f.s.blend_split > 0) return launch_blend<0, 2>(f, g, b, im, out_color, num_tiles, f.s.blend_split);
             if (after > 0) return launch_blend<0, 1>(f, g, b, im, out_color, num_tiles, after);
@@ -1818,7 +1860,7 @@ cudaError_t gs_launch_blend_forward(const GsFrame& f, const GsGeom& g, const GsB
                 static const int plain = [] { const char* e = getenv("GSPLAT_B200_BLEND_PLAIN"); return e ? atoi(e) : 0; }();
                 if (plain) return launch_blend<0, 0>(f, g, b, im, out_color, num_tiles, 0);
             }
-            return launch_blend_grouped(f, g, b, im, out_color, num_tiles);
+            return launch_blend_grouped<0>(f, g, b, im, out_color, num_tiles);
     }
 }
 

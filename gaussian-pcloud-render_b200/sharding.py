@@ -40,6 +40,30 @@ def balanced_rows(row_cost: np.ndarray, world: int) -> List[Tuple[int, int]]:
     return [(int(cuts[k]), int(cuts[k + 1])) for k in range(world)]
 
 
+def rebalance_rows(rows: Sequence[Tuple[int, int]], times_ms: Sequence[float], n_rows: int) -> List[Tuple[int, int]]:
+    """Profile-guided refinement of a tile-row partition: given the time every rank took for ITS range of the same view,
+    moves the range boundaries so that every rank gets a share of the rows inversely proportional to its time per row
+    (what the cost model does not see -- the Gaussians a rank must still process because they reach into its rows from
+    the neighbouring ranges, the fixed cost of the small sort / list kernels -- is in the measured times).
+    Deterministic in its inputs, so every rank derives the same partition from the all-gathered times; ranges stay
+    contiguous, ordered and cover [0, n_rows); a rank that had no rows keeps none."""
+    world = len(rows)
+    cnt = np.array([max(0, b - a) for a, b in rows], dtype=np.float64)
+    t = np.maximum(np.asarray(times_ms, dtype=np.float64), 1e-6)
+    speed = np.where(cnt > 0, cnt / t, 0.0)              # rows per ms of each rank on its own stretch of the frame
+    if not np.any(speed > 0):
+        return [tuple(r) for r in rows]
+    # target: equal time T with rows_k = speed_k * T  ->  rows_k proportional to speed_k; move at most a quarter of a range
+    want = speed / speed.sum() * cnt.sum()
+    want = np.clip(want, 0.75 * cnt, 1.25 * cnt + 1.0)
+    want *= cnt.sum() / max(want.sum(), 1e-9)
+    cuts = np.concatenate([[0.0], np.cumsum(want)])
+    cuts = np.rint(cuts).astype(np.int64)
+    cuts[0], cuts[-1] = 0, int(n_rows)
+    cuts = np.maximum.accumulate(np.clip(cuts, 0, n_rows))
+    return [(int(cuts[k]), int(cuts[k + 1])) for k in range(world)]
+
+
 def row_cost(need_tiles: np.ndarray, inst_tiles: np.ndarray) -> np.ndarray:
     """Per tile-row cost model: blended list prefix (need_t) + a share of the binned instances + a constant."""
     return need_tiles.sum(1).astype(np.float64) + 0.25 * inst_tiles.sum(1).astype(np.float64) + 8.0

@@ -51,6 +51,22 @@ def test_balanced_rows_partition():
     assert bench.balanced_rows(np.zeros(5), 4)[-1][1] == 5
 
 
+def test_rebalance_rows_moves_rows_towards_the_faster_ranks():
+    import sharding
+    rows = [(0, 22), (22, 40), (40, 55), (55, 70), (70, 85), (85, 100), (100, 114), (114, 128)]
+    times = [0.66, 0.70, 0.72, 0.73, 0.73, 0.72, 0.70, 0.65]
+    new = sharding.rebalance_rows(rows, times, 128)
+    assert new[0][0] == 0 and new[-1][1] == 128
+    assert all(new[k][1] == new[k + 1][0] and new[k][1] >= new[k][0] for k in range(7))
+    n_old, n_new = [b - a for a, b in rows], [b - a for a, b in new]
+    assert n_new[0] >= n_old[0] and n_new[7] >= n_old[7]          # the fast edge ranks take rows ...
+    assert n_new[3] <= n_old[3] and n_new[4] <= n_old[4]          # ... from the slow middle ones
+    assert sharding.rebalance_rows(rows, [1.0] * 8, 128) == rows   # equal times per row count? equal speed x rows: unchanged
+    # an empty range stays empty, nothing is lost
+    r2 = sharding.rebalance_rows([(0, 10), (10, 10), (10, 30)], [1.0, 0.0, 1.0], 30)
+    assert r2[0][0] == 0 and r2[-1][1] == 30 and r2[1][0] == r2[1][1]
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
