@@ -278,13 +278,45 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreArgs a) {
 // ---- Shard cull (GsScene.shard_cull): which Gaussians can reach tile rows [row0, row1)? ---------------------------------
 // A Gaussian is kept unless its splat provably misses the shard: same near-plane test and the same pixel y as the
 // per-Gaussian stage (identical expressions), and an upper bound R on its screen radius ceil(3 sqrt(lambda_max)):
-//   lambda_max(Sigma') <= trace(Sigma') = a + c,   a <= |j0|^2 |W|_F^2 trace(V) + 0.3,   c likewise with j1,
-// (j0, j1 the rows of the projection Jacobian, W the view rotation, V the world covariance, trace(V) = sum_k S_k^2 |a_k|^2
-// for V = A S^2 A^T), plus a relative allowance for rounding and the reference's max(0.1, .) under the square root.
-// Reads 40 B per Gaussian instead of the 92 - 236 B of the full stage.  The three kernels (flags + counts per
-// 4096-block, scan of the block counts, ordered scatter) give the ascending candidate list: the depth sort's stable
-// tie order is the Gaussian index, so the compaction must keep it.
-__device__ __forceinline__ bool shard_candidate(const PreArgs& a, int i) {
+//   lambda_max(Sigma') <= trace(Sigma') = a + c,   a <= |j0|^2 |W|_2^2 lambda_max(V) + 0.3 <= |j0|^2 g trace(V) + 0.3,
+// c likewise with j1 (j0, j1 the rows of the projection Jacobian, W the 3x3 part of the view matrix with
+// |W|_2^2 <= g = the largest absolute row sum of W^T W -- Gershgorin; exactly 1 for a rigid view --, V the world
+// covariance, trace(V) = sum_k S_k^2 |a_k|^2 for V = A S^2 A^T), plus a relative allowance for rounding and the
+// reference's max(0.1, .) under the square root.  Reads 40 B per Gaussian instead of the 92 - 236 B of the full stage;
+// everything that depends on the camera alone is computed once per thread (CullCam).  Measured and not kept: the exact
+// radius of the full stage (cov3d_from_scale_rot + cov2d_eval) with two pixels of margin -- fewer candidates at C2
+// (cull + per-Gaussian stage of a shard 0.082 -> 0.063 ms) but 110 more instructions per Gaussian, slower where the
+// splats are small against a shard (C4: 0.245 -> 0.257 ms).
+// The three kernels (flags + counts per 4096-block, scan of the block counts, ordered scatter) give the ascending
+// candidate list: the depth sort's stable tie order is the Gaussian index, so the compaction must keep it.
+struct CullCam {
+    float v[12];   // view matrix, rows 0-2 of the column-major 4x4: v[3 c + r] = view[4 c + r]
+    float p1[4], p3[4];  // rows 1 (y) and 3 (w) of the projection matrix
+    float g;       // bound on |W|_2^2
+};
+__device__ __forceinline__ CullCam make_cull_cam(const PreArgs& a) {
+    CullCam c;
+#pragma unroll
+    for (int col = 0; col < 4; col++) {
+#pragma unroll
+        for (int r = 0; r < 3; r++) c.v[3 * col + r] = a.view[4 * col + r];
+        c.p1[col] = a.proj[4 * col + 1];
+        c.p3[col] = a.proj[4 * col + 3];
+    }
+    float g = 0.f;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {  // row i of W^T W: dot products of the columns of W
+        float rs = 0.f;
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+            rs += fabsf(c.v[3 * i] * c.v[3 * j] + c.v[3 * i + 1] * c.v[3 * j + 1] + c.v[3 * i + 2] * c.v[3 * j + 2]);
+        g = fmaxf(g, rs);
+    }
+    c.g = g * 1.0001f;
+    return c;
+}
+
+__device__ __forceinline__ bool shard_candidate(const PreArgs& a, const CullCam& cam, int i) {
     const float3 mean = make_float3(a.means[3 * (size_t)i], a.means[3 * (size_t)i + 1], a.means[3 * (size_t)i + 2]);
     // (all inputs are requested before the near-plane early-out: one round trip to memory per Gaussian)
     float tr_in[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -296,11 +328,15 @@ __device__ __forceinline__ bool shard_candidate(const PreArgs& a, int i) {
 #pragma unroll
         for (int k = 0; k < 3; k++) tr_in[4 + k] = a.scales[3 * (size_t)i + k];
     }
-    const float3 p_view = xform43(a.view, mean);
+    // view-space position and pixel y: the expressions of xform43 / xform44 / ndc_to_pix (same operand order)
+    const float3 p_view = make_float3(cam.v[0] * mean.x + cam.v[3] * mean.y + cam.v[6] * mean.z + cam.v[9],
+                                      cam.v[1] * mean.x + cam.v[4] * mean.y + cam.v[7] * mean.z + cam.v[10],
+                                      cam.v[2] * mean.x + cam.v[5] * mean.y + cam.v[8] * mean.z + cam.v[11]);
     if (p_view.z <= 0.2f) return false;
-    const float4 p_hom = xform44(a.proj, mean);
-    const float p_w = 1.0f / (p_hom.w + 0.0000001f);
-    const float py = ndc_to_pix(p_hom.y * p_w, a.H);
+    const float hy = cam.p1[0] * mean.x + cam.p1[1] * mean.y + cam.p1[2] * mean.z + cam.p1[3];
+    const float hw = cam.p3[0] * mean.x + cam.p3[1] * mean.y + cam.p3[2] * mean.z + cam.p3[3];
+    const float p_w = 1.0f / (hw + 0.0000001f);
+    const float py = ndc_to_pix(hy * p_w, a.H);
     float tr;  // trace of the world covariance
     if (a.cov3D_pre != nullptr) {
         tr = tr_in[0] + tr_in[1] + tr_in[2];
@@ -314,14 +350,11 @@ __device__ __forceinline__ bool shard_candidate(const PreArgs& a, int i) {
         tr = s0 * s0 * (a00 * a00 + a10 * a10 + a20 * a20) + s1 * s1 * (a01 * a01 + a11 * a11 + a21 * a21) +
              s2 * s2 * (a02 * a02 + a12 * a12 + a22 * a22);
     }
-    const float* vm = a.view;
-    const float wn = vm[0] * vm[0] + vm[1] * vm[1] + vm[2] * vm[2] + vm[4] * vm[4] + vm[5] * vm[5] + vm[6] * vm[6] +
-                     vm[8] * vm[8] + vm[9] * vm[9] + vm[10] * vm[10];
     const float iz = 1.0f / p_view.z;
     const float ux = fminf(1.3f * a.tanx, fabsf(p_view.x * iz)), uy = fminf(1.3f * a.tany, fabsf(p_view.y * iz));
     const float j0 = (a.fx * iz) * (a.fx * iz) * (1.f + ux * ux), j1 = (a.fy * iz) * (a.fy * iz) * (1.f + uy * uy);
-    const float lam = (j0 + j1) * wn * tr * 1.01f + 1.0f;  // >= a + c + 0.32 with room for rounding
-    if (!(lam < 1.0e12f)) return true;                     // overflow / NaN: let the full stage decide
+    const float lam = (j0 + j1) * cam.g * tr * 1.01f + 1.0f;  // >= a + c + 0.32 with room for rounding
+    if (!(lam < 1.0e12f)) return true;                        // overflow / NaN: let the full stage decide
     const float R = ceilf(3.f * sqrtf(lam)) + 1.f;
     const int y0 = min(a.gy, max(0, (int)((py - R) / GS_TILE)));
     const int y1 = min(a.gy, max(0, (int)((py + R + GS_TILE - 1) / GS_TILE)));
@@ -334,10 +367,11 @@ __global__ void __launch_bounds__(256) shard_flag_kernel(const PreArgs a, uint32
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t base = (size_t)blockIdx.x * GS_CULL_CHUNK;
     unsigned mine = 0;
+    const CullCam cam = make_cull_cam(a);
 #pragma unroll 4
     for (int r = 0; r < GS_CULL_CHUNK / 256; r++) {
         const size_t i = base + (size_t)r * 256 + threadIdx.x;
-        const bool keep = i < (size_t)a.P && shard_candidate(a, (int)i);
+        const bool keep = i < (size_t)a.P && shard_candidate(a, cam, (int)i);
         const unsigned m = __ballot_sync(GS_FULL, keep);
         if (lane == 0) {
             cmask[(base >> 5) + (size_t)r * 8 + warp] = m;
