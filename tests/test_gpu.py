@@ -954,6 +954,49 @@ print('TEAM OK' if ok else 'TEAM MISMATCH')
     assert "TEAM OK" in out.stdout, out.stdout[-1500:] + out.stderr[-1500:]
 
 
+def test_split_walk_mode_stays_within_the_pixel_tolerance():
+    """GsScene.blend_split (opt-in latency mode, NOT bit-identical): long walks cut into segments merged associatively.
+    Pixels within the north star's 1e-4 of the exact frame (observed ~1.6e-6), final T within 1e-5, and the contributor
+    counts of (almost) every pixel equal, so that gs_backward stays consistent.  Child process with a time limit."""
+    _dev()
+    import subprocess
+    import sys
+    from conftest import ROOT
+    code = r"""
+import sys, torch
+sys.path.insert(0, %r); sys.path.insert(0, %r + '/gaussian-pcloud-render_b200')
+import scenes
+from diff_gaussian_rasterization import _C
+from renderer import FrameRenderer
+dev = torch.device('cuda:0')
+cl = scenes.human_cloud(400000, scale_factor=448.0, seed=3)
+W, H = 1280, 720
+worst = (0.0, 0.0, 0.0)
+for k in (2, 7):
+    v = scenes.make_view(scenes.orbit_c2w(12)[k], W, H)
+    ref = FrameRenderer(cl, W, H, [1, 1, 1], dev, capacity=12_000_000)
+    vd = ref.upload_view(v)
+    a = ref.render(vd).clone()
+    sc = ref._scene(vd, None)
+    ta = _C.fetch('final_T', sc, ref.geom, ref.binning, ref.img, ref.capacity)
+    na = _C.fetch('n_contrib', sc, ref.geom, ref.binning, ref.img, ref.capacity)
+    for split in (8, 64):
+        fr = FrameRenderer(cl, W, H, [1, 1, 1], dev, capacity=12_000_000, blend_split=split)
+        b = fr.render(vd)
+        sc = fr._scene(vd, None)
+        tb = _C.fetch('final_T', sc, fr.geom, fr.binning, fr.img, fr.capacity)
+        nb = _C.fetch('n_contrib', sc, fr.geom, fr.binning, fr.img, fr.capacity)
+        worst = (max(worst[0], float((a - b).abs().max())), max(worst[1], float((ta - tb).abs().max())),
+                 max(worst[2], float((na != nb).float().mean())))
+print('SPLIT', worst[0], worst[1], worst[2])
+""" % (ROOT, ROOT)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=240)
+    line = [ln for ln in out.stdout.splitlines() if ln.startswith("SPLIT")]
+    assert line, out.stdout[-1500:] + out.stderr[-1500:]
+    dpix, dT, dn = (float(x) for x in line[0].split()[1:])
+    assert dpix <= PIX_TOL and dT <= 1e-5 and dn <= 1e-5, line[0]
+
+
 def test_two_devices_in_one_process():
     """The library keeps its launcher state (dynamic shared-memory opt-ins, grid sizes) per device: one process renders
     the same frame, forward and backward, on cuda:0 and then on cuda:1.  Needs two GPUs."""
