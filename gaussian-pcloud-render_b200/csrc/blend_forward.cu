@@ -1,7 +1,11 @@
 // blend_forward.cu -- per-tile front-to-back alpha compositing (K6; replaces renderCUDA,
 // dgr/cuda_rasterizer/forward.cu:264-377).
 //
-// Work decomposition (B200: 148 SMs, one persistent grid of 3 CTAs x 8 warps per SM):
+// The kernel that runs is blend_forward_grouped_kernel<K> (second half of this file; K = extra colour passes of the
+// same walk); blend_forward_px2_kernel is the round-1 loop (one instance per iteration) that it grew out of -- kept for
+// the opt-in latency experiments built on it (TEAM = 1: exact CTA teams, GsScene.team_after; TEAM = 2: associative split
+// walks, GsScene.blend_split) and as the A/B partner of the grouped loop (developer switch GSPLAT_B200_BLEND_PLAIN=1).
+// Work decomposition, common to both (B200: 148 SMs):
 //   * the unit of work is ONE WARP blending an 8x8 pixel block (1/4 of a 16x16 tile) against the tile's
 //     depth-ordered instance list, two pixels per lane; warps never synchronise with each other (the reference's
 //     per-batch __syncthreads was its top stall reason and its CTA-per-tile grid left the average SM idle 60 % of
@@ -10,7 +14,7 @@
 //     time-first); empty tiles (85 % of a THuman frame) are not blended at all: one warp fills a whole tile with
 //     the background;
 //   * each lane gathers one packed 48-B record per step straight into a per-warp shared-memory ring with cp.async
-//     (3 x 16 B, no register staging; the table is L2 resident), two batches ahead, list indices three ahead;
+//     (3 x 16 B, no register staging; the table is L2 resident), two batches ahead, list indices further ahead;
 //   * before blending, every lane tests ITS Gaussian against the warp's pixel block with an exact box-maximum of
 //     the (concave) exponent; instances whose alpha is provably < 1/255 on the whole block are dropped by a ballot
 //     and never enter the per-pixel loop (the reference skips those per pixel through `alpha < 1/255`, so the image
