@@ -13,7 +13,7 @@ instance lists; the per-frame input set, 160 MB of Gaussian attributes, exceeds 
           drop-in call are reported next to it).  N > 1: the cloud crosses PCIe once per step and NODE (each rank
           uploads 1/N of it, one NVLink all-gather per array completes it on every GPU).
   single_frame_ms / dropin_serial_fps : one frame at a time (latency), the drop-in module called serially.
-  extra_workloads : C3 (forward + backward, with a roofline record of the blend-backward kernel) and C4 (5M random
+  extra_workloads : C1 (BASELINE config 1 as a GPU frame), C3 (forward + backward, with a roofline record of the blend-backward kernel) and C4 (5M random
           Gaussians, 2048^2) measured in the same run, both arms, so the driver's two lines give their ratios too.
   tiles (N > 1) : the north star's split -- ONE frame sharded by tile rows over the N GPUs, image assembled on every
           GPU by peer stores from the blend epilogue (or one NCCL all-gather); asserted bit-identical to the
@@ -695,6 +695,8 @@ def run_b200(args, rank, world):
         extra = {"C3": c3_leg_b200(cloud, views, w, dev, need_sum, n=max(8, min(args.steps, 24)))}
         torch.cuda.empty_cache()
         extra["C4"] = frames_leg_b200("C4", dev)
+        torch.cuda.empty_cache()
+        extra["C1"] = frames_leg_b200("C1", dev, streams=6, steps=48)
 
     out = None
     if rank == 0:
@@ -880,6 +882,8 @@ def run_reference(args, rank, world):
         del ref
         torch.cuda.empty_cache()
         extra["C4"] = frames_leg(ReferenceCUDA(), "C4", 16)
+        torch.cuda.empty_cache()
+        extra["C1"] = frames_leg(ReferenceCUDA(), "C1", 24)
     return {"impl": "reference", "metric": "frames/sec at 1080p, 800K Gaussians" if args.workload == "C2" else f"frames/sec ({args.workload})",
             "value": value, "unit": "frames/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -67,6 +67,24 @@ def test_rebalance_rows_moves_rows_towards_the_faster_ranks():
     assert r2[0][0] == 0 and r2[-1][1] == 30 and r2[1][0] == r2[1][1]
 
 
+def test_host_block_is_one_buffer_with_aligned_views():
+    """renderer.host_block: the five attribute arrays become views into ONE float32 block (one host->device copy per
+    step in FramePipeline.enqueue_host); values unchanged, every array starts at a multiple of 64 floats."""
+    import scenes
+    from renderer import host_block, FramePipeline
+    cl = scenes.tiny_cloud(1000, seed=3, sh_degree=1)
+    blk = host_block(cl, pin=False)
+    flat = blk["_flat"]
+    assert flat.dtype == torch.float32 and flat.dim() == 1
+    end = 0
+    for (n, off, shp), name in zip(blk["_layout"], FramePipeline._ATTRS):
+        assert n == name and off % 64 == 0 and off >= end and tuple(blk[n].shape) == tuple(cl[n].shape) == shp
+        assert torch.equal(blk[n], cl[n].float())
+        assert blk[n].data_ptr() == flat.data_ptr() + 4 * off          # a view, not a copy
+        end = off + blk[n].numel()
+    assert end <= flat.numel()
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
