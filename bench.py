@@ -710,7 +710,7 @@ def run_b200(args, rank, world):
                            ("blend epilogue stores into all ranks' images over NVLink + one barrier per frame"
                             if peer is not None else "one NCCL all-gather per frame") if tiles_mode
                            else f"view-parallel x{world}: rank r renders views r, r+{world}, ... (no collective)"),
-                          "l2_policy": "inputs larger than L2 (160 MB of attributes per frame; consecutive steps render different views)",
+                          "l2_policy": "working set larger than L2: every step streams the resident cloud (74 MB at C2: the attribute arrays with the (degree+1)^2 SH coefficients the rasterizer reads) and ~230 MB of private per-lane workspace (records, sort buffers, row items, lists, image), six lanes; consecutive steps render different views",
                           "frames_in_flight": in_flight,
                           "mean_num_rendered": float(np.mean(rendered))},
                "single_frame_ms": single_frame_ms, "dropin_serial_fps": serial,
@@ -889,7 +889,7 @@ def run_reference(args, rank, world):
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "device": "cuda:0 (the reference's implementation of this path is CUDA-only)",
             "config": {"workload": f"{args.workload}: {w['desc']}", "parallelism": "single GPU", "frames_in_flight": 1,
-                       "l2_policy": "inputs larger than L2 (160 MB of attributes per frame; consecutive steps render different views)",
+                       "l2_policy": "working set larger than L2: every step streams the resident cloud (74 MB at C2: the attribute arrays with the (degree+1)^2 SH coefficients the rasterizer reads) and ~230 MB of private per-lane workspace (records, sort buffers, row items, lists, image), six lanes; consecutive steps render different views",
                        "reference": "unmodified diff-gaussian-rasterization (forward.cu/backward.cu/rasterizer_impl.cu + CUB) compiled for sm_100a, driven through oracle/ref_shim.cu"},
             "single_frame_ms": ms / args.steps, "dropin_serial_fps": e2e_steps / (e2e_ms / 1e3),
             "e2e": {"value": e2e_steps / (e2e_ms / 1e3), "unit": "frames/s",

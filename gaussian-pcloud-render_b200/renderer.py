@@ -45,8 +45,15 @@ class FrameRenderer:
         else:
             f32 = lambda t: t.to(self.dev, torch.float32).contiguous()
             self.means3D, self.opacities = f32(cloud["means3D"]), f32(cloud["opacities"])
-            self.scales, self.rotations, self.shs = f32(cloud["scales"]), f32(cloud["rotations"]), f32(cloud["shs"])
+            self.scales, self.rotations = f32(cloud["scales"]), f32(cloud["rotations"])
             self.sh_degree = int(cloud["sh_degree"])
+            # resident layout: only the (degree + 1)^2 coefficients the rasterizer reads are kept on the device -- the
+            # reference's pcrender clouds carry 13 coefficients per point and render with degree 1, and at DRAM
+            # granularity the per-Gaussian stage would otherwise pull in the 9 unread ones of every row too
+            # (160 MB instead of 83 MB per frame at 800 K points).  Same frame bit for bit.
+            sh = cloud["shs"]
+            need = (self.sh_degree + 1) ** 2
+            self.shs = f32(sh[:, :need] if sh.shape[1] > need else sh)
         self.P = int(self.means3D.shape[0])
         self.bg = torch.as_tensor(bg, dtype=torch.float32).to(self.dev)
         self.headroom = headroom
@@ -347,16 +354,18 @@ class FramePipeline:
 
     _ATTRS = ("means3D", "opacities", "scales", "rotations", "shs")
 
-    def _own_inputs(self, ln, rows: int) -> None:
-        """Private device copies of the Gaussian attributes for one lane (`rows` >= P rows each; the renderer reads
-        the first P)."""
-        if getattr(ln, "_in_rows", 0) == rows:
+    def _own_inputs(self, ln, rows: int, host_cloud: dict) -> None:
+        """Private device copies of the Gaussian attributes for one lane, shaped like the host arrays that will be copied
+        into them (`rows` >= P rows each; the renderer reads the first P)."""
+        key = (rows,) + tuple(tuple(host_cloud[n].shape[1:]) for n in self._ATTRS)
+        if getattr(ln, "_in_key", None) == key:
             return
         ln._in = {}
         for n in self._ATTRS:
-            t = getattr(ln, n)
-            ln._in[n] = torch.empty((rows,) + tuple(t.shape[1:]), dtype=torch.float32, device=self.dev)
+            ln._in[n] = torch.empty((rows,) + tuple(host_cloud[n].shape[1:]), dtype=torch.float32, device=self.dev)
             setattr(ln, n, ln._in[n][: ln.P])
+        ln._in_key = key
+        ln._flat_key = None
         ln._view_dev = (torch.empty(4, 4, device=self.dev), torch.empty(4, 4, device=self.dev),
                         torch.empty(3, device=self.dev))
         ln._in_rows = rows
@@ -375,7 +384,7 @@ class FramePipeline:
                 setattr(ln, n, ln._flat[o:o + cnt].view(shp))
             ln._view_dev = (torch.empty(4, 4, device=self.dev), torch.empty(4, 4, device=self.dev),
                             torch.empty(3, device=self.dev))
-            ln._flat_key, ln._in_rows, ln._consumed = (numel, world), 0, None
+            ln._flat_key, ln._in_key, ln._consumed = (numel, world), None, None
         return S
 
     def enqueue_host(self, host_cloud: dict, host_view, tanfov, out_host: torch.Tensor, slot: int = 0,
@@ -425,7 +434,7 @@ class FramePipeline:
                 out_host.copy_(out, non_blocking=True)
             return k
         if group is None:
-            self._own_inputs(ln, ln.P)
+            self._own_inputs(ln, ln.P, host_cloud)
             with torch.cuda.stream(self.streams[k]):
                 for n in self._ATTRS:
                     getattr(ln, n).copy_(host_cloud[n], non_blocking=True)
@@ -437,7 +446,7 @@ class FramePipeline:
         import torch.distributed as dist
         world, rank = dist.get_world_size(group), dist.get_rank(group)
         S = (ln.P + world - 1) // world
-        self._own_inputs(ln, S * world)
+        self._own_inputs(ln, S * world, host_cloud)
         if not hasattr(self, "_feed"):  # all collectives of this pipeline are issued from ONE stream, in step order
             self._feed = torch.cuda.Stream(self.dev)
         a, b = min(ln.P, rank * S), min(ln.P, (rank + 1) * S)
