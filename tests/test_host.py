@@ -85,6 +85,54 @@ def test_host_block_is_one_buffer_with_aligned_views():
     assert end <= flat.numel()
 
 
+def test_grouped_recurrence_equals_the_reference_recurrence():
+    """The grouped hit loop of the blend kernel applies alpha values in list order with the recurrence
+    tt = T * (done ? 1 : 1 - a);  done' = done or tt < 1e-4;  C += (c * (done' ? 0 : a)) * T;  T = done' ? T : tt
+    where a = 0 for an instance the reference skips at this pixel (alpha < 1/255 or power > 0).  This is the reference's loop
+    (forward.cu:336-366: skip, test_T = T (1 - alpha), stop test, C += c alpha T, T = test_T, last contributor) with the
+    branches turned into selects; checked here operation for operation in float32 on random alpha streams, including
+    pixels that stop and streams with skipped instances (fused multiply-adds are emulated the same way on both sides)."""
+    rng = np.random.default_rng(11)
+    f32 = np.float32
+    for trial in range(200):
+        n = int(rng.integers(1, 400))
+        alpha = rng.uniform(0.0, 0.99, n).astype(np.float32) * (rng.random(n) < 0.8)
+        alpha[rng.random(n) < 0.2] = f32(0.001)               # below 1/255: skipped
+        power_pos = rng.random(n) < 0.05                      # "power > 0": skipped
+        col = rng.random((n, 3)).astype(np.float32)
+        # --- the reference's loop
+        T, C, last, done = f32(1.0), np.zeros(3, np.float32), 0, False
+        for i in range(n):
+            if done:
+                break
+            a = alpha[i]
+            if power_pos[i] or a < f32(1.0 / 255.0):
+                continue
+            test_T = f32(T * f32(f32(1.0) - a))
+            if test_T < f32(0.0001):
+                done = True
+                continue
+            for ch in range(3):
+                C[ch] = f32(f32(f32(col[i, ch] * a) * T) + C[ch])
+            T = test_T
+            last = i + 1
+        # --- the grouped formulation (phase A: a = 0 where skipped; phase B: selects)
+        T2, C2, last2, done2 = f32(1.0), np.zeros(3, np.float32), 0, False
+        for i in range(n):
+            a = f32(0.0) if (power_pos[i] or alpha[i] < f32(1.0 / 255.0)) else alpha[i]
+            om = f32(f32(1.0) - a)
+            tt = f32(T2 * (f32(1.0) if done2 else om))
+            d = done2 or bool(tt < f32(0.0001))
+            eff = f32(0.0) if d else a
+            for ch in range(3):
+                C2[ch] = f32(f32(f32(col[i, ch] * eff) * T2) + C2[ch])
+            T2 = T2 if d else tt
+            if (not d) and a != f32(0.0):
+                last2 = i + 1
+            done2 = d
+        assert T.tobytes() == T2.tobytes() and C.tobytes() == C2.tobytes() and last == last2 and done == done2, trial
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
