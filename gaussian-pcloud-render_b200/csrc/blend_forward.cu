@@ -157,7 +157,9 @@ struct BfExtra {
     float* out[3];
 };
 
+#ifndef BF_CHECK
 #define BF_CHECK 16  // batches between two looks at which pixels of the block are still live
+#endif
 
 // Output images of the epilogue: this rank's out_color, or (tile-row sharding with peer stores) the images of all
 // ranks, addressed through NVLink peer mappings -- the blend kernel assembles the frame on every GPU itself.
